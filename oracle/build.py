@@ -1,0 +1,81 @@
+"""TEST INFRASTRUCTURE ONLY: build recipe for the CPU oracle and the compiled reference.
+
+* ``build_oracle()`` compiles ``oracle/whvi_oracle.c`` (the C restatement) with gcc
+  into ``oracle/_build/libwhvi_oracle.so``.
+* ``build_ref()`` compiles the reference's own C++ CPU FWHT **from the sources where
+  they lie** (``/root/reference/src/fwht/cpp/fwht.cpp``, unmodified, never copied into
+  this repo) with a direct ``g++`` command line against the installed torch headers,
+  into ``oracle/_ref/fwht_cpp.so``.  That directory is git-ignored but travels to the
+  GPU box with ``gpurun``.  It is only attempted when ``/root/reference`` exists (this
+  container); the GPU box uses the prebuilt file.
+
+Run ``python oracle/build.py`` to build both.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import sysconfig
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+BUILD_DIR = HERE / "_build"
+REF_DIR = HERE / "_ref"
+ORACLE_SO = BUILD_DIR / "libwhvi_oracle.so"
+REF_SO = REF_DIR / "fwht_cpp.so"
+REF_SRC = Path("/root/reference/src/fwht/cpp/fwht.cpp")
+
+
+def _newer(target: Path, *sources: Path) -> bool:
+    if not target.exists():
+        return False
+    t = target.stat().st_mtime
+    return all(s.exists() and s.stat().st_mtime <= t for s in sources)
+
+
+def build_oracle(force: bool = False) -> Path:
+    src = HERE / "whvi_oracle.c"
+    hdr = HERE / "whvi_oracle_impl.h"
+    if not force and _newer(ORACLE_SO, src, hdr):
+        return ORACLE_SO
+    BUILD_DIR.mkdir(exist_ok=True)
+    # no -march=native: the .so travels to the GPU box, whose host CPU may differ
+    cmd = ["gcc", "-O3", "-fopenmp", "-shared", "-fPIC", "-o", str(ORACLE_SO), str(src), "-lm"]
+    subprocess.run(cmd, check=True, cwd=str(HERE))
+    return ORACLE_SO
+
+
+def build_ref(force: bool = False) -> Path | None:
+    """Compile the unmodified reference fwht.cpp into oracle/_ref/fwht_cpp.so."""
+    if not REF_SRC.exists():
+        return REF_SO if REF_SO.exists() else None
+    if not force and _newer(REF_SO, REF_SRC):
+        return REF_SO
+    import torch
+    from torch.utils import cpp_extension
+
+    REF_DIR.mkdir(exist_ok=True)
+    torch_lib = Path(torch.__file__).resolve().parent / "lib"
+    inc = [f"-I{p}" for p in cpp_extension.include_paths()]
+    inc.append(f"-I{sysconfig.get_paths()['include']}")
+    cmd = [
+        "g++", "-O2", "-std=c++17", "-shared", "-fPIC",
+        "-DTORCH_EXTENSION_NAME=fwht_cpp", "-DTORCH_API_INCLUDE_EXTENSION_H",
+        f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+        *inc, str(REF_SRC), "-o", str(REF_SO),
+        f"-L{torch_lib}", "-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python",
+        f"-Wl,-rpath,{torch_lib}",
+    ]
+    subprocess.run(cmd, check=True)
+    return REF_SO
+
+
+def main() -> int:
+    print("oracle:", build_oracle(force="--force" in sys.argv))
+    print("reference fwht_cpp:", build_ref(force="--force" in sys.argv))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

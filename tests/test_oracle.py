@@ -1,0 +1,144 @@
+"""CPU: pin the oracle (oracle/) to the reference's own known answers and to golden
+fixtures produced by running the reference itself (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from conftest import rel_err
+
+
+# ---- FWHT ------------------------------------------------------------------------------
+def test_fwht_known_answers(golden):
+    g = golden("fwht")  # test/walsh.py:12-20
+    for dt in (np.float32, np.float64):
+        out = O.fwht(g["kat_in"].astype(dt))
+        assert np.array_equal(out, g["kat_out_expected"].astype(dt))
+    assert np.allclose(g["kat_out_cpp"], g["kat_out_expected"], atol=1e-5)
+
+
+@pytest.mark.parametrize("D", [4, 32, 64, 1024, 4096])
+def test_fwht_matches_reference_cpp_and_python(golden, D):
+    g = golden("fwht")
+    a = g[f"in_{D}"]
+    out = O.fwht(a)
+    # same butterfly order as src/fwht/cpp/fwht.cpp:8-18 => bit-identical fp32
+    assert np.array_equal(out, g[f"cpp_{D}"])
+    assert rel_err(out, g[f"py_{D}"]) < 1e-5
+    if D <= 1024:
+        assert np.allclose(out, g[f"matmul_{D}"], atol=1e-3)
+        assert rel_err(O.fwht(a.astype(np.float64)), g[f"dense64_{D}"]) < 1e-12
+        assert rel_err(out, g[f"dense64_{D}"]) < 1e-5
+
+
+@pytest.mark.parametrize("D", [1, 2, 8, 32])
+def test_numpy_restatements_agree(D):
+    rng = np.random.default_rng(D)
+    a = rng.standard_normal((5, D))
+    assert np.allclose(O.fwht(a), O.fwht_dense(a), atol=1e-12)
+    assert np.allclose(O.fwht(a), O.fwht_cat(a), atol=1e-12)
+    H = O.build_H(D)
+    assert np.array_equal(H @ H, D * np.eye(D))
+
+
+def test_fwht_involution_large():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((3, 1 << 15)).astype(np.float32)
+    back = O.fwht(O.fwht(a)) / (1 << 15)
+    assert rel_err(back, a) < 1e-5
+
+
+# ---- KL / MNLL --------------------------------------------------------------------------
+def test_kl_matches_reference(golden):
+    g = golden("kl")
+    for i in range(4):
+        D, lam = int(g[f"D_{i}"]), float(g[f"lam_{i}"])
+        v, dmu, drho = O.kl(g[f"mu_{i}"].astype(np.float64), g[f"rho_{i}"].astype(np.float64), lam, 0, grads=True)
+        assert abs(v - float(g[f"kl_{i}"])) <= 2e-5 * max(1.0, abs(v))
+        assert rel_err(dmu, g[f"dmu_{i}"]) < 1e-5
+        assert rel_err(drho, g[f"drho_{i}"]) < 1e-5
+        assert D == g[f"mu_{i}"].shape[0]
+    # the reference's formula equals torch's MVN(mu, diag(sd)) KL (test/utils.py:22-34)
+    assert np.allclose(g["gen_kl"], g["gen_kl_torch"])
+
+
+def test_mnll_matches_reference(golden):
+    g = golden("mnll")
+    assert abs(O.mnll(g["fixed_y"], g["fixed_yhat"], 1.0, 12) - float(g["fixed_mnll"])) < 1e-4
+    assert abs(O.mnll(g["rand_y"], g["rand_yhat"], 15.21, 116) - float(g["rand_mnll"])) < 1e-3
+    assert abs(O.mnll(g["multi_y"], g["multi_yhat"], 0.7, 40) - float(g["multi_mnll"])) < 1e-3
+
+
+# ---- reference-as-written layer -------------------------------------------------------
+def test_ref_as_written_square(golden):
+    g = golden("layers")
+    name = "square16"
+    x = g[f"{name}.x"].astype(np.float64)
+    P = {k: g[f"{name}.param.weight_submodule.{k}"].astype(np.float64) for k in ("s1", "s2", "g_mu", "g_rho")}
+    assert int(g[f"{name}.n_eps"]) == 1
+    eps = g[f"{name}.eps0"].astype(np.float64)
+    sig = O.softplus(P["g_rho"])
+    y = O.ref_sample_lrt(x, P["g_mu"], sig * eps, P["s1"], P["s2"])
+    assert rel_err(y, g[f"{name}.y"]) < 1e-5
+    # as written, W collapses to D*diag(s1*g*s2)
+    D = 16
+    closed = x * (D * P["s1"] * (P["g_mu"] + sig * eps) * P["s2"])
+    assert rel_err(closed, g[f"{name}.y"]) < 1e-5
+    W = O.ref_w_bar(P["g_mu"], P["s1"], P["s2"])
+    assert np.allclose(W, np.diag(D * P["s1"] * P["g_mu"] * P["s2"]), atol=1e-12)
+
+
+# ---- PAPER layer -------------------------------------------------------------------------
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_paper_layer_matches_dense_autograd(golden, idx):
+    g = golden("paper")
+    x, s1, s2, mu, rho, eps, dy = (g[f"{k}_{idx}"] for k in ("x", "s1", "s2", "mu", "rho", "eps", "dy"))
+    gg = O.reparam(mu, rho, eps)
+    assert rel_err(gg, g[f"g_{idx}"]) < 1e-12
+    y = O.layer_fwd(x, gg, s1, s2)
+    assert rel_err(y, g[f"y_{idx}"]) < 1e-11
+    dx, dg, ds1, ds2 = O.layer_bwd(x, dy, gg, s1, s2)
+    assert rel_err(dx, g[f"dx_{idx}"]) < 1e-11
+    assert rel_err(dg, g[f"dg_{idx}"]) < 1e-11
+    assert rel_err(ds1, g[f"ds1_{idx}"]) < 1e-11
+    assert rel_err(ds2, g[f"ds2_{idx}"]) < 1e-11
+    dmu, drho = O.reparam_bwd(rho, eps, dg)
+    assert rel_err(dmu, g[f"dmu_{idx}"]) < 1e-11
+    assert rel_err(drho, g[f"drho_{idx}"]) < 1e-11
+    # fp32 oracle (the CPU baseline flavour) stays within the layer tolerance
+    y32 = O.layer_fwd(x.astype(np.float32), gg.astype(np.float32), s1.astype(np.float32), s2.astype(np.float32))
+    assert rel_err(y32, g[f"y_{idx}"]) < 1e-4
+
+
+def test_paper_dense_weight_and_column():
+    rng = np.random.default_rng(5)
+    D = 32
+    g_, s1, s2 = rng.standard_normal(D), rng.standard_normal(D), rng.standard_normal(D)
+    H = O.build_H(D)
+    W = np.diag(s1) @ H @ np.diag(g_) @ H @ np.diag(s2)
+    assert np.allclose(O.paper_weight(g_, s1, s2), W, atol=1e-10)
+    assert np.allclose(O.column_weight_paper(g_, s1, s2, 20), W.reshape(-1)[:20], atol=1e-10)
+    x = rng.standard_normal((3, D))
+    assert np.allclose(O.layer_fwd(x, g_[None], s1, s2)[0], x @ W.T, atol=1e-9)
+
+
+def test_shared_x_and_bias():
+    rng = np.random.default_rng(6)
+    S, B, D = 3, 4, 16
+    x = rng.standard_normal((B, D))
+    g_, s1, s2, bias = rng.standard_normal((S, D)), rng.standard_normal(D), rng.standard_normal(D), rng.standard_normal(D)
+    y_shared = O.layer_fwd(x, g_, s1, s2, bias)
+    y_full = O.layer_fwd(np.broadcast_to(x, (S, B, D)).copy(), g_, s1, s2, bias)
+    assert np.array_equal(y_shared, y_full)
+    dy = rng.standard_normal((S, B, D))
+    dx_s, dg_s, ds1_s, ds2_s, db = O.layer_bwd(x, dy, g_, s1, s2, want_dbias=True)
+    dx_f, dg_f, ds1_f, ds2_f = O.layer_bwd(np.broadcast_to(x, (S, B, D)).copy(), dy, g_, s1, s2)
+    assert np.allclose(dx_s, dx_f.sum(0)) and np.allclose(dg_s, dg_f) and np.allclose(ds1_s, ds1_f)
+    assert np.allclose(db, dy.sum((0, 1)))
+
+
+def test_stacked_dims_match_reference_probe():
+    # SURVEY Appendix C probe of WHVIStackedMatrix.setup_dimensions
+    assert O.stacked_dims(3, 16) == (4, 16, 1, 4)
+    assert O.stacked_dims(13, 128) == (16, 128, 3, 8)
+    assert O.stacked_dims(13, 32) == (16, 32, 3, 2)
+    assert O.stacked_dims(8, 20) == (8, 24, 0, 3)
