@@ -1,0 +1,143 @@
+"""GPU parity of kernel (1), the batched FWHT, through the C ABI (whvi_fwht_f32) and the
+FWHTFunction frontend, against the CPU oracle and the reference-generated goldens.
+Tolerance (north_star / SURVEY 8c): max|y - y64| / max|y64| <= 1e-5, plus the atol
+values of the reference's own tests (test/walsh.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FWHT_TOL = 1e-5
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def run(a: np.ndarray) -> np.ndarray:
+    from whvi_b200 import FWHTFunction
+    x = torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+    y = FWHTFunction.apply(x)
+    torch.cuda.synchronize()
+    assert torch.equal(x.cpu(), torch.from_numpy(np.ascontiguousarray(a))), "input was modified"
+    return y.cpu().numpy()
+
+
+def test_known_answer_vectors(golden):
+    g = golden("fwht")  # test/walsh.py:12-20
+    out = run(g["kat_in"])
+    assert np.allclose(out, g["kat_out_expected"], atol=1e-5)
+    assert np.array_equal(out, g["kat_out_expected"])
+
+
+def test_reference_cuda_tests_restated(golden):
+    # test/walsh.py:61-69 (D=4, batch 2, default allclose) and :71-79 (D=1024, batch 19, atol 1e-4)
+    g = golden("fwht")
+    a = g["in_4"]
+    assert np.allclose(run(a), O.fwht_dense(a.astype(np.float64)), rtol=1e-5, atol=1e-8)
+    a = g["in_1024"]
+    assert np.allclose(run(a), g["dense64_1024"], atol=1e-4)
+
+
+@pytest.mark.parametrize("D", [4, 32, 64, 1024, 4096])
+def test_matches_reference_generated_goldens(golden, D):
+    g = golden("fwht")
+    out = run(g[f"in_{D}"])
+    assert rel_err(out, g[f"cpp_{D}"]) < FWHT_TOL  # reference C++ CPU FWHT
+    assert rel_err(out, g[f"py_{D}"]) < FWHT_TOL   # reference python FWHT
+
+
+@pytest.mark.parametrize("k", list(range(0, 16)))
+@pytest.mark.parametrize("rows", [1, 3, 19])
+def test_all_sizes_ragged_rows(k, rows):
+    D = 1 << k
+    rng = np.random.default_rng(1000 * k + rows)
+    a = rng.standard_normal((rows, D)).astype(np.float32)
+    out = run(a)
+    ref = O.fwht(a.astype(np.float64))
+    assert rel_err(out, ref) < FWHT_TOL
+
+
+@pytest.mark.parametrize("D,rows", [(64, 16 * 8 + 1), (64, 16 * 8 - 1), (128, 8 * 8 * 3 + 5), (1024, 17), (2048, 9),
+                                    (8, 128 * 8 + 3), (16, 1000), (4096, 7), (8192, 5), (16384, 3), (32768, 2)])
+def test_tile_boundaries(D, rows):
+    rng = np.random.default_rng(D + rows)
+    a = rng.standard_normal((rows, D)).astype(np.float32)
+    assert rel_err(run(a), O.fwht(a.astype(np.float64))) < FWHT_TOL
+
+
+def test_empty_and_in_place():
+    from whvi_b200 import FWHTFunction, fwht_
+    e = FWHTFunction.apply(torch.empty(0, 64, device=dev()))
+    assert e.shape == (0, 64)
+    x = torch.randn(37, 512, device=dev())
+    ref = O.fwht(x.cpu().numpy().astype(np.float64))
+    fwht_(x, out=x)
+    torch.cuda.synchronize()
+    assert rel_err(x.cpu().numpy(), ref) < FWHT_TOL
+
+
+def test_non_contiguous_and_errors():
+    from whvi_b200 import FWHTFunction
+    x = torch.randn(256, 40, device=dev()).t()  # (40, 256) non-contiguous
+    ref = O.fwht(x.cpu().numpy().astype(np.float64))
+    assert rel_err(FWHTFunction.apply(x).cpu().numpy(), ref) < FWHT_TOL
+    with pytest.raises(RuntimeError, match="two-dimensional"):
+        FWHTFunction.apply(torch.randn(2, 3, 4, device=dev()))
+    with pytest.raises(RuntimeError, match="power of 2"):
+        FWHTFunction.apply(torch.randn(2, 12, device=dev()))
+    with pytest.raises(RuntimeError, match="exceeds"):
+        FWHTFunction.apply(torch.randn(1, 1 << 16, device=dev()))
+
+
+def test_autograd_backward_is_the_transform():
+    from whvi_b200 import FWHT
+    x = torch.randn(11, 256, device=dev(), requires_grad=True)
+    dy = torch.randn(11, 256, device=dev())
+    y = FWHT()(x)
+    y.backward(dy)
+    ref = O.fwht(dy.cpu().numpy().astype(np.float64))
+    assert rel_err(x.grad.cpu().numpy(), ref) < FWHT_TOL
+
+
+def test_side_stream():
+    from whvi_b200 import FWHTFunction
+    s = torch.cuda.Stream()
+    x = torch.randn(64, 2048, device=dev())
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        y = FWHTFunction.apply(x)
+    s.synchronize()
+    assert rel_err(y.cpu().numpy(), O.fwht(x.cpu().numpy().astype(np.float64))) < FWHT_TOL
+
+
+@pytest.mark.parametrize("k", [6, 10, 13, 15])
+def test_full_size_properties(k):
+    """BASELINE config 2 sizes (2^28 elements = 1 GiB): involution H(Hx) = D x and
+    linearity, checked on the device (size-independent properties)."""
+    from whvi_b200 import fwht_
+    D = 1 << k
+    rows = (1 << 28) // D
+    g = torch.Generator(device=dev()).manual_seed(k)
+    x = torch.randn(rows, D, device=dev(), generator=g)
+    y = fwht_(x)
+    back = fwht_(y)
+    err = (back / D - x).abs().max().item() / x.abs().max().item()
+    assert err < FWHT_TOL
+    # Parseval: ||Hx||^2 = D ||x||^2 per row (first 1024 rows, fp64 accumulate)
+    n = min(rows, 1024)
+    lhs = y[:n].double().pow(2).sum(1)
+    rhs = x[:n].double().pow(2).sum(1) * D
+    assert ((lhs - rhs).abs() / rhs).max().item() < 1e-5
+    del back
+    x2 = torch.randn(rows, D, device=dev(), generator=g)
+    lin = fwht_(x + 2.0 * x2) - (y + 2.0 * fwht_(x2))
+    assert lin.abs().max().item() / y.abs().max().item() < 1e-5
+    # spot-check 4 rows against the fp64 oracle
+    idx = [0, 1, rows // 2, rows - 1]
+    ref = O.fwht(x[idx].cpu().numpy().astype(np.float64))
+    assert rel_err(y[idx].cpu().numpy(), ref) < FWHT_TOL

@@ -1,0 +1,49 @@
+"""ctypes binding of libwhvi_b200.so (C ABI declared in include/whvi_b200.h).
+
+There is no fallback of any kind: if the library is missing or a call fails, a
+RuntimeError is raised (mirroring the TORCH_CHECK -> RuntimeError behaviour of the
+reference extension, src/fwht/cuda/fwht_cuda.cpp:6-10).
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libwhvi_b200.so"
+
+# name -> (restype, argtypes); kept in one place so tests can check that every symbol
+# the header declares is exported and bound.
+FP = POINTER(c_float)
+SIGNATURES = {
+    "whvi_abi_version": (c_int, []),
+    "whvi_last_error": (c_char_p, []),
+    "whvi_max_dim": (c_int64, []),
+    "whvi_fwht_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m whvi_b200.build` "
+                "(whvi_b200 has no CPU or PyTorch fallback)")
+        L = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.whvi_abi_version() != 1:
+            raise RuntimeError("libwhvi_b200.so ABI version mismatch; rebuild with python -m whvi_b200.build --force")
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().whvi_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed ({rc}): {msg}")

@@ -1,0 +1,71 @@
+"""Build libwhvi_b200.so (the C-ABI CUDA library) in-tree with plain nvcc for sm_100a.
+
+    python -m whvi_b200.build [--force] [--verbose]
+
+No torch headers are involved, so the whole library builds in seconds.  The .so lands
+next to this file (git-ignored, but shipped to the GPU box by gpurun).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+OBJ = PKG / "_obj"
+LIB = PKG / "libwhvi_b200.so"
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CFLAGS = ["-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
+          "-Xcompiler", "-fvisibility=hidden", "-DWHVI_BUILDING"]
+
+
+def sources() -> list[Path]:
+    return sorted(CSRC.glob("*.cu"))
+
+
+def _deps() -> list[Path]:
+    return sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "whvi_b200.h"]
+
+
+def _stale(target: Path, deps: list[Path]) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    OBJ.mkdir(exist_ok=True)
+    hdrs = _deps()
+    jobs = []
+    for src in sources():
+        obj = OBJ / (src.stem + ".o")
+        if force or _stale(obj, [src] + hdrs):
+            cmd = [NVCC, *ARCH, *CFLAGS, "-c", str(src), "-o", str(obj)]
+            if verbose:
+                cmd[1:1] = ["-Xptxas", "-v"]
+            jobs.append(cmd)
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError(f"nvcc failed: {' '.join(cmd)}\n{r.stderr}")
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            list(ex.map(run, jobs))
+    objs = [OBJ / (s.stem + ".o") for s in sources()]
+    if force or jobs or _stale(LIB, objs):
+        run([NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

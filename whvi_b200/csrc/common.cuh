@@ -1,0 +1,57 @@
+// Shared host-side plumbing of libwhvi_b200: status codes, thread-local error text,
+// launch checks.  No torch headers anywhere in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include "../../include/whvi_b200.h"
+
+namespace whvi {
+
+char* error_buffer();  // thread-local, 512 bytes (api.cu)
+
+inline int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+inline int check_launch(const char* what)
+{
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", what, cudaGetErrorString(e));
+    return WHVI_OK;
+}
+
+inline bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+inline int ilog2(int64_t v)
+{
+    int k = 0;
+    while ((int64_t(1) << k) < v) ++k;
+    return k;
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Opt a kernel in to > 48 KB of dynamic shared memory, once per (kernel, device).
+template <class Kernel>
+inline int ensure_smem(Kernel kernel, size_t bytes, unsigned char* done_flags /*[64]*/)
+{
+    if (bytes <= 48 * 1024) return WHVI_OK;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && done_flags[dev]) return WHVI_OK;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) done_flags[dev] = 1;
+    return WHVI_OK;
+}
+
+constexpr int kMaxLog2D = 15;  // single-pass kernels keep a whole row in one CTA's shared memory
+
+int launch_fwht(const float* in, float* out, int64_t rows, int64_t D, cudaStream_t stream);
+
+}  // namespace whvi

@@ -1,0 +1,137 @@
+// Kernel (1): batched in-place-capable FWHT over power-of-two D, fp32.
+//
+// Replaces fwht_batch1_kernel / fwht_batch2_kernel of the reference
+// (src/fwht/cuda/fwht_cuda_kernel.cu:74-146, :35-67) and its host wrapper (:156-181,
+// fwht_cuda.cpp:5-14).  Not a port: rows live in registers (32 or 64 floats per thread),
+// all butterflies are register-local FADD2s, and the cross-thread exchanges are two
+// swizzled, bank-conflict-free shared-memory transpositions (layout.cuh); global traffic
+// is one 128-bit coalesced read and one 128-bit coalesced write per element (8 B/elt,
+// the algorithmic minimum; the reference moves 16 B/elt because of its clone).
+#include "common.cuh"
+#include "engine.cuh"
+
+namespace whvi {
+
+template <int N, int C, int K, int GROUPS>
+__global__ void __launch_bounds__((1 << (N - C)) * GROUPS)
+fwht_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total)
+{
+    constexpr int T = 1 << (N - C);
+    constexpr int E = 1 << C;
+    constexpr int64_t TILE = int64_t(1) << N;
+    constexpr int SEQ = seq_pack(V_FIRST, V_MID, V_LAST);
+    // only bits 0,1 to transform: FIRST alone covers them and is already store-friendly
+    constexpr bool kOneRound = (K <= 2);
+
+    extern __shared__ float4 smem4[];
+    const int group = threadIdx.x / T;
+    const uint32_t tid = threadIdx.x % T;
+    const int64_t base = (int64_t(blockIdx.x) * GROUPS + group) * TILE;
+    if (base >= total) return;  // whole group leaves together; barriers are per group
+    float* buf = reinterpret_cast<float*>(smem4) + size_t(group) * (kOneRound ? 0 : TILE);
+
+    float v[E];
+    const uint32_t toff = tile_thread_offset<N, C, V_FIRST>(tid);
+    static_for<0, E / 4>([&](auto m_) {
+        constexpr int m = decltype(m_)::value;
+        constexpr uint32_t roff = tile_reg_offset<N, C, V_FIRST>(m);
+        const int64_t g = base + toff + roff;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < total) q = ldg_stream(in + g);
+        v[4 * m + 0] = q.x;
+        v[4 * m + 1] = q.y;
+        v[4 * m + 2] = q.z;
+        v[4 * m + 3] = q.w;
+    });
+    bfly_round<N, C, K, SEQ, 0>(v);
+
+    if constexpr (kOneRound) {
+        static_for<0, E / 4>([&](auto m_) {
+            constexpr int m = decltype(m_)::value;
+            constexpr uint32_t roff = tile_reg_offset<N, C, V_FIRST>(m);
+            const int64_t g = base + toff + roff;
+            if (g < total) stg_stream(out + g, make_float4(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]));
+        });
+    } else {
+        transpose_write<N, C, V_FIRST, V_MID>(v, buf, transpose_writer_base<N, C, V_FIRST, V_MID>(tid));
+        group_sync<T, GROUPS>(group);
+        transpose_read<C>(v, buf, tid);
+        bfly_round<N, C, K, SEQ, 1>(v);
+        group_sync<T, GROUPS>(group);  // every read of buf is done before it is overwritten
+        transpose_write<N, C, V_MID, V_LAST>(v, buf, transpose_writer_base<N, C, V_MID, V_LAST>(tid));
+        group_sync<T, GROUPS>(group);
+        transpose_read<C>(v, buf, tid);
+        bfly_round<N, C, K, SEQ, 2>(v);
+
+        const uint32_t soff = tile_thread_offset<N, C, V_LAST>(tid);
+        static_for<0, E / 4>([&](auto m_) {
+            constexpr int m = decltype(m_)::value;
+            constexpr uint32_t roff = tile_reg_offset<N, C, V_LAST>(m);
+            const int64_t g = base + soff + roff;
+            if (g < total) stg_stream(out + g, make_float4(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]));
+        });
+    }
+}
+
+// D = 1 (identity) and D = 2: too narrow for a float4; one thread per row.
+__global__ void fwht_tiny_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int D)
+{
+    const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    if (D == 1) {
+        out[r] = in[r];
+    } else {
+        const float2 q = reinterpret_cast<const float2*>(in)[r];
+        reinterpret_cast<float2*>(out)[r] = make_float2(q.x + q.y, q.x - q.y);
+    }
+}
+
+template <int N, int C, int K, int GROUPS>
+static int launch_cfg(const float* in, float* out, int64_t total, cudaStream_t stream)
+{
+    static unsigned char smem_ok[64] = {};
+    constexpr int threads = (1 << (N - C)) * GROUPS;
+    constexpr size_t smem = (K <= 2) ? 0 : sizeof(float) * (size_t(1) << N) * GROUPS;
+    auto kernel = fwht_kernel<N, C, K, GROUPS>;
+    if (int rc = ensure_smem(kernel, smem, smem_ok)) return rc;
+    const int64_t tiles = (total + (int64_t(1) << N) - 1) >> N;
+    const int64_t ctas = (tiles + GROUPS - 1) / GROUPS;
+    if (ctas > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "fwht: %lld tiles exceed the grid limit", (long long)ctas);
+    kernel<<<static_cast<unsigned>(ctas), threads, smem, stream>>>(in, out, total);
+    return check_launch("fwht_kernel");
+}
+
+int launch_fwht(const float* in, float* out, int64_t rows, int64_t D, cudaStream_t stream)
+{
+    const int K = ilog2(D);
+    const int64_t total = rows * D;
+    if (K <= 1) {
+        const int threads = 256;
+        const int64_t blocks = (rows + threads - 1) / threads;
+        fwht_tiny_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(in, out, rows, static_cast<int>(D));
+        return check_launch("fwht_tiny_kernel");
+    }
+    switch (K) {
+    // D <= 1024: one warp per 1024-float tile (1024/D rows), 8 tiles per CTA
+    case 2: return launch_cfg<10, 5, 2, 8>(in, out, total, stream);
+    case 3: return launch_cfg<10, 5, 3, 8>(in, out, total, stream);
+    case 4: return launch_cfg<10, 5, 4, 8>(in, out, total, stream);
+    case 5: return launch_cfg<10, 5, 5, 8>(in, out, total, stream);
+    case 6: return launch_cfg<10, 5, 6, 8>(in, out, total, stream);
+    case 7: return launch_cfg<10, 5, 7, 8>(in, out, total, stream);
+    case 8: return launch_cfg<10, 5, 8, 8>(in, out, total, stream);
+    case 9: return launch_cfg<10, 5, 9, 8>(in, out, total, stream);
+    case 10: return launch_cfg<10, 5, 10, 8>(in, out, total, stream);
+    // one row per group of 64/128/256 threads
+    case 11: return launch_cfg<11, 5, 11, 4>(in, out, total, stream);
+    case 12: return launch_cfg<12, 5, 12, 2>(in, out, total, stream);
+    case 13: return launch_cfg<13, 5, 13, 1>(in, out, total, stream);
+    // 64 floats per thread
+    case 14: return launch_cfg<14, 6, 14, 1>(in, out, total, stream);
+    case 15: return launch_cfg<15, 6, 15, 1>(in, out, total, stream);
+    default: break;
+    }
+    return fail(WHVI_E_SHAPE, "fwht: D = %lld exceeds the single-pass limit 2^%d", (long long)D, kMaxLog2D);
+}
+
+}  // namespace whvi
