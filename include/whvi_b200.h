@@ -66,6 +66,63 @@ WHVI_API int64_t whvi_max_dim(void);
  */
 WHVI_API int whvi_fwht_f32(const float* in, float* out, int64_t rows, int64_t D, whvi_stream_t stream);
 
+/*
+ * Fused WHVILinear forward, PAPER semantics (docstring src/weights.py:77):
+ *   y[s,b,:] = s1 * H( g[s,:] * H( s2 * x[s,b,:] ) ) (+ bias)
+ * x: rows (s,b) at x + s*x_sample_stride + b*D; x_sample_stride is B*D for a contiguous
+ *    (S,B,D) tensor or 0 when all samples share one (B,D) block (first layer of a net).
+ * g: (S,D), one reparameterised vector per MC sample; s1, s2: (D); bias: (D) or NULL;
+ * y: (S,B,D) contiguous.  4 <= D <= 8192, power of two.  Replaces the chain of ~20 torch
+ * ops and the B x D x D GEMM of WHVISquarePow2Matrix.sample_lrt (src/weights.py:87-93).
+ */
+WHVI_API int whvi_layer_fwd_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1,
+                                const float* s2, const float* bias, float* y, int64_t S, int64_t B, int64_t D,
+                                whvi_stream_t stream);
+
+/* Bytes of device workspace whvi_layer_bwd_f32 needs for this shape. */
+WHVI_API int whvi_layer_bwd_workspace_bytes(int64_t S, int64_t B, int64_t D, size_t* bytes);
+
+/*
+ * Fused WHVILinear backward, recomputing the two forward transforms:
+ *   dx[s,b,:] = s2 * H( g[s] * H( s1 * dy[s,b,:] ) )           (S,B,D), or NULL to skip
+ *   dg[s,:]   = sum_b H(s1*dy) * H(s2*x)                        (S,D)
+ *   ds1 = sum_{s,b} dy * H(g*H(s2*x));  ds2 = sum_{s,b} H(g*H(s1*dy)) * x     (D) each
+ *   dbias = sum_{s,b} dy                                         (D), or NULL to skip
+ * All outputs are overwritten (not accumulated).  Reductions use a fixed order, so results
+ * are bit-reproducible run to run.  When x_sample_stride == 0 and dx != NULL, dx still has
+ * the (S,B,D) shape; the caller sums it over s.
+ */
+WHVI_API int whvi_layer_bwd_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* g,
+                                const float* s1, const float* s2, float* dx, float* dg, float* ds1, float* ds2,
+                                float* dbias, void* workspace, size_t workspace_bytes, int64_t S, int64_t B,
+                                int64_t D, whvi_stream_t stream);
+
+/*
+ * Reparameterisation (src/weights.py:43-50, :82-83, :92-93), one eps row per MC sample:
+ *   mode 0:  g[s,:] = mu + softplus(rho) * eps[s,:]              (diagonal; the reference)
+ * eps, g: (S,D); mu, rho: (D).
+ */
+#define WHVI_REPARAM_DIAG 0
+WHVI_API int whvi_reparam_f32(const float* mu, const float* rho, const float* eps, float* g, int64_t S, int64_t D,
+                              int mode, whvi_stream_t stream);
+/* dmu = sum_s dg[s];  drho = (sum_s dg[s]*eps[s]) * sigmoid(rho).  accumulate != 0: += */
+WHVI_API int whvi_reparam_bwd_f32(const float* rho, const float* eps, const float* dg, float* dmu, float* drho,
+                                  int64_t S, int64_t D, int mode, int accumulate, whvi_stream_t stream);
+
+/*
+ * Gaussian KL of N(mu, diag) against N(0, lambda I) with sigma = softplus(rho), value and
+ * gradient in one pass (src/weights.py:52-64 -> src/utils.py:49-71):
+ *   mode 0 (reference, sigma used as a variance):
+ *        0.5*( D ln(lambda) - sum ln(sigma) - D + sum sigma/lambda + sum mu^2/lambda )
+ *   mode 1 (statistically consistent): sigma -> sigma^2 in the log and ratio terms.
+ * out_kl: device float[1].  dmu/drho: (D) or both NULL; they receive grad_scale * dKL/d.
+ * (accumulate != 0: added to the existing contents).
+ */
+#define WHVI_KL_REFERENCE 0
+#define WHVI_KL_CONSISTENT 1
+WHVI_API int whvi_kl_f32(const float* mu, const float* rho, float lambda_, int64_t D, int mode, float* out_kl,
+                         float* dmu, float* drho, float grad_scale, int accumulate, whvi_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,165 @@
+"""GPU parity of kernels (2) fused forward, (3) fused backward, the reparameterisation and
+(5) the KL reduction, through the C ABI, against the fp64 CPU oracle and the goldens.
+Tolerances (north_star): layer outputs and gradients <= 1e-4 in max|a-b|/max|b|."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev())
+
+
+def make_case(S, B, D, seed, shared=False):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, D) if shared else (S, B, D))
+    g = rng.standard_normal((S, D))
+    s1, s2 = rng.standard_normal(D), rng.standard_normal(D)
+    dy = rng.standard_normal((S, B, D))
+    bias = rng.standard_normal(D)
+    return x, g, s1, s2, dy, bias
+
+
+CASES = [(1, 1, 4), (3, 5, 4), (2, 300, 8), (3, 67, 16), (2, 64, 16), (4, 33, 64), (3, 9, 128), (2, 256, 128),
+         (2, 7, 512), (3, 5, 1024), (2, 3, 2048), (2, 5, 4096), (2, 3, 8192), (5, 1, 1024)]
+
+
+@pytest.mark.parametrize("S,B,D", CASES)
+@pytest.mark.parametrize("shared", [False, True])
+def test_forward_backward_vs_oracle(S, B, D, shared):
+    from whvi_b200 import functional as F
+    x, g, s1, s2, dy, bias = make_case(S, B, D, 17 * D + S + B, shared)
+    y = F.layer_forward_raw(t(x), t(g), t(s1), t(s2), t(bias))
+    y_ref = O.layer_fwd(x, g, s1, s2, bias)
+    assert rel_err(y.cpu().numpy(), y_ref) < TOL
+    dx, dg, ds1, ds2, db = F.layer_backward_raw(t(x), t(dy), t(g), t(s1), t(s2), want_dx=True, want_dbias=True)
+    rdx, rdg, rds1, rds2, rdb = O.layer_bwd(x, dy, g, s1, s2, want_dbias=True)
+    dx = dx.cpu().numpy()
+    if shared:
+        dx = dx.astype(np.float64).sum(0)
+    assert rel_err(dx, rdx) < TOL
+    assert rel_err(dg.cpu().numpy(), rdg) < TOL
+    assert rel_err(ds1.cpu().numpy(), rds1) < TOL
+    assert rel_err(ds2.cpu().numpy(), rds2) < TOL
+    assert rel_err(db.cpu().numpy(), rdb) < TOL
+
+
+def test_backward_without_dx_and_bias_and_determinism():
+    from whvi_b200 import functional as F
+    x, g, s1, s2, dy, _ = make_case(3, 41, 256, 5)
+    a = F.layer_backward_raw(t(x), t(dy), t(g), t(s1), t(s2), want_dx=False, want_dbias=False)
+    b = F.layer_backward_raw(t(x), t(dy), t(g), t(s1), t(s2), want_dx=True, want_dbias=False)
+    assert a[0] is None and a[4] is None
+    for u, v in zip(a[1:4], b[1:4]):
+        assert torch.equal(u, v)  # fixed reduction order => bit-reproducible
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_paper_golden(golden, idx):
+    """Dense fp64 H-matrix formula with the reference's own build_H (tests/golden/paper.npz)."""
+    from whvi_b200 import functional as F
+    gd = golden("paper")
+    x, s1, s2, mu, rho, eps, dy = (gd[f"{k}_{idx}"] for k in ("x", "s1", "s2", "mu", "rho", "eps", "dy"))
+    xt = t(x).requires_grad_()
+    s1t, s2t, mut, rhot = (t(v).requires_grad_() for v in (s1, s2, mu, rho))
+    gg = F.reparam(mut, rhot, t(eps))
+    y = F.whvi_layer(xt, gg, s1t, s2t)
+    assert rel_err(gg.detach().cpu().numpy(), gd[f"g_{idx}"]) < 1e-6
+    assert rel_err(y.detach().cpu().numpy(), gd[f"y_{idx}"]) < TOL
+    (y * t(dy)).sum().backward()
+    for name, tt in (("dx", xt), ("ds1", s1t), ("ds2", s2t), ("dmu", mut), ("drho", rhot)):
+        assert rel_err(tt.grad.cpu().numpy(), gd[f"{name}_{idx}"]) < TOL, name
+
+
+def test_shared_x_autograd_sums_over_samples():
+    from whvi_b200 import functional as F
+    x, g, s1, s2, dy, bias = make_case(4, 6, 64, 9, shared=True)
+    xt = t(x).requires_grad_()
+    bt = t(bias).requires_grad_()
+    y = F.whvi_layer(xt, t(g), t(s1), t(s2), bt)
+    (y * t(dy)).sum().backward()
+    rdx, _, _, _, rdb = O.layer_bwd(x, dy, g, s1, s2, want_dbias=True)
+    assert rel_err(xt.grad.cpu().numpy(), rdx) < TOL
+    assert rel_err(bt.grad.cpu().numpy(), rdb) < TOL
+
+
+def test_kl_matches_reference_golden(golden):
+    from whvi_b200 import functional as F
+    gd = golden("kl")
+    for i in range(4):
+        lam = float(gd[f"lam_{i}"])
+        mu, rho = t(gd[f"mu_{i}"]).requires_grad_(), t(gd[f"rho_{i}"]).requires_grad_()
+        kl = F.kl_gaussian(mu, rho, lam, 0)
+        (3.0 * kl).backward()
+        ref = float(gd[f"kl_{i}"])
+        assert abs(kl.item() - ref) <= 1e-5 * max(1.0, abs(ref))
+        assert rel_err(mu.grad.cpu().numpy() / 3.0, gd[f"dmu_{i}"]) < 1e-5
+        assert rel_err(rho.grad.cpu().numpy() / 3.0, gd[f"drho_{i}"]) < 1e-5
+
+
+@pytest.mark.parametrize("D", [1, 7, 100, 4096, 32768])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_kl_vs_oracle(D, mode):
+    from whvi_b200 import functional as F
+    rng = np.random.default_rng(D + mode)
+    mu, rho = rng.standard_normal(D), rng.standard_normal(D) * 2
+    mt, rt = t(mu).requires_grad_(), t(rho).requires_grad_()
+    kl = F.kl_gaussian(mt, rt, 0.7, mode)
+    kl.backward()
+    v, dmu, drho = O.kl(mu, rho, 0.7, mode, grads=True)
+    assert abs(kl.item() - v) <= 2e-5 * max(1.0, abs(v))
+    assert rel_err(mt.grad.cpu().numpy(), dmu) < 1e-5
+    assert rel_err(rt.grad.cpu().numpy(), drho) < 1e-4
+
+
+@pytest.mark.parametrize("S,D", [(1, 4), (3, 100), (64, 128), (7, 8192)])
+def test_reparam_vs_oracle(S, D):
+    from whvi_b200 import functional as F
+    rng = np.random.default_rng(S * D)
+    mu, rho, eps, dg = rng.standard_normal(D), rng.standard_normal(D), rng.standard_normal((S, D)), rng.standard_normal((S, D))
+    mt, rt = t(mu).requires_grad_(), t(rho).requires_grad_()
+    g = F.reparam(mt, rt, t(eps))
+    assert rel_err(g.detach().cpu().numpy(), O.reparam(mu, rho, eps)) < 1e-6
+    (g * t(dg)).sum().backward()
+    dmu, drho = O.reparam_bwd(rho, eps, dg)
+    assert rel_err(mt.grad.cpu().numpy(), dmu) < 1e-5
+    assert rel_err(rt.grad.cpu().numpy(), drho) < 1e-5
+
+
+def test_layer_full_size_properties():
+    """BASELINE config 4 shard (D = 4096, 2^17 rows): adjointness <W x, dy> = <x, W^T dy>
+    ties the forward and the backward kernels together at full size, and a row sample is
+    checked against the fp64 oracle."""
+    from whvi_b200 import functional as F
+    S, B, D = 16, 8192, 4096
+    gen = torch.Generator(device=dev()).manual_seed(1)
+    x = torch.randn(S, B, D, device=dev(), generator=gen)
+    dy = torch.randn(S, B, D, device=dev(), generator=gen)
+    g = torch.randn(S, D, device=dev(), generator=gen)
+    s1 = torch.randn(D, device=dev(), generator=gen)
+    s2 = torch.randn(D, device=dev(), generator=gen)
+    y = F.layer_forward_raw(x, g, s1, s2)
+    dx, dg, ds1, ds2, _ = F.layer_backward_raw(x, dy, g, s1, s2)
+    lhs = (y.double() * dy.double()).sum().item()
+    rhs = (x.double() * dx.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+    # <y, dy> also equals <s1, ds1> = <s2, ds2> = <g, dg> (each parameter enters linearly)
+    for p, dp in ((s1, ds1), (s2, ds2), (g, dg)):
+        assert abs((p.double() * dp.double()).sum().item() - lhs) <= 1e-4 * abs(lhs)
+    rows = [(0, 0), (3, 4097), (15, 8191)]
+    xs = np.stack([x[s, b].cpu().numpy() for s, b in rows]).astype(np.float64)
+    for i, (s, b) in enumerate(rows):
+        ref = O.layer_fwd(xs[i][None, None], g[s].cpu().numpy().astype(np.float64)[None], s1.cpu().numpy().astype(np.float64),
+                          s2.cpu().numpy().astype(np.float64))[0, 0]
+        assert rel_err(y[s, b].cpu().numpy(), ref) < TOL

@@ -20,6 +20,17 @@ SIGNATURES = {
     "whvi_last_error": (c_char_p, []),
     "whvi_max_dim": (c_int64, []),
     "whvi_fwht_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "whvi_layer_fwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int64, c_int64, c_int64, c_void_p]),
+    "whvi_layer_bwd_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, POINTER(c_size_t)]),
+    "whvi_layer_bwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_int64, c_int64,
+                                   c_void_p]),
+    "whvi_reparam_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "whvi_reparam_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
+                                     c_void_p]),
+    "whvi_kl_f32": (c_int, [c_void_p, c_void_p, c_float, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int,
+                            c_void_p]),
 }
 
 _lib = None

@@ -30,4 +30,86 @@ int whvi_fwht_f32(const float* in, float* out, int64_t rows, int64_t D, whvi_str
     return launch_fwht(in, out, rows, D, static_cast<cudaStream_t>(stream));
 }
 
+static int check_layer_shape(const char* who, int64_t S, int64_t B, int64_t D, int64_t xs)
+{
+    if (S < 0 || B < 0 || D < 1) return fail(WHVI_E_SHAPE, "%s: S=%lld B=%lld D=%lld", who, (long long)S, (long long)B, (long long)D);
+    if (!is_pow2(D)) return fail(WHVI_E_SHAPE, "%s: D must be a power of 2 (got %lld)", who, (long long)D);
+    if (D < 4 || D > 8192) return fail(WHVI_E_SHAPE, "%s: D = %lld outside [4, 8192]", who, (long long)D);
+    if (xs != 0 && xs != B * D) return fail(WHVI_E_SHAPE, "%s: x_sample_stride must be 0 or B*D", who);
+    return WHVI_OK;
+}
+
+int whvi_layer_fwd_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1, const float* s2,
+                       const float* bias, float* y, int64_t S, int64_t B, int64_t D, whvi_stream_t stream)
+{
+    if (int rc = check_layer_shape("layer_fwd", S, B, D, x_sample_stride)) return rc;
+    if (S == 0 || B == 0) return WHVI_OK;
+    if (!x || !g || !s1 || !s2 || !y) return fail(WHVI_E_NULL, "layer_fwd: null pointer");
+    if (!aligned16(x) || !aligned16(g) || !aligned16(s1) || !aligned16(s2) || !aligned16(y) || !aligned16(bias))
+        return fail(WHVI_E_ALIGN, "layer_fwd: pointers must be 16-byte aligned");
+    return launch_layer_fwd(x, x_sample_stride, g, s1, s2, bias, y, S, B, D, static_cast<cudaStream_t>(stream));
+}
+
+int whvi_layer_bwd_workspace_bytes(int64_t S, int64_t B, int64_t D, size_t* bytes)
+{
+    if (!bytes) return fail(WHVI_E_NULL, "layer_bwd_workspace_bytes: null pointer");
+    if (int rc = check_layer_shape("layer_bwd_workspace_bytes", S, B, D, 0)) return rc;
+    *bytes = 0;
+    if (S == 0 || B == 0) return WHVI_OK;
+    return launch_layer_bwd(nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                            nullptr, 0, S, B, D, nullptr, bytes);
+}
+
+int whvi_layer_bwd_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* g, const float* s1,
+                       const float* s2, float* dx, float* dg, float* ds1, float* ds2, float* dbias, void* workspace,
+                       size_t workspace_bytes, int64_t S, int64_t B, int64_t D, whvi_stream_t stream)
+{
+    if (int rc = check_layer_shape("layer_bwd", S, B, D, x_sample_stride)) return rc;
+    if (!dg || !ds1 || !ds2) return fail(WHVI_E_NULL, "layer_bwd: null output pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (S == 0 || B == 0) {  // empty sums
+        cudaMemsetAsync(dg, 0, sizeof(float) * size_t(S) * D, st);
+        cudaMemsetAsync(ds1, 0, sizeof(float) * D, st);
+        cudaMemsetAsync(ds2, 0, sizeof(float) * D, st);
+        if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * D, st);
+        return check_launch("layer_bwd(empty)");
+    }
+    if (!x || !dy || !g || !s1 || !s2) return fail(WHVI_E_NULL, "layer_bwd: null pointer");
+    if (!aligned16(x) || !aligned16(dy) || !aligned16(g) || !aligned16(s1) || !aligned16(s2) || !aligned16(dx) ||
+        !aligned16(workspace))
+        return fail(WHVI_E_ALIGN, "layer_bwd: pointers must be 16-byte aligned");
+    return launch_layer_bwd(x, x_sample_stride, dy, g, s1, s2, dx, dg, ds1, ds2, dbias, static_cast<float*>(workspace),
+                            workspace_bytes, S, B, D, st, nullptr);
+}
+
+int whvi_reparam_f32(const float* mu, const float* rho, const float* eps, float* g, int64_t S, int64_t D, int mode,
+                     whvi_stream_t stream)
+{
+    if (S < 0 || D < 1) return fail(WHVI_E_SHAPE, "reparam: S=%lld D=%lld", (long long)S, (long long)D);
+    if (mode != WHVI_REPARAM_DIAG) return fail(WHVI_E_MODE, "reparam: unknown mode %d", mode);
+    if (S == 0) return WHVI_OK;
+    if (!mu || !rho || !eps || !g) return fail(WHVI_E_NULL, "reparam: null pointer");
+    return launch_reparam_diag(mu, rho, eps, g, S, D, static_cast<cudaStream_t>(stream));
+}
+
+int whvi_reparam_bwd_f32(const float* rho, const float* eps, const float* dg, float* dmu, float* drho, int64_t S,
+                         int64_t D, int mode, int accumulate, whvi_stream_t stream)
+{
+    if (S < 0 || D < 1) return fail(WHVI_E_SHAPE, "reparam_bwd: S=%lld D=%lld", (long long)S, (long long)D);
+    if (mode != WHVI_REPARAM_DIAG) return fail(WHVI_E_MODE, "reparam_bwd: unknown mode %d", mode);
+    if (!rho || !dmu || !drho || (S > 0 && (!eps || !dg))) return fail(WHVI_E_NULL, "reparam_bwd: null pointer");
+    return launch_reparam_diag_bwd(rho, eps, dg, dmu, drho, S, D, accumulate, static_cast<cudaStream_t>(stream));
+}
+
+int whvi_kl_f32(const float* mu, const float* rho, float lambda_, int64_t D, int mode, float* out_kl, float* dmu,
+                float* drho, float grad_scale, int accumulate, whvi_stream_t stream)
+{
+    if (D < 1) return fail(WHVI_E_SHAPE, "kl: D=%lld", (long long)D);
+    if (mode != WHVI_KL_REFERENCE && mode != WHVI_KL_CONSISTENT) return fail(WHVI_E_MODE, "kl: unknown mode %d", mode);
+    if (!(lambda_ > 0.f)) return fail(WHVI_E_SHAPE, "kl: lambda must be positive");
+    if (!mu || !rho || !out_kl) return fail(WHVI_E_NULL, "kl: null pointer");
+    if ((dmu == nullptr) != (drho == nullptr)) return fail(WHVI_E_NULL, "kl: dmu and drho must both be given or both NULL");
+    return launch_kl(mu, rho, lambda_, D, mode, out_kl, dmu, drho, grad_scale, accumulate, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -1,0 +1,185 @@
+"""Autograd functions over the C ABI (libwhvi_b200.so): the fused WHVILinear layer, the
+reparameterisation and the KL term.  PyTorch only owns the tensors, the autograd graph and
+the stream; every FLOP of the hot path happens in the hand-written sm_100a kernels.
+
+Shapes: ``x`` is ``(B, D)`` (one block shared by all MC samples -- the first WHVI layer of
+a network) or ``(S, B, D)``; ``g`` is ``(S, D)``, one reparameterised vector per sample;
+``s1, s2, bias`` are ``(D,)``; the output is ``(S, B, D)``.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+_WORKSPACES: dict[tuple[int, int], torch.Tensor] = {}
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Per (device, stream) scratch buffer owned by PyTorch's caching allocator; the
+    library itself never allocates."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream(device))
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.device.type != "cuda":
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32 (got {t.dtype})")
+    return t.contiguous()
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def layer_forward_raw(x, g, s1, s2, bias=None, out=None):
+    """y = s1 * H(g[s] * H(s2 * x)) (+bias), no autograd."""
+    x, g, s1, s2 = _f32c(x, "x"), _f32c(g, "g"), _f32c(s1, "s1"), _f32c(s2, "s2")
+    if g.dim() != 2:
+        raise RuntimeError("g must be (S, D)")
+    S, D = g.shape
+    if x.dim() == 2:
+        B, xs = x.size(0), 0
+    elif x.dim() == 3 and x.size(0) == S:
+        B, xs = x.size(1), x.size(1) * D
+    else:
+        raise RuntimeError(f"x must be (B, D) or (S, B, D) with S = {S}; got {tuple(x.shape)}")
+    if x.size(-1) != D or s1.numel() != D or s2.numel() != D:
+        raise RuntimeError("last dimension of x, s1, s2 must equal D")
+    if bias is not None:
+        bias = _f32c(bias, "bias").reshape(-1)
+        if bias.numel() != D:
+            raise RuntimeError("bias must have D elements")
+    if out is None:
+        out = torch.empty((S, B, D), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().whvi_layer_fwd_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
+                                           out.data_ptr(), S, B, D, _stream(x.device))
+    _lib.check(rc, "whvi_layer_fwd_f32")
+    return out
+
+
+def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False):
+    """Returns (dx | None, dg, ds1, ds2, dbias | None); dx is (S,B,D) even for shared x."""
+    x, dy, g, s1, s2 = _f32c(x, "x"), _f32c(dy, "dy"), _f32c(g, "g"), _f32c(s1, "s1"), _f32c(s2, "s2")
+    S, D = g.shape
+    B, xs = (x.size(0), 0) if x.dim() == 2 else (x.size(1), x.size(1) * D)
+    if dy.shape != (S, B, D):
+        raise RuntimeError(f"dy must be {(S, B, D)}, got {tuple(dy.shape)}")
+    dev = x.device
+    dx = torch.empty((S, B, D), dtype=torch.float32, device=dev) if want_dx else None
+    dg = torch.empty((S, D), dtype=torch.float32, device=dev)
+    ds1 = torch.empty(D, dtype=torch.float32, device=dev)
+    ds2 = torch.empty(D, dtype=torch.float32, device=dev)
+    dbias = torch.empty(D, dtype=torch.float32, device=dev) if want_dbias else None
+    L = _lib.lib()
+    need = ctypes.c_size_t(0)
+    _lib.check(L.whvi_layer_bwd_workspace_bytes(S, B, D, ctypes.byref(need)), "whvi_layer_bwd_workspace_bytes")
+    ws = _workspace(dev, need.value)
+    with torch.cuda.device(dev):
+        rc = L.whvi_layer_bwd_f32(x.data_ptr(), xs, dy.data_ptr(), g.data_ptr(), s1.data_ptr(), s2.data_ptr(),
+                                  _ptr(dx), dg.data_ptr(), ds1.data_ptr(), ds2.data_ptr(), _ptr(dbias),
+                                  ws.data_ptr(), ws.numel(), S, B, D, _stream(dev))
+    _lib.check(rc, "whvi_layer_bwd_f32")
+    return dx, dg, ds1, ds2, dbias
+
+
+class WHVILayerFunction(Function):
+    """y[s,b] = s1 * H(g[s] * H(s2 * x[s,b])) (+ bias) with the fused backward."""
+
+    @staticmethod
+    def forward(ctx, x, g, s1, s2, bias):
+        y = layer_forward_raw(x, g, s1, s2, bias)
+        ctx.save_for_backward(x, g, s1, s2)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, s1, s2 = ctx.saved_tensors
+        want_dx = ctx.needs_input_grad[0]
+        want_db = ctx.has_bias and ctx.needs_input_grad[4]
+        dx, dg, ds1, ds2, dbias = layer_backward_raw(x, dy, g, s1, s2, want_dx=want_dx, want_dbias=want_db)
+        if dx is not None and x.dim() == 2:
+            dx = dx.sum(dim=0)
+        return dx, dg, ds1, ds2, dbias
+
+
+def whvi_layer(x, g, s1, s2, bias=None):
+    return WHVILayerFunction.apply(x, g, s1, s2, bias)
+
+
+class ReparamFunction(Function):
+    """g[s] = mu + softplus(rho) * eps[s]  (src/weights.py:43-50, :82-83)."""
+
+    @staticmethod
+    def forward(ctx, mu, rho, eps):
+        mu, rho, eps = _f32c(mu, "g_mu"), _f32c(rho, "g_rho"), _f32c(eps, "eps")
+        S, D = eps.shape
+        g = torch.empty_like(eps)
+        with torch.cuda.device(eps.device):
+            rc = _lib.lib().whvi_reparam_f32(mu.data_ptr(), rho.data_ptr(), eps.data_ptr(), g.data_ptr(), S, D, 0,
+                                             _stream(eps.device))
+        _lib.check(rc, "whvi_reparam_f32")
+        ctx.save_for_backward(rho, eps)
+        return g
+
+    @staticmethod
+    def backward(ctx, dg):
+        rho, eps = ctx.saved_tensors
+        dg = _f32c(dg, "dg")
+        S, D = eps.shape
+        dmu = torch.empty(D, dtype=torch.float32, device=eps.device)
+        drho = torch.empty(D, dtype=torch.float32, device=eps.device)
+        with torch.cuda.device(eps.device):
+            rc = _lib.lib().whvi_reparam_bwd_f32(rho.data_ptr(), eps.data_ptr(), dg.data_ptr(), dmu.data_ptr(),
+                                                 drho.data_ptr(), S, D, 0, 0, _stream(eps.device))
+        _lib.check(rc, "whvi_reparam_bwd_f32")
+        return dmu, drho, None
+
+
+def reparam(mu, rho, eps):
+    return ReparamFunction.apply(mu, rho, eps)
+
+
+class KLFunction(Function):
+    """KL(N(mu, softplus(rho)) || N(0, lambda)) value + gradient in one kernel.
+    mode 0 = the reference's formula (src/utils.py:49-71), mode 1 = sigma^2 form."""
+
+    @staticmethod
+    def forward(ctx, mu, rho, lambda_, mode):
+        mu, rho = _f32c(mu, "g_mu"), _f32c(rho, "g_rho")
+        D = mu.numel()
+        out = torch.empty(1, dtype=torch.float32, device=mu.device)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        dmu = torch.empty_like(mu) if need_grad else None
+        drho = torch.empty_like(rho) if need_grad else None
+        with torch.cuda.device(mu.device):
+            rc = _lib.lib().whvi_kl_f32(mu.data_ptr(), rho.data_ptr(), float(lambda_), D, int(mode), out.data_ptr(),
+                                        _ptr(dmu), _ptr(drho), 1.0, 0, _stream(mu.device))
+        _lib.check(rc, "whvi_kl_f32")
+        if need_grad:
+            ctx.save_for_backward(dmu, drho)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, dkl):
+        dmu, drho = ctx.saved_tensors
+        return dmu * dkl, drho * dkl, None, None
+
+
+def kl_gaussian(mu, rho, lambda_, mode=0):
+    return KLFunction.apply(mu, rho, lambda_, mode)
