@@ -16,6 +16,7 @@ What is recorded (all from reference code paths, nothing from this repo):
   layers.npz    reference-AS-WRITTEN forward outputs and all parameter/input grads of
                 Square (D=16), Stacked (3->16, 13->32 with bias) and Column (16->1, 1->8)
                 layers with the eps draws captured (monkeypatched torch.randn)
+  init.npz      state_dict of a freshly constructed model under torch.manual_seed(0)
   toy.npz       README toy model (README.md:25-44): loss, KL, MNLL and every grad for one
                 batch with captured eps; state_dict key names
   paper.npz     PAPER-semantics layer (docstring src/weights.py:77) from a dense fp64
@@ -238,7 +239,20 @@ def gen_paper():
     np.savez_compressed(HERE / "paper.npz", **out)
 
 
+def gen_init():
+    """Parameter initialisation under a fixed seed (src/weights.py:28-32 draw order)."""
+    out = {}
+    torch.manual_seed(0)
+    model = WHVIRegression([WHVILinear(3, 16, lambda_=2.0), torch.nn.ReLU(), WHVILinear(16, 16, bias=True),
+                            torch.nn.ReLU(), WHVILinear(16, 1)])
+    for k, v in model.state_dict().items():
+        out[k] = npy(v)
+    out["__keys__"] = np.array(list(model.state_dict().keys()))
+    np.savez_compressed(HERE / "init.npz", **out)
+
+
 if __name__ == "__main__":
+    gen_init()
     gen_fwht()
     gen_kl()
     gen_mnll()

@@ -1,0 +1,202 @@
+"""GPU: the drop-in modules against (a) goldens produced by the reference itself, in
+semantics="reference" with the captured noise injected, and (b) the fp64 oracle in the
+default PAPER semantics."""
+import numpy as np
+import pytest
+import torch
+
+import whvi_b200 as W
+from conftest import rel_err
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev())
+
+
+LAYER_CASES = ["square16", "square16_bias", "stacked_3_16", "stacked_13_32_bias", "column_16_1", "column_1_8_bias"]
+
+
+def load_layer(g, name, semantics):
+    n_in, n_out, bias, B = (int(v) for v in g[f"{name}.shape"])
+    layer = W.WHVILinear(n_in, n_out, lambda_=2.0, bias=bool(bias), semantics=semantics)
+    sd = {k: torch.from_numpy(g[f"{name}.param.{k}"]) for k in layer.state_dict().keys()}
+    layer.load_state_dict(sd)
+    return layer.to(dev()), n_in, n_out, B
+
+
+@pytest.mark.parametrize("name", LAYER_CASES)
+def test_reference_semantics_reproduce_the_reference(golden, name):
+    """Same parameters + same eps => same outputs, KL and gradients as the reference code."""
+    g = golden("layers")
+    layer, n_in, n_out, B = load_layer(g, name, "reference")
+    blocks = layer.square_blocks()
+    assert int(g[f"{name}.n_eps"]) == len(blocks)
+    for i, b in enumerate(blocks):
+        b.inject_eps(t(g[f"{name}.eps{i}"]))
+    x = t(g[f"{name}.x"]).requires_grad_()
+    y = layer(x)
+    assert y.shape == (B, n_out)
+    assert rel_err(y.detach().cpu().numpy(), g[f"{name}.y"]) < TOL
+    (y * t(g[f"{name}.dy"])).sum().backward()
+    assert rel_err(x.grad.cpu().numpy(), g[f"{name}.dx"]) < TOL
+    for pname, p in layer.named_parameters():
+        ref = g[f"{name}.grad.{pname}"]
+        got = np.zeros_like(ref) if p.grad is None else p.grad.cpu().numpy()
+        if np.max(np.abs(ref)) == 0:
+            assert np.max(np.abs(got)) < 1e-6, pname
+        else:
+            assert rel_err(got, ref) < TOL, pname
+    assert abs(float(layer.kl) - float(g[f"{name}.kl"])) < 1e-4 * max(1.0, abs(float(g[f"{name}.kl"])))
+
+
+def test_reference_semantics_toy_model(golden):
+    """README toy model, one training batch: loss, KL, MNLL and every gradient."""
+    g = golden("toy")
+    model = W.WHVIRegression([W.WHVILinear(3, 16, lambda_=2.0, semantics="reference"), torch.nn.ReLU(),
+                              W.WHVILinear(16, 1, semantics="reference")], train_samples=3)
+    assert list(model.state_dict().keys()) == [str(k) for k in g["state_dict_keys"]]
+    model.load_state_dict({k: torch.from_numpy(g[f"param.{k}"]) for k in model.state_dict().keys()})
+    model = model.to(dev()).train()
+    blocks = [b for layer in model._whvi_layers() for b in layer.square_blocks()]
+    S, n_blocks = 3, len(blocks)
+    assert int(g["n_eps"]) == S * n_blocks  # reference order: sample-major, then layer, then block
+    for i, b in enumerate(blocks):
+        b.inject_eps(torch.stack([t(g[f"eps{s * n_blocks + i}"]) for s in range(S)]))
+    loss = model.loss(t(g["x"]), t(g["y"]), n=150)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    assert abs(float(model.current_kl) - float(g["kl"])) < 1e-4 * abs(float(g["kl"]))
+    assert abs(float(model.current_mnll) - float(g["mnll"])) < 1e-4 * abs(float(g["mnll"]))
+    for name, p in model.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), g[f"grad.{name}"]) < TOL, name
+    # eval-mode predictions, 4 samples
+    model.eval_samples = 4
+    model.eval()
+    S = 4
+    for i, b in enumerate(blocks):
+        b.inject_eps(torch.stack([t(g[f"eval_eps{s * n_blocks + i}"]) for s in range(S)]))
+    with torch.no_grad():
+        pred = model(t(g["eval_x"]))
+    assert pred.shape == g["eval_pred"].shape
+    assert rel_err(pred.cpu().numpy(), g["eval_pred"]) < TOL
+
+
+def oracle_layer(layer, x, eps_per_block):
+    """PAPER-semantics expected output of a WHVILinear from the fp64 oracle pieces."""
+    w = layer.weight_submodule
+    f64 = lambda p: p.detach().cpu().numpy().astype(np.float64)
+    if isinstance(w, W.WHVISquarePow2Matrix):
+        g = O.reparam(f64(w.g_mu), f64(w.g_rho), eps_per_block[0])
+        y = O.layer_fwd(x, g, f64(w.s1), f64(w.s2), None if w.bias is None else f64(w.bias))
+        return y
+    if isinstance(w, W.WHVIStackedMatrix):
+        pad = [(0, 0)] * (x.ndim - 1) + [(0, w.D_in - w.n_in)]
+        xp = np.pad(x, pad)
+        ys = []
+        for blk, eps in zip(w.weight_matrices, eps_per_block):
+            g = O.reparam(f64(blk.g_mu), f64(blk.g_rho), eps)
+            ys.append(O.layer_fwd(xp, g, f64(blk.s1), f64(blk.s2)))
+        y = np.concatenate(ys, axis=-1)
+        if w.bias is not None:
+            y = y + f64(w.bias)
+        return y[..., :w.n_out]
+    sub = w.weight_submodule
+    g = O.reparam(f64(sub.g_mu), f64(sub.g_rho), eps_per_block[0])
+    S = g.shape[0]
+    wv = np.stack([O.column_weight_paper(g[s], f64(sub.s1), f64(sub.s2), w.D) for s in range(S)])  # (S, D)
+    xs = np.broadcast_to(x, (S,) + x.shape[-2:]) if x.ndim == 2 else x
+    y = np.einsum("sbi,si->sb", xs, wv)[..., None] if w.transposed else xs * wv[:, None, :]
+    if w.bias is not None:
+        y = y + f64(w.bias)
+    return y
+
+
+@pytest.mark.parametrize("n_in,n_out,bias", [(16, 16, False), (128, 128, True), (3, 16, False), (13, 128, True),
+                                             (128, 1, False), (1, 8, True), (20, 50, False), (1024, 1024, False)])
+@pytest.mark.parametrize("shared", [True, False])
+def test_paper_semantics_vs_oracle(n_in, n_out, bias, shared):
+    torch.manual_seed(n_in * 1000 + n_out)
+    S, B = 3, 6
+    layer = W.WHVILinear(n_in, n_out, lambda_=3.0, bias=bias).to(dev())
+    with torch.no_grad():
+        for name, p in layer.named_parameters():
+            p.copy_(torch.randn_like(p) * (0.5 if name.endswith("g_rho") else 1.0))
+    rng = np.random.default_rng(n_in + n_out)
+    x = rng.standard_normal((B, n_in) if shared else (S, B, n_in))
+    blocks = layer.square_blocks()
+    eps = [rng.standard_normal((S, b.D)) for b in blocks]
+    for b, e in zip(blocks, eps):
+        b.inject_eps(t(e))
+    layer.mc_samples = S
+    y = layer(t(x))
+    layer.mc_samples = None
+    assert y.shape == (S, B, n_out)
+    ref = oracle_layer(layer, x, eps)
+    assert rel_err(y.detach().cpu().numpy(), ref) < TOL
+
+
+def test_standalone_call_is_two_dimensional_and_dense_sample_agrees():
+    torch.manual_seed(3)
+    layer = W.WHVISquarePow2Matrix(64, lambda_=1.0).to(dev())
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.copy_(torch.randn_like(p))
+    x = torch.randn(5, 64, device=dev())
+    eps = torch.randn(1, 64, device=dev())
+    layer.inject_eps(eps)
+    y = layer(x)
+    assert y.shape == (5, 64)
+    layer.inject_eps(eps)
+    Wd = layer.sample()  # dense (D, D), same eps
+    assert rel_err((x @ Wd.T).cpu().detach().numpy(), y.cpu().detach().numpy()) < 1e-4
+
+
+def test_network_shapes_like_reference_test():
+    # test/networks.py:11-23
+    for k in (1, 2, 7, 20):
+        net = W.WHVIRegression([torch.nn.Linear(1, 8), torch.nn.ReLU(), W.WHVILinear(8, 8), torch.nn.ReLU(),
+                                torch.nn.Linear(8, k)], train_samples=5, eval_samples=6).to(dev())
+        net.train()
+        assert net(torch.randn(50, 1, device=dev())).size() == (50, k, 5)
+        net.eval()
+        assert net(torch.randn(50, 1, device=dev())).size() == (50, k, 6)
+
+
+def test_rng_mode_reference_draw_order():
+    model = W.WHVIRegression([W.WHVILinear(3, 16), torch.nn.ReLU(), W.WHVILinear(16, 1)], train_samples=2,
+                             rng_mode="reference").to(dev()).train()
+    blocks = [b for layer in model._whvi_layers() for b in layer.square_blocks()]
+    torch.manual_seed(123)
+    expected = [[torch.randn(b.D, device=dev()) for b in blocks] for _ in range(2)]  # sample-major loop
+    torch.manual_seed(123)
+    model._predraw_reference_order(2)
+    for i, b in enumerate(blocks):
+        got = b._eps_queue.pop(0)
+        assert torch.equal(got, torch.stack([expected[s][i] for s in range(2)]))
+
+
+def test_train_and_eval_model_run_and_learn():
+    torch.manual_seed(0)
+    x = torch.randn(200, 3, device=dev())
+    y = torch.reshape(x[:, 0] + x[:, 1] ** 2 - 0.3 * x[:, 2] ** 3, (-1, 1))
+    ds = torch.utils.data.TensorDataset(x[:150], y[:150])
+    loader = torch.utils.data.DataLoader(ds, batch_size=64)
+    model = W.WHVIRegression([W.WHVILinear(3, 16, lambda_=2.0), torch.nn.ReLU(), W.WHVILinear(16, 1)]).to(dev())
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: (1 + 0.0005 * s) ** (-0.3))
+    model.train()
+    first = float(model.loss(x[:64], y[:64], n=150))
+    model.train_model(loader, opt, sched, epochs1=30, epochs2=30, pbar_update_period=1000)
+    err, mnll = model.eval_model(x[150:], y[150:])
+    assert np.isfinite(err) and np.isfinite(mnll)
+    model.train()
+    last = float(model.loss(x[:64], y[:64], n=150))
+    assert last < first

@@ -1,0 +1,146 @@
+"""``WHVINetwork`` / ``WHVIRegression`` with the reference's signatures
+(``src/networks.py``): forward -> ``(batch, out, n_samples)``, ``loss`` (ELBO),
+``train_model`` (two-phase loop), ``eval_model``.
+
+The reference runs the whole ``nn.Sequential`` once per MC sample in a Python loop
+(``src/networks.py:48``).  Here the MC samples are a leading tensor axis: the sequence runs
+ONCE, every WHVI layer handles all S samples in one fused kernel launch, and foreign
+modules (``nn.Linear``, activations, ...) see the samples folded into the batch.
+"""
+from __future__ import annotations
+
+import pathlib
+from typing import Iterable, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .layers import WHVI, WHVILinear
+from .likelihoods import GaussianLikelihood, Likelihood
+
+try:  # progress bars exactly like the reference when tqdm is around
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(it, **kwargs):
+        return it
+
+
+class WHVINetwork(nn.Module, WHVI):
+    def __init__(self, modules: Iterable[nn.Module], likelihood: Likelihood, train_samples=1, eval_samples=64, *,
+                 rng_mode="batched"):
+        """
+        :param modules: modules for the underlying ``nn.Sequential``.
+        :param likelihood: likelihood used in training.
+        :param int train_samples: MC samples per forward pass in training mode.
+        :param int eval_samples: MC samples per forward pass in eval mode.
+        :param str rng_mode: "batched" draws one ``randn(S, D)`` per weight block;
+            "reference" draws ``randn(D)`` per (sample, layer, block) in the reference's loop
+            order (``src/networks.py:48`` -> ``src/weights.py:180`` -> ``:92``) so that the same
+            seed yields the same noise as the reference.
+        """
+        super().__init__()
+        if rng_mode not in ("batched", "reference"):
+            raise ValueError("rng_mode must be 'batched' or 'reference'")
+        self.sequential = nn.Sequential(*modules)
+        self.likelihood = likelihood
+        self.train_samples = train_samples
+        self.eval_samples = eval_samples
+        self.rng_mode = rng_mode
+        self.current_mnll = 0.0
+        self.current_kl = 0.0
+
+    @property
+    def kl(self):
+        return sum([m.kl for m in self.sequential.children() if 'kl' in dir(m)])
+
+    def _whvi_layers(self):
+        return [m for m in self.sequential.children() if isinstance(m, WHVILinear)]
+
+    def _predraw_reference_order(self, n_samples: int) -> None:
+        blocks = [b for layer in self._whvi_layers() for b in layer.square_blocks()]
+        draws = [[] for _ in blocks]
+        for _ in range(n_samples):
+            for i, b in enumerate(blocks):
+                draws[i].append(torch.randn(b.D, device=b.g_mu.device))
+        for b, d in zip(blocks, draws):
+            b.inject_eps(torch.stack(d))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: (batch_size, in_dim) -> (batch_size, out_dim, n_samples)."""
+        assert x.dim() == 2, "Input shape must be (batch_size, in_dim)"
+        batch_size = x.size()[0]
+        n_samples = self.train_samples if self.training else self.eval_samples
+        layers = self._whvi_layers()
+        if self.rng_mode == "reference":
+            self._predraw_reference_order(n_samples)
+        for layer in layers:
+            layer.mc_samples = n_samples
+        try:
+            h = x
+            for module in self.sequential.children():
+                if isinstance(module, WHVILinear) or h.dim() == 2:
+                    h = module(h)
+                else:  # foreign module: fold the sample axis into the batch
+                    S, B = h.shape[0], h.shape[1]
+                    h = module(h.reshape(S * B, *h.shape[2:]))
+                    h = h.reshape(S, B, *h.shape[1:])
+        finally:
+            for layer in layers:
+                layer.mc_samples = None
+        if h.dim() == 2:  # no WHVI layer introduced a sample axis: S identical predictions
+            h = h.unsqueeze(0).expand(n_samples, *h.shape)
+        predictions = h.reshape(n_samples, batch_size, -1).permute(1, 2, 0)
+        assert predictions.dim() == 3
+        return predictions
+
+    def loss(self, x: torch.Tensor, y: torch.Tensor, n: int, ignore_kl=False) -> torch.Tensor:
+        """Negative ELBO: MNLL estimate + KL (``src/networks.py:56-69``)."""
+        self.current_mnll = self.likelihood.mnll_batch_estimate(y, self(x), n)
+        self.current_kl = self.kl
+        return self.current_mnll + self.current_kl if not ignore_kl else self.current_mnll
+
+    def train_model(self, data_loader, optimizer, scheduler, epochs1: int = 500, epochs2: int = 5000,
+                    pbar_update_period=20, ignore_kl=False, checkpoint_dir=None):
+        """Two-phase training loop of the reference (``src/networks.py:71-99``)."""
+        self.train()
+        self.likelihood.requires_grad = False
+        for phase, epochs, label in ((1, epochs1, 'Fixed LH'), (2, epochs2, 'Optimized LH')):
+            if phase == 2:
+                self.likelihood.requires_grad = True
+            pbar = tqdm(range(epochs), desc=f'[{label}] KL = {float(self.current_kl):.2f}, '
+                                            f'MNLL = {float(self.current_mnll):.2f}')
+            for epoch in pbar:
+                for data_x, data_y in data_loader:
+                    loss = self.loss(data_x, data_y, n=len(data_loader.dataset), ignore_kl=ignore_kl)
+                    loss.backward()
+                    optimizer.step()
+                    scheduler.step()
+                    self.zero_grad(set_to_none=(phase == 1))
+                if phase == 2 and epoch % 5000 == 0 and checkpoint_dir is not None:
+                    torch.save(self.state_dict(), pathlib.Path(checkpoint_dir) / f'epoch-{epoch}.pth')
+                if epoch % pbar_update_period == 0 and hasattr(pbar, "set_description"):
+                    pbar.set_description(f'[{label}] KL = {float(self.current_kl):.2f}, '
+                                         f'MNLL = {float(self.current_mnll):.2f}')
+        self.eval()
+
+    def eval_model(self, X_test: torch.Tensor, y_test: torch.Tensor, loss) -> Tuple[float, float]:
+        """Test error (``loss(y_pred, y_true)``) and MNLL on test data."""
+        self.eval()
+        y_pred = self(X_test)
+        test_mnll = self.likelihood.mnll_batch_estimate(y_test, y_pred, n=y_test.size()[0])
+        test_error = loss(y_pred, y_test)
+        return float(test_error), float(test_mnll)
+
+
+def _rmse_of_mc_mean(y_pred, y_true):
+    return torch.sqrt(F.mse_loss(y_pred.mean(dim=2).flatten(), y_true.flatten()))
+
+
+class WHVIRegression(WHVINetwork):
+    def __init__(self, modules: Iterable[nn.Module], sigma: float = 1.0, **kwargs):
+        """WHVI network for regression with a Gaussian likelihood (``src/networks.py:118-128``)."""
+        super().__init__(modules, likelihood=GaussianLikelihood(sigma), **kwargs)
+
+    def eval_model(self, X_test: torch.Tensor, y_test: torch.Tensor, loss=_rmse_of_mc_mean) -> Tuple[float, float]:
+        return super().eval_model(X_test, y_test, loss)

@@ -1,0 +1,260 @@
+"""WHVI weight parameterisations behind the reference's class names and signatures
+(reference ``src/weights.py``): ``WHVISquarePow2Matrix``, ``WHVIStackedMatrix``,
+``WHVIColumnMatrix``.  Parameter names, shapes, initialisation and registration order are
+the reference's (``src/weights.py:28-32``), so ``state_dict``s are interchangeable.
+
+What changed underneath: the reference materialises a D x D matrix per MC sample through
+four FWHTs of D x D matrices and multiplies by it (``src/weights.py:73``, ``:93``); here a
+whole batch of MC samples goes through ONE fused kernel launch per layer
+(``functional.whvi_layer``), O(S.B.D log D) work and O(S.B.D) memory.
+
+MC samples are a leading tensor axis instead of a Python loop: a layer called with a 2-D
+``(B, n_in)`` input and ``mc_samples = S`` (set by ``WHVINetwork``) returns ``(S, B, n_out)``;
+called with ``(S, B, n_in)`` it maps sample to sample.  Called standalone on a 2-D input
+(``mc_samples`` unset) it behaves exactly like the reference: one draw, 2-D output.
+
+``semantics``:
+  * ``"paper"`` (default) -- W = S1 H diag(g) H S2, the docstring formula at
+    ``src/weights.py:77`` and the north-star definition of the hot path.
+  * ``"reference"`` -- the op chain as the reference actually executes it
+    (``src/weights.py:73``: both FWHTs act on rows, so W collapses to D.diag(s1 g s2),
+    SURVEY F1), run literally with this repo's FWHT kernel in place of ``fwht_cuda``; for
+    seed-for-seed comparisons with the reference.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as WF
+from .fwht import FWHTFunction
+
+_SEMANTICS = ("paper", "reference")
+
+
+def _next_pow2(n: int) -> int:
+    return 1 << max(0, (int(n) - 1).bit_length())
+
+
+def _rowscale(d: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
+    """diag(d) @ A (the reference's matmul_diag_left, src/utils.py:4-12)."""
+    return d.unsqueeze(-1) * A
+
+
+class WHVISquarePow2Matrix(nn.Module):
+    def __init__(self, D, lambda_=1e-5, bias=False, *, semantics="paper", kl_mode=0):
+        """Square WHVI matrix of size (D, D), D a power of two.
+
+        :param int D: rows/columns; power of two.
+        :param float lambda_: prior variance.
+        :param boolean bias: add a (non-variational) bias after the linear map.
+        :param str semantics: "paper" or "reference" (module docstring).
+        :param int kl_mode: 0 = the reference's KL formula (sigma used as a variance,
+            src/utils.py:49-71), 1 = the statistically consistent sigma^2 form.
+        """
+        super().__init__()
+        if D < 1 or D & (D - 1):
+            raise ValueError(f"D must be a power of two, got {D}")
+        if semantics not in _SEMANTICS:
+            raise ValueError(f"semantics must be one of {_SEMANTICS}")
+        self.D = D
+        self.lambda_ = lambda_
+        self.padding = 0
+        self.semantics = semantics
+        self.kl_mode = kl_mode
+        self.mc_samples = None      # set by WHVINetwork while it runs a forward pass
+        self._eps_queue = []        # injected noise, consumed first-in first-out
+
+        # same registration and RNG draw order as src/weights.py:28-32
+        self.bias = nn.Parameter(torch.zeros(1, D)) if bias else None
+        self.s1 = nn.Parameter(torch.randn(D) * 0.01)
+        self.s2 = nn.Parameter(torch.randn(D) * 0.01)
+        self.g_mu = nn.Parameter(torch.zeros(D))
+        self.g_rho = nn.Parameter(torch.rand(D) - 3)
+
+    # ------------------------------------------------------------------ noise
+    def inject_eps(self, eps: torch.Tensor) -> None:
+        """Queue an ``(S, D)`` (or ``(D,)``) noise tensor for the next forward call."""
+        self._eps_queue.append(eps.reshape(-1, self.D))
+
+    def _draw_eps(self, S: int) -> torch.Tensor:
+        if self._eps_queue:
+            eps = self._eps_queue.pop(0).to(device=self.g_mu.device, dtype=torch.float32)
+            if eps.size(0) != S:
+                raise RuntimeError(f"injected eps has {eps.size(0)} samples, the forward pass needs {S}")
+            return eps
+        return torch.randn(S, self.D, device=self.g_mu.device)
+
+    # ------------------------------------------------------------------ reference surface
+    def fwht(self, x):
+        return FWHTFunction.apply(x)
+
+    @property
+    def g_sigma(self):
+        """Standard deviations of g: softplus(g_rho) (src/weights.py:43-50)."""
+        return F.softplus(self.g_rho)
+
+    @property
+    def kl(self):
+        """KL from the N(0, lambda I) prior to the posterior of g (src/weights.py:52-64)."""
+        if self.g_mu.device.type != "cuda":
+            raise RuntimeError("whvi_b200 runs on CUDA only (no CPU fallback); move the module to a GPU")
+        return WF.kl_gaussian(self.g_mu, self.g_rho, self.lambda_, self.kl_mode)
+
+    def w_bar(self, u):
+        """Dense D x D matrix S1 H diag(u) H S2 ("paper") or the as-written chain."""
+        if self.semantics == "reference":
+            return _rowscale(self.s1, self.fwht(_rowscale(u, self.fwht(torch.diag(self.s2)))))
+        eye = torch.eye(self.D, device=u.device)
+        return WF.whvi_layer(eye, u.reshape(1, self.D), self.s1, self.s2)[0].t()
+
+    def sample(self):
+        """One dense sample W (D x D)."""
+        eps = self._draw_eps(1)[0]
+        return self.w_bar(self.g_mu + self.g_sigma * eps)
+
+    def _resolve_samples(self, x):
+        if x.dim() == 3:
+            return x.size(0), False
+        if x.dim() != 2:
+            raise RuntimeError("input must be (batch, D) or (samples, batch, D)")
+        if self.mc_samples is None:
+            return 1, True
+        return int(self.mc_samples), False
+
+    def sample_lrt(self, h):
+        """W h for a fresh draw of g per MC sample (local reparameterisation)."""
+        S, squeeze = self._resolve_samples(h)
+        eps = self._draw_eps(S)
+        if self.semantics == "reference":
+            y = self._as_written(h, eps)
+        else:
+            g = WF.reparam(self.g_mu, self.g_rho, eps)
+            y = WF.whvi_layer(h, g, self.s1, self.s2, None)
+        return y[0] if squeeze else y
+
+    def _as_written(self, h, eps):
+        """src/weights.py:93 per sample: h @ (w_bar(mu) + w_bar(sigma*eps)).T"""
+        outs = []
+        w_mu = self.w_bar(self.g_mu)
+        for s in range(eps.size(0)):
+            W = w_mu + self.w_bar(self.g_sigma * eps[s])
+            hs = h if h.dim() == 2 else h[s]
+            outs.append(hs @ W.T)
+        return torch.stack(outs)
+
+    def forward(self, x, use_lrt=True):
+        """x: (batch, D) or (samples, batch, D).  ``use_lrt`` is kept for signature
+        compatibility; both branches of the reference compute W x for a sampled W."""
+        y = self.sample_lrt(x)
+        if self.bias is not None:
+            y = y + self.bias
+        return y
+
+
+class WHVIStackedMatrix(nn.Module):
+    def __init__(self, n_in, n_out, lambda_=1e-5, bias=False, *, semantics="paper", kl_mode=0):
+        """Non-square WHVI matrix as a stack of square blocks (src/weights.py:111-133)."""
+        super().__init__()
+        self.n_in = n_in
+        self.n_out = n_out
+        self.lambda_ = lambda_
+        self.D_in, self.D_out, self.padding, self.stack = self.setup_dimensions(n_in, n_out)
+        self.weight_matrices = nn.ModuleList([
+            WHVISquarePow2Matrix(self.D_in, lambda_=lambda_, semantics=semantics, kl_mode=kl_mode)
+            for _ in range(self.stack)
+        ])
+        self.bias = nn.Parameter(torch.zeros(1, self.D_out)) if bias else None
+
+    @staticmethod
+    def setup_dimensions(D_in, D_out):
+        """(D_in_adjusted, D_out_adjusted, padding, stack) as src/weights.py:135-160, with
+        integer arithmetic (the reference's float log needs a fix-up branch, :151)."""
+        D_adj = _next_pow2(D_in)
+        padding = D_adj - D_in
+        stack = -(-D_out // D_adj)
+        return D_adj, D_adj * stack, padding, stack
+
+    @property
+    def mc_samples(self):
+        return self.weight_matrices[0].mc_samples
+
+    @mc_samples.setter
+    def mc_samples(self, value):
+        for w in self.weight_matrices:
+            w.mc_samples = value
+
+    @property
+    def kl(self):
+        return sum(weight.kl for weight in self.weight_matrices)
+
+    def sample(self):
+        return torch.cat([weight.sample() for weight in self.weight_matrices])
+
+    def sample_lrt(self, h):
+        return torch.cat([weight.sample_lrt(h) for weight in self.weight_matrices], dim=-1)
+
+    def forward(self, x, use_lrt=True):
+        """x: (..., n_in) -> (..., n_out): zero-pad to D_in, apply every block, concatenate,
+        add the bias, drop the padding outputs (src/weights.py:182-208)."""
+        x_padded = F.pad(x, (0, self.D_in - self.n_in)) if self.D_in != self.n_in else x
+        output = self.sample_lrt(x_padded)
+        if self.bias is not None:
+            output = output + self.bias
+        return output[..., :self.n_out]
+
+
+class WHVIColumnMatrix(nn.Module):
+    def __init__(self, n_out, lambda_=1e-5, bias=False, transposed=False, *, semantics="paper", kl_mode=0):
+        """Single-column (or, transposed, single-row) WHVI matrix (src/weights.py:211-229)."""
+        super().__init__()
+        self.D = n_out
+        self.D_adjusted = _next_pow2(n_out)
+        self.weight_submodule = WHVISquarePow2Matrix(self.D_adjusted, lambda_=lambda_, semantics=semantics,
+                                                     kl_mode=kl_mode)
+        self.transposed = transposed
+        self.bias = nn.Parameter(torch.zeros(1, 1 if transposed else n_out)) if bias else None
+
+    @property
+    def mc_samples(self):
+        return self.weight_submodule.mc_samples
+
+    @mc_samples.setter
+    def mc_samples(self, value):
+        self.weight_submodule.mc_samples = value
+
+    @property
+    def kl(self):
+        return self.weight_submodule.kl
+
+    def _weights(self, S):
+        """(S, D): the first D entries of the flattened sampled matrix, i.e. of its row 0
+        (src/weights.py:239-245).  "paper": W[0, j] = s1[0] * s2[j] * (H g)[j], one FWHT of
+        g per sample instead of a D x D sample."""
+        sub = self.weight_submodule
+        eps = sub._draw_eps(S)
+        if sub.semantics == "reference":
+            rows = [sub.w_bar(sub.g_mu + sub.g_sigma * eps[s]).reshape(-1)[:self.D] for s in range(S)]
+            return torch.stack(rows)
+        g = WF.reparam(sub.g_mu, sub.g_rho, eps)
+        return (sub.s1[0] * sub.s2 * FWHTFunction.apply(g))[:, :self.D]
+
+    def sample(self):
+        w = self._weights(1)[0].reshape(-1, 1)
+        return w.T if self.transposed else w
+
+    def forward(self, x):
+        S, squeeze = self.weight_submodule._resolve_samples(x)
+        w = self._weights(S)                                   # (S, D)
+        if self.transposed:                                    # (.., D) -> (.., 1)
+            if x.dim() == 2:
+                y = (x @ w.t()).t().unsqueeze(-1)              # (S, B, 1)
+            else:
+                y = torch.bmm(x, w.unsqueeze(-1))              # (S, B, 1)
+        else:                                                  # (.., 1) -> (.., D)
+            xs = x.unsqueeze(0) if x.dim() == 2 else x         # (1|S, B, 1)
+            y = xs * w.unsqueeze(1)                            # (S, B, D)
+        if self.bias is not None:
+            y = y + self.bias
+        return y[0] if squeeze else y
