@@ -17,6 +17,37 @@ from . import _lib
 
 _WORKSPACES: dict[tuple[int, int], torch.Tensor] = {}
 
+# Kernel-launch accounting (bench.py reads it): launches issued by each C-ABI call.
+LAUNCH_COUNTS: dict[str, int] = {}
+_LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_layer_fwd_f32": 1, "whvi_layer_bwd_f32": 2, "whvi_reparam_f32": 1,
+                      "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1}
+# When set to a dict {"name": [(start_event, stop_event), ...]}, the named calls are bracketed
+# by CUDA events on the launching stream (bench.py's per-kernel roofline timing).
+EVENT_SINK: dict[str, list] | None = None
+
+
+def _count(name: str) -> None:
+    LAUNCH_COUNTS[name] = LAUNCH_COUNTS.get(name, 0) + _LAUNCHES_PER_CALL[name]
+
+
+class _Timed:
+    def __init__(self, name: str):
+        self.name = name
+        self.on = EVENT_SINK is not None and name in EVENT_SINK
+
+    def __enter__(self):
+        _count(self.name)
+        if self.on:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.b.record()
+            EVENT_SINK[self.name].append((self.a, self.b))
+
 
 def _stream(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
@@ -65,7 +96,7 @@ def layer_forward_raw(x, g, s1, s2, bias=None, out=None):
             raise RuntimeError("bias must have D elements")
     if out is None:
         out = torch.empty((S, B, D), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _Timed("whvi_layer_fwd_f32"):
         rc = _lib.lib().whvi_layer_fwd_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
                                            out.data_ptr(), S, B, D, _stream(x.device))
     _lib.check(rc, "whvi_layer_fwd_f32")
@@ -89,7 +120,7 @@ def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False):
     need = ctypes.c_size_t(0)
     _lib.check(L.whvi_layer_bwd_workspace_bytes(S, B, D, ctypes.byref(need)), "whvi_layer_bwd_workspace_bytes")
     ws = _workspace(dev, need.value)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _Timed("whvi_layer_bwd_f32"):
         rc = L.whvi_layer_bwd_f32(x.data_ptr(), xs, dy.data_ptr(), g.data_ptr(), s1.data_ptr(), s2.data_ptr(),
                                   _ptr(dx), dg.data_ptr(), ds1.data_ptr(), ds2.data_ptr(), _ptr(dbias),
                                   ws.data_ptr(), ws.numel(), S, B, D, _stream(dev))
@@ -130,7 +161,7 @@ class ReparamFunction(Function):
         mu, rho, eps = _f32c(mu, "g_mu"), _f32c(rho, "g_rho"), _f32c(eps, "eps")
         S, D = eps.shape
         g = torch.empty_like(eps)
-        with torch.cuda.device(eps.device):
+        with torch.cuda.device(eps.device), _Timed("whvi_reparam_f32"):
             rc = _lib.lib().whvi_reparam_f32(mu.data_ptr(), rho.data_ptr(), eps.data_ptr(), g.data_ptr(), S, D, 0,
                                              _stream(eps.device))
         _lib.check(rc, "whvi_reparam_f32")
@@ -144,7 +175,7 @@ class ReparamFunction(Function):
         S, D = eps.shape
         dmu = torch.empty(D, dtype=torch.float32, device=eps.device)
         drho = torch.empty(D, dtype=torch.float32, device=eps.device)
-        with torch.cuda.device(eps.device):
+        with torch.cuda.device(eps.device), _Timed("whvi_reparam_bwd_f32"):
             rc = _lib.lib().whvi_reparam_bwd_f32(rho.data_ptr(), eps.data_ptr(), dg.data_ptr(), dmu.data_ptr(),
                                                  drho.data_ptr(), S, D, 0, 0, _stream(eps.device))
         _lib.check(rc, "whvi_reparam_bwd_f32")
@@ -167,7 +198,7 @@ class KLFunction(Function):
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         dmu = torch.empty_like(mu) if need_grad else None
         drho = torch.empty_like(rho) if need_grad else None
-        with torch.cuda.device(mu.device):
+        with torch.cuda.device(mu.device), _Timed("whvi_kl_f32"):
             rc = _lib.lib().whvi_kl_f32(mu.data_ptr(), rho.data_ptr(), float(lambda_), D, int(mode), out.data_ptr(),
                                         _ptr(dmu), _ptr(drho), 1.0, 0, _stream(mu.device))
         _lib.check(rc, "whvi_kl_f32")

@@ -39,7 +39,8 @@ def fwht_(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         raise RuntimeError("out must be a contiguous float32 tensor shaped like x on the same device")
     if x.numel() == 0:
         return out
-    with torch.cuda.device(x.device):
+    from . import functional as _F
+    with torch.cuda.device(x.device), _F._Timed("whvi_fwht_f32"):
         rc = _lib.lib().whvi_fwht_f32(x.data_ptr(), out.data_ptr(), x.size(0), n, _stream_ptr(x.device))
     _lib.check(rc, "whvi_fwht_f32")
     return out
