@@ -239,7 +239,7 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
     WF.LAUNCH_COUNTS.clear()
-    WF.EVENT_SINK = {"whvi_layer_bwd_f32": [], "whvi_layer_fwd_f32": []}
+    WF.EVENT_SINK = {"whvi_layer_bwd_fused_f32": [], "whvi_layer_fwd_fused_f32": []}
     with ClockSampler(local_rank) as clk:
         ms_total = timed(lambda: step(x_dev, y_dev), args.steps)
     sink, WF.EVENT_SINK = WF.EVENT_SINK, None
@@ -260,8 +260,8 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (fused backward) from events inside the timed region
     peak, peak_src = measured_peaks()
-    bwd_ms = [a.elapsed_time(b) for a, b in sink["whvi_layer_bwd_f32"]]
-    fwd_ms = [a.elapsed_time(b) for a, b in sink["whvi_layer_fwd_f32"]]
+    bwd_ms = [a.elapsed_time(b) for a, b in sink["whvi_layer_bwd_fused_f32"]]
+    fwd_ms = [a.elapsed_time(b) for a, b in sink["whvi_layer_fwd_fused_f32"]]
     rows_per_launch = chunk * B
     bwd_avg = sum(bwd_ms) / len(bwd_ms)
     fwd_avg = sum(fwd_ms) / len(fwd_ms)

@@ -98,6 +98,33 @@ WHVI_API int whvi_layer_bwd_f32(const float* x, int64_t x_sample_stride, const f
                                 int64_t D, whvi_stream_t stream);
 
 /*
+ * Fused variants (the steps either side of the layer folded into it).
+ *  forward:  flags & WHVI_LAYER_RELU_OUT  -> y = max(y, 0) before the store (the nn.ReLU
+ *            that follows the layer in the reference's networks);
+ *            target != NULL ((B,D), broadcast over samples) -> additionally
+ *            sq_partials[i] = partial sums of (y - target)^2, i < whvi_layer_fwd_partials();
+ *            their plain sum is the data term of GaussianLikelihood.mnll_batch_estimate
+ *            (src/likelihoods.py:18-29).
+ *  backward: flags & WHVI_LAYER_RELU_IN   -> x is the output of a fused ReLU; dx is
+ *            multiplied by (x > 0), i.e. it is the gradient w.r.t. the producer's
+ *            pre-activation;
+ *            target != NULL -> `dy` points at the layer's saved OUTPUT and the upstream
+ *            gradient is formed on the fly as coef[0] * (output - target) (coef: device
+ *            scalar), the gradient of the Gaussian MNLL, so it never exists in HBM.
+ */
+#define WHVI_LAYER_RELU_OUT 1
+#define WHVI_LAYER_RELU_IN 1
+WHVI_API int whvi_layer_fwd_partials(int64_t S, int64_t B, int64_t D, int64_t* count);
+WHVI_API int whvi_layer_fwd_fused_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1,
+                                      const float* s2, const float* bias, float* y, int64_t S, int64_t B, int64_t D,
+                                      int flags, const float* target, float* sq_partials, whvi_stream_t stream);
+WHVI_API int whvi_layer_bwd_fused_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* g,
+                                      const float* s1, const float* s2, float* dx, float* dg, float* ds1, float* ds2,
+                                      float* dbias, void* workspace, size_t workspace_bytes, int64_t S, int64_t B,
+                                      int64_t D, int flags, const float* target, const float* coef,
+                                      whvi_stream_t stream);
+
+/*
  * Reparameterisation (src/weights.py:43-50, :82-83, :92-93), one eps row per MC sample:
  *   mode 0:  g[s,:] = mu + softplus(rho) * eps[s,:]              (diagonal; the reference)
  * eps, g: (S,D); mu, rho: (D).

@@ -55,6 +55,35 @@ def test_forward_backward_vs_oracle(S, B, D, shared):
     assert rel_err(db.cpu().numpy(), rdb) < TOL
 
 
+@pytest.mark.parametrize("S,B,D", [(2, 37, 16), (3, 70, 128), (2, 9, 1024), (2, 6, 2048), (2, 5, 4096), (2, 3, 8192)])
+def test_fused_flags(S, B, D):
+    """N1/N2 fusions: ReLU on the output, ReLU mask on dx, Gaussian-MNLL residual as dy and
+    its squared-error reduction."""
+    from whvi_b200 import functional as F
+    x, g, s1, s2, dy, bias = make_case(S, B, D, 3 * D + B)
+    rng = np.random.default_rng(D)
+    target = rng.standard_normal((B, D))
+    y_ref = O.layer_fwd(x, g, s1, s2, bias)
+    y, sq = F.layer_forward_raw(t(x), t(g), t(s1), t(s2), t(bias), relu_out=True, target=t(target))
+    yr = np.maximum(y_ref, 0.0)
+    assert rel_err(y.cpu().numpy(), yr) < TOL
+    sq_ref = float(((yr - target[None]) ** 2).sum())
+    assert abs(sq.item() - sq_ref) < 1e-4 * sq_ref
+    # backward: x plays the role of a ReLU output (mask = x > 0); dy formed from a residual
+    coef = 0.37
+    yhat = rng.standard_normal((S, B, D))
+    dy_explicit = coef * (yhat - target[None])
+    dx, dg, ds1, ds2, db = F.layer_backward_raw(t(x), t(yhat), t(g), t(s1), t(s2), want_dx=True, want_dbias=True,
+                                                 relu_in=True, target=t(target), coef=torch.tensor(coef, device=dev()))
+    x32 = x.astype(np.float32)
+    rdx, rdg, rds1, rds2, rdb = O.layer_bwd(x, dy_explicit, g, s1, s2, want_dbias=True)
+    assert rel_err(dx.cpu().numpy(), rdx * (x32 > 0)) < TOL
+    assert rel_err(dg.cpu().numpy(), rdg) < TOL
+    assert rel_err(ds1.cpu().numpy(), rds1) < TOL
+    assert rel_err(ds2.cpu().numpy(), rds2) < TOL
+    assert rel_err(db.cpu().numpy(), rdb) < TOL
+
+
 def test_backward_without_dx_and_bias_and_determinism():
     from whvi_b200 import functional as F
     x, g, s1, s2, dy, _ = make_case(3, 41, 256, 5)

@@ -26,6 +26,12 @@ SIGNATURES = {
     "whvi_layer_bwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_int64, c_int64,
                                    c_void_p]),
+    "whvi_layer_fwd_partials": (c_int, [c_int64, c_int64, c_int64, POINTER(c_int64)]),
+    "whvi_layer_fwd_fused_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "whvi_layer_bwd_fused_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_int64, c_int64,
+                                         c_int, c_void_p, c_void_p, c_void_p]),
     "whvi_reparam_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "whvi_reparam_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                      c_void_p]),

@@ -39,15 +39,42 @@ static int check_layer_shape(const char* who, int64_t S, int64_t B, int64_t D, i
     return WHVI_OK;
 }
 
+int whvi_layer_fwd_partials(int64_t S, int64_t B, int64_t D, int64_t* count)
+{
+    if (!count) return fail(WHVI_E_NULL, "layer_fwd_partials: null pointer");
+    if (int rc = check_layer_shape("layer_fwd_partials", S, B, D, 0)) return rc;
+    *count = 0;
+    if (S == 0 || B == 0) return WHVI_OK;
+    size_t n = 0;
+    LayerFwdCall c{};
+    c.S = S;
+    c.B = B;
+    c.partials_needed = &n;
+    const int rc = launch_layer_fwd(c, D, nullptr);
+    *count = static_cast<int64_t>(n);
+    return rc;
+}
+
+int whvi_layer_fwd_fused_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1, const float* s2,
+                             const float* bias, float* y, int64_t S, int64_t B, int64_t D, int flags,
+                             const float* target, float* sq_partials, whvi_stream_t stream)
+{
+    if (int rc = check_layer_shape("layer_fwd", S, B, D, x_sample_stride)) return rc;
+    if (flags & ~WHVI_LAYER_RELU_OUT) return fail(WHVI_E_MODE, "layer_fwd: unknown flags %d", flags);
+    if (S == 0 || B == 0) return WHVI_OK;
+    if (!x || !g || !s1 || !s2 || !y) return fail(WHVI_E_NULL, "layer_fwd: null pointer");
+    if (target && !sq_partials) return fail(WHVI_E_NULL, "layer_fwd: target given without sq_partials");
+    if (!aligned16(x) || !aligned16(g) || !aligned16(s1) || !aligned16(s2) || !aligned16(y) || !aligned16(bias) ||
+        !aligned16(target))
+        return fail(WHVI_E_ALIGN, "layer_fwd: pointers must be 16-byte aligned");
+    LayerFwdCall c{x, g, s1, s2, bias, target, y, sq_partials, x_sample_stride, S, B, flags & WHVI_LAYER_RELU_OUT, nullptr};
+    return launch_layer_fwd(c, D, static_cast<cudaStream_t>(stream));
+}
+
 int whvi_layer_fwd_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1, const float* s2,
                        const float* bias, float* y, int64_t S, int64_t B, int64_t D, whvi_stream_t stream)
 {
-    if (int rc = check_layer_shape("layer_fwd", S, B, D, x_sample_stride)) return rc;
-    if (S == 0 || B == 0) return WHVI_OK;
-    if (!x || !g || !s1 || !s2 || !y) return fail(WHVI_E_NULL, "layer_fwd: null pointer");
-    if (!aligned16(x) || !aligned16(g) || !aligned16(s1) || !aligned16(s2) || !aligned16(y) || !aligned16(bias))
-        return fail(WHVI_E_ALIGN, "layer_fwd: pointers must be 16-byte aligned");
-    return launch_layer_fwd(x, x_sample_stride, g, s1, s2, bias, y, S, B, D, static_cast<cudaStream_t>(stream));
+    return whvi_layer_fwd_fused_f32(x, x_sample_stride, g, s1, s2, bias, y, S, B, D, 0, nullptr, nullptr, stream);
 }
 
 int whvi_layer_bwd_workspace_bytes(int64_t S, int64_t B, int64_t D, size_t* bytes)
@@ -56,30 +83,45 @@ int whvi_layer_bwd_workspace_bytes(int64_t S, int64_t B, int64_t D, size_t* byte
     if (int rc = check_layer_shape("layer_bwd_workspace_bytes", S, B, D, 0)) return rc;
     *bytes = 0;
     if (S == 0 || B == 0) return WHVI_OK;
-    return launch_layer_bwd(nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                            nullptr, 0, S, B, D, nullptr, bytes);
+    LayerBwdCall c{};
+    c.S = S;
+    c.B = B;
+    c.need_only = bytes;
+    return launch_layer_bwd(c, D, nullptr);
 }
 
-int whvi_layer_bwd_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* g, const float* s1,
-                       const float* s2, float* dx, float* dg, float* ds1, float* ds2, float* dbias, void* workspace,
-                       size_t workspace_bytes, int64_t S, int64_t B, int64_t D, whvi_stream_t stream)
+int whvi_layer_bwd_fused_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* g, const float* s1,
+                             const float* s2, float* dx, float* dg, float* ds1, float* ds2, float* dbias,
+                             void* workspace, size_t workspace_bytes, int64_t S, int64_t B, int64_t D, int flags,
+                             const float* target, const float* coef, whvi_stream_t stream)
 {
     if (int rc = check_layer_shape("layer_bwd", S, B, D, x_sample_stride)) return rc;
+    if (flags & ~WHVI_LAYER_RELU_IN) return fail(WHVI_E_MODE, "layer_bwd: unknown flags %d", flags);
     if (!dg || !ds1 || !ds2) return fail(WHVI_E_NULL, "layer_bwd: null output pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (S == 0 || B == 0) {  // empty sums
-        cudaMemsetAsync(dg, 0, sizeof(float) * size_t(S) * D, st);
+        if (S > 0) cudaMemsetAsync(dg, 0, sizeof(float) * size_t(S) * D, st);
         cudaMemsetAsync(ds1, 0, sizeof(float) * D, st);
         cudaMemsetAsync(ds2, 0, sizeof(float) * D, st);
         if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * D, st);
         return check_launch("layer_bwd(empty)");
     }
     if (!x || !dy || !g || !s1 || !s2) return fail(WHVI_E_NULL, "layer_bwd: null pointer");
+    if (target && !coef) return fail(WHVI_E_NULL, "layer_bwd: target given without coef");
     if (!aligned16(x) || !aligned16(dy) || !aligned16(g) || !aligned16(s1) || !aligned16(s2) || !aligned16(dx) ||
-        !aligned16(workspace))
+        !aligned16(workspace) || !aligned16(target))
         return fail(WHVI_E_ALIGN, "layer_bwd: pointers must be 16-byte aligned");
-    return launch_layer_bwd(x, x_sample_stride, dy, g, s1, s2, dx, dg, ds1, ds2, dbias, static_cast<float*>(workspace),
-                            workspace_bytes, S, B, D, st, nullptr);
+    LayerBwdCall c{x, dy, g, s1, s2, target, coef, dx, dg, ds1, ds2, dbias, static_cast<float*>(workspace),
+                   workspace_bytes, x_sample_stride, S, B, flags & WHVI_LAYER_RELU_IN, nullptr};
+    return launch_layer_bwd(c, D, st);
+}
+
+int whvi_layer_bwd_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* g, const float* s1,
+                       const float* s2, float* dx, float* dg, float* ds1, float* ds2, float* dbias, void* workspace,
+                       size_t workspace_bytes, int64_t S, int64_t B, int64_t D, whvi_stream_t stream)
+{
+    return whvi_layer_bwd_fused_f32(x, x_sample_stride, dy, g, s1, s2, dx, dg, ds1, ds2, dbias, workspace,
+                                    workspace_bytes, S, B, D, 0, nullptr, nullptr, stream);
 }
 
 int whvi_reparam_f32(const float* mu, const float* rho, const float* eps, float* g, int64_t S, int64_t D, int mode,

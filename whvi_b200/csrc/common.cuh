@@ -53,11 +53,23 @@ inline int ensure_smem(Kernel kernel, size_t bytes, unsigned char* done_flags /*
 constexpr int kMaxLog2D = 15;  // single-pass kernels keep a whole row in one CTA's shared memory
 
 int launch_fwht(const float* in, float* out, int64_t rows, int64_t D, cudaStream_t stream);
-int launch_layer_fwd(const float* x, int64_t xs, const float* g, const float* s1, const float* s2, const float* bias,
-                     float* y, int64_t S, int64_t B, int64_t D, cudaStream_t stream);
-int launch_layer_bwd(const float* x, int64_t xs, const float* dy, const float* g, const float* s1, const float* s2,
-                     float* dx, float* dg, float* ds1, float* ds2, float* dbias, float* ws, size_t ws_bytes, int64_t S,
-                     int64_t B, int64_t D, cudaStream_t stream, size_t* need_only);
+struct LayerFwdCall {
+    const float *x, *g, *s1, *s2, *bias, *target;
+    float *y, *sq_partials;
+    int64_t xs, S, B;
+    int relu_out;
+    size_t* partials_needed;  // query mode: number of floats of sq_partials
+};
+struct LayerBwdCall {
+    const float *x, *dy, *g, *s1, *s2, *target, *coef;
+    float *dx, *dg, *ds1, *ds2, *dbias, *ws;
+    size_t ws_bytes;
+    int64_t xs, S, B;
+    int relu_in;
+    size_t* need_only;  // query mode: workspace bytes
+};
+int launch_layer_fwd(const LayerFwdCall& c, int64_t D, cudaStream_t stream);
+int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream);
 int launch_reparam_diag(const float* mu, const float* rho, const float* eps, float* g, int64_t S, int64_t D,
                         cudaStream_t stream);
 int launch_reparam_diag_bwd(const float* rho, const float* eps, const float* dg, float* dmu, float* drho, int64_t S,

@@ -19,7 +19,8 @@ _WORKSPACES: dict[tuple[int, int], torch.Tensor] = {}
 
 # Kernel-launch accounting (bench.py reads it): launches issued by each C-ABI call.
 LAUNCH_COUNTS: dict[str, int] = {}
-_LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_layer_fwd_f32": 1, "whvi_layer_bwd_f32": 2, "whvi_reparam_f32": 1,
+_LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_layer_fwd_f32": 1, "whvi_layer_bwd_f32": 2,
+                      "whvi_layer_fwd_fused_f32": 1, "whvi_layer_bwd_fused_f32": 2, "whvi_reparam_f32": 1,
                       "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1}
 # When set to a dict {"name": [(start_event, stop_event), ...]}, the named calls are bracketed
 # by CUDA events on the launching stream (bench.py's per-kernel roofline timing).
@@ -76,9 +77,7 @@ def _ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
 
-def layer_forward_raw(x, g, s1, s2, bias=None, out=None):
-    """y = s1 * H(g[s] * H(s2 * x)) (+bias), no autograd."""
-    x, g, s1, s2 = _f32c(x, "x"), _f32c(g, "g"), _f32c(s1, "s1"), _f32c(s2, "s2")
+def _layer_dims(x, g, s1, s2):
     if g.dim() != 2:
         raise RuntimeError("g must be (S, D)")
     S, D = g.shape
@@ -90,27 +89,51 @@ def layer_forward_raw(x, g, s1, s2, bias=None, out=None):
         raise RuntimeError(f"x must be (B, D) or (S, B, D) with S = {S}; got {tuple(x.shape)}")
     if x.size(-1) != D or s1.numel() != D or s2.numel() != D:
         raise RuntimeError("last dimension of x, s1, s2 must equal D")
+    return S, B, D, xs
+
+
+def layer_forward_raw(x, g, s1, s2, bias=None, out=None, relu_out=False, target=None):
+    """y = s1 * H(g[s] * H(s2 * x)) (+bias) [-> max(y, 0)], no autograd.
+    With ``target`` (B, D): returns ``(y, sum (y - target)^2)``, the sum as a 0-d tensor."""
+    x, g, s1, s2 = _f32c(x, "x"), _f32c(g, "g"), _f32c(s1, "s1"), _f32c(s2, "s2")
+    S, B, D, xs = _layer_dims(x, g, s1, s2)
     if bias is not None:
         bias = _f32c(bias, "bias").reshape(-1)
         if bias.numel() != D:
             raise RuntimeError("bias must have D elements")
     if out is None:
         out = torch.empty((S, B, D), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device), _Timed("whvi_layer_fwd_f32"):
-        rc = _lib.lib().whvi_layer_fwd_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
-                                           out.data_ptr(), S, B, D, _stream(x.device))
-    _lib.check(rc, "whvi_layer_fwd_f32")
+    L = _lib.lib()
+    partials = None
+    if target is not None:
+        target = _f32c(target, "target")
+        if target.shape != (B, D):
+            raise RuntimeError(f"target must be {(B, D)}, got {tuple(target.shape)}")
+        n = ctypes.c_int64(0)
+        _lib.check(L.whvi_layer_fwd_partials(S, B, D, ctypes.byref(n)), "whvi_layer_fwd_partials")
+        partials = torch.empty(max(n.value, 1), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _Timed("whvi_layer_fwd_fused_f32"):
+        rc = L.whvi_layer_fwd_fused_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
+                                        out.data_ptr(), S, B, D, 1 if relu_out else 0, _ptr(target), _ptr(partials),
+                                        _stream(x.device))
+    _lib.check(rc, "whvi_layer_fwd_fused_f32")
+    if target is not None:
+        return out, partials.sum() if S * B > 0 else partials.sum() * 0
     return out
 
 
-def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False):
-    """Returns (dx | None, dg, ds1, ds2, dbias | None); dx is (S,B,D) even for shared x."""
+def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False, relu_in=False, target=None, coef=None):
+    """Returns (dx | None, dg, ds1, ds2, dbias | None); dx is (S,B,D) even for shared x.
+    ``relu_in``: x came out of a fused ReLU, dx is masked by x > 0.  ``target``/``coef``:
+    ``dy`` holds the layer's saved output and the upstream gradient is
+    coef * (output - target) formed inside the kernel (coef: 0-d / 1-element CUDA tensor)."""
     x, dy, g, s1, s2 = _f32c(x, "x"), _f32c(dy, "dy"), _f32c(g, "g"), _f32c(s1, "s1"), _f32c(s2, "s2")
-    S, D = g.shape
-    B, xs = (x.size(0), 0) if x.dim() == 2 else (x.size(1), x.size(1) * D)
+    S, B, D, xs = _layer_dims(x, g, s1, s2)
     if dy.shape != (S, B, D):
         raise RuntimeError(f"dy must be {(S, B, D)}, got {tuple(dy.shape)}")
     dev = x.device
+    if target is not None:
+        target, coef = _f32c(target, "target"), _f32c(coef, "coef").reshape(1)
     dx = torch.empty((S, B, D), dtype=torch.float32, device=dev) if want_dx else None
     dg = torch.empty((S, D), dtype=torch.float32, device=dev)
     ds1 = torch.empty(D, dtype=torch.float32, device=dev)
@@ -120,11 +143,12 @@ def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False):
     need = ctypes.c_size_t(0)
     _lib.check(L.whvi_layer_bwd_workspace_bytes(S, B, D, ctypes.byref(need)), "whvi_layer_bwd_workspace_bytes")
     ws = _workspace(dev, need.value)
-    with torch.cuda.device(dev), _Timed("whvi_layer_bwd_f32"):
-        rc = L.whvi_layer_bwd_f32(x.data_ptr(), xs, dy.data_ptr(), g.data_ptr(), s1.data_ptr(), s2.data_ptr(),
-                                  _ptr(dx), dg.data_ptr(), ds1.data_ptr(), ds2.data_ptr(), _ptr(dbias),
-                                  ws.data_ptr(), ws.numel(), S, B, D, _stream(dev))
-    _lib.check(rc, "whvi_layer_bwd_f32")
+    with torch.cuda.device(dev), _Timed("whvi_layer_bwd_fused_f32"):
+        rc = L.whvi_layer_bwd_fused_f32(x.data_ptr(), xs, dy.data_ptr(), g.data_ptr(), s1.data_ptr(), s2.data_ptr(),
+                                        _ptr(dx), dg.data_ptr(), ds1.data_ptr(), ds2.data_ptr(), _ptr(dbias),
+                                        ws.data_ptr(), ws.numel(), S, B, D, 1 if relu_in else 0, _ptr(target),
+                                        _ptr(coef), _stream(dev))
+    _lib.check(rc, "whvi_layer_bwd_fused_f32")
     return dx, dg, ds1, ds2, dbias
 
 
