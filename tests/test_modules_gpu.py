@@ -205,3 +205,48 @@ def test_train_and_eval_model_run_and_learn():
     model.train()
     last = float(model.loss(x[:64], y[:64], n=150))
     assert last < first
+
+
+@pytest.mark.parametrize("D,bias", [(64, False), (128, True), (1024, False)])
+def test_fused_relu_and_mnll_match_unfused(D, bias):
+    """fuse=True (ReLU and Gaussian MNLL folded into the layer kernels) must give the same
+    loss and gradients as fuse=False (every module its own op, like the reference)."""
+    S, B = 3, 37
+    torch.manual_seed(D)
+
+    def make(fuse):
+        torch.manual_seed(1)
+        m = W.WHVIRegression([W.WHVILinear(D, D, lambda_=2.0, bias=bias), torch.nn.ReLU(),
+                              W.WHVILinear(D, D, lambda_=2.0, bias=bias), torch.nn.ReLU(),
+                              W.WHVILinear(D, D, lambda_=2.0, bias=bias)], train_samples=S, sigma=0.8, fuse=fuse)
+        with torch.no_grad():
+            for name, p in m.named_parameters():
+                if name.endswith(("s1", "s2")):
+                    p.mul_(100.0 / D ** 0.5)   # O(1)-gain layers so that activations stay O(1)
+                if name.endswith("g_mu"):
+                    p.copy_(torch.randn_like(p))
+        return m.to(dev()).train()
+
+    fused, plain = make(True), make(False)
+    x = torch.randn(B, D, device=dev())
+    y = torch.randn(B, D, device=dev())
+    eps = [torch.randn(S, D, device=dev()) for _ in range(3)]
+    losses = []
+    for model in (fused, plain):
+        for layer, e in zip(model._whvi_layers(), eps):
+            layer.square_blocks()[0].inject_eps(e)
+        loss = model.loss(x, y, n=500)
+        loss.backward()
+        losses.append(loss.item())
+    assert abs(losses[0] - losses[1]) < 1e-4 * abs(losses[1])
+    scale = max(float(p.grad.abs().max()) for p in plain.parameters())
+    for (name, a), (_, b) in zip(fused.named_parameters(), plain.named_parameters()):
+        assert float((a.grad - b.grad).abs().max()) < TOL * scale, name
+    # predictions (forward()) are unaffected by the loss-side fusion
+    for model in (fused, plain):
+        for layer, e in zip(model._whvi_layers(), eps):
+            layer.square_blocks()[0].inject_eps(e)
+    with torch.no_grad():
+        pf, pp = fused(x), plain(x)
+    assert pf.shape == (B, D, S)
+    assert rel_err(pf.cpu().numpy(), pp.cpu().numpy()) < TOL

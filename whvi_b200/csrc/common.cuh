@@ -40,7 +40,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 template <class Kernel>
 inline int ensure_smem(Kernel kernel, size_t bytes, unsigned char* done_flags /*[64]*/)
 {
-    if (bytes <= 48 * 1024) return WHVI_OK;
+    if (bytes <= 40 * 1024) return WHVI_OK;  // static __shared__ of the kernel counts against the 48 KB default too
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && done_flags[dev]) return WHVI_OK;

@@ -43,6 +43,17 @@ constexpr bool seq_bit_new(int n, int c, int k, int seq, int round, int b)
     return view_has(v, c, b);
 }
 
+// Same, ignoring the transform length (for kernels that take K at run time).
+constexpr bool seq_bit_first_seen(int n, int c, int seq, int round, int b)
+{
+    for (int r = 0; r < round; ++r) {
+        const View v = get_view(n, c, seq_at(seq, r));
+        if (view_has(v, c, b)) return false;
+    }
+    const View v = get_view(n, c, seq_at(seq, round));
+    return view_has(v, c, b);
+}
+
 // ---- memory helpers ------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg_stream(const float* p)
 {
@@ -70,6 +81,34 @@ __device__ __forceinline__ void group_sync(int group)
     } else {
         asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(T) : "memory");
     }
+}
+
+// Barrier among T threads on named barrier `id` (T == 32: the threads are one warp).
+template <int T>
+__device__ __forceinline__ void role_sync(int id)
+{
+    if constexpr (T == 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(T) : "memory");
+    }
+}
+// Producer/consumer handshake between two thread sets on named barrier `id` (COUNT =
+// total threads of both sets): the producer side arrives, the consumer side waits.
+template <int COUNT>
+__device__ __forceinline__ void bar_arrive(int id)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(COUNT) : "memory");
+}
+template <int COUNT>
+__device__ __forceinline__ void bar_wait(int id)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(COUNT) : "memory");
+}
+// Ask the L2 to fetch `bytes` (multiple of 16) starting at p (16-byte aligned).
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // ---- butterflies -----------------------------------------------------------------------
@@ -102,14 +141,27 @@ __device__ __forceinline__ void bfly_stage(float (&v)[E])
     }
 }
 
-// All butterflies of round ROUND of sequence SEQ for a transform over logical bits [0,K).
-template <int N, int C, int K, int SEQ, int ROUND>
-__device__ __forceinline__ void bfly_round(float (&v)[1 << C])
+// Transform length as a template argument: KT >= 0 is log2(D) itself; KT < 0 encodes a
+// run-time length k in the closed range [lo, hi] as KT = -(32*lo + hi) (one instantiation
+// then serves a family of D; only stages on bits lo..hi-1 carry a uniform run-time guard).
+constexpr int k_family(int lo, int hi) { return -(32 * lo + hi); }
+constexpr int k_lo(int KT) { return KT >= 0 ? KT : (-KT) / 32; }
+constexpr int k_hi(int KT) { return KT >= 0 ? KT : (-KT) % 32; }
+
+// All butterflies of round ROUND of sequence SEQ for a transform over logical bits [0,k).
+template <int N, int C, int KT, int SEQ, int ROUND>
+__device__ __forceinline__ void bfly_round(float (&v)[1 << C], int k = KT)
 {
     static_for<0, C>([&](auto p_) {
         constexpr int p = decltype(p_)::value;
         constexpr int b = get_view(N, C, seq_at(SEQ, ROUND)).bit[p];
-        if constexpr (seq_bit_new(N, C, K, SEQ, ROUND, b)) bfly_stage<(1 << C), p>(v);
+        if constexpr (seq_bit_first_seen(N, C, SEQ, ROUND, b)) {
+            if constexpr (b < k_lo(KT)) {
+                bfly_stage<(1 << C), p>(v);
+            } else if constexpr (b < k_hi(KT)) {
+                if (b < k) bfly_stage<(1 << C), p>(v);
+            }
+        }
     });
 }
 

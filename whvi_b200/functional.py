@@ -153,13 +153,21 @@ def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False, relu_in
 
 
 class WHVILayerFunction(Function):
-    """y[s,b] = s1 * H(g[s] * H(s2 * x[s,b])) (+ bias) with the fused backward."""
+    """y[s,b] = s1 * H(g[s] * H(s2 * x[s,b])) (+ bias) with the fused backward.
+
+    ``relu_out``: the ReLU that follows the layer is applied inside the forward kernel.
+    ``relu_in``: the input is the output of such a fused ReLU; the backward kernel masks
+    dx by x > 0, i.e. returns the gradient w.r.t. the PRODUCER's pre-activation.  The two
+    flags are set in matching pairs by ``WHVINetwork`` (producer relu_out <-> consumer
+    relu_in), which is what makes the chain rule come out right without the ReLU ever
+    touching HBM."""
 
     @staticmethod
-    def forward(ctx, x, g, s1, s2, bias):
-        y = layer_forward_raw(x, g, s1, s2, bias)
+    def forward(ctx, x, g, s1, s2, bias, relu_out=False, relu_in=False):
+        y = layer_forward_raw(x, g, s1, s2, bias, relu_out=relu_out)
         ctx.save_for_backward(x, g, s1, s2)
         ctx.has_bias = bias is not None
+        ctx.relu_in = relu_in
         return y
 
     @staticmethod
@@ -167,14 +175,55 @@ class WHVILayerFunction(Function):
         x, g, s1, s2 = ctx.saved_tensors
         want_dx = ctx.needs_input_grad[0]
         want_db = ctx.has_bias and ctx.needs_input_grad[4]
-        dx, dg, ds1, ds2, dbias = layer_backward_raw(x, dy, g, s1, s2, want_dx=want_dx, want_dbias=want_db)
+        dx, dg, ds1, ds2, dbias = layer_backward_raw(x, dy, g, s1, s2, want_dx=want_dx, want_dbias=want_db,
+                                                     relu_in=ctx.relu_in)
         if dx is not None and x.dim() == 2:
             dx = dx.sum(dim=0)
-        return dx, dg, ds1, ds2, dbias
+        return dx, dg, ds1, ds2, dbias, None, None
 
 
-def whvi_layer(x, g, s1, s2, bias=None):
-    return WHVILayerFunction.apply(x, g, s1, s2, bias)
+def whvi_layer(x, g, s1, s2, bias=None, relu_out=False, relu_in=False):
+    return WHVILayerFunction.apply(x, g, s1, s2, bias, relu_out, relu_in)
+
+
+class WHVILayerSqErrFunction(Function):
+    """Last layer of a regression net fused with the data term of the Gaussian MNLL:
+    returns ``(y_hat, sum (y_hat - target)^2)``.  The squared-error sum is reduced inside the
+    forward kernel, and in the backward the upstream gradient 2*d_sq*(y_hat - target) is
+    formed inside the backward kernel from the saved output -- no dy tensor, no separate
+    elementwise passes (reference: src/likelihoods.py:18-29 on top of src/weights.py:87-93)."""
+
+    @staticmethod
+    def forward(ctx, x, g, s1, s2, bias, target, relu_in=False):
+        y, sq = layer_forward_raw(x, g, s1, s2, bias, target=target)
+        ctx.save_for_backward(x, g, s1, s2, y, target)
+        ctx.has_bias = bias is not None
+        ctx.relu_in = relu_in
+        ctx.set_materialize_grads(False)
+        return y, sq
+
+    @staticmethod
+    def backward(ctx, d_y, d_sq):
+        x, g, s1, s2, y, target = ctx.saved_tensors
+        want_dx = ctx.needs_input_grad[0]
+        want_db = ctx.has_bias and ctx.needs_input_grad[4]
+        if d_sq is None:
+            d_sq = torch.zeros((), device=x.device)
+        if d_y is None:   # the usual case: the predictions feed nothing but the loss
+            dx, dg, ds1, ds2, dbias = layer_backward_raw(x, y, g, s1, s2, want_dx=want_dx, want_dbias=want_db,
+                                                         relu_in=ctx.relu_in, target=target,
+                                                         coef=(2.0 * d_sq).to(torch.float32))
+        else:
+            dy = d_y + 2.0 * d_sq * (y - target)
+            dx, dg, ds1, ds2, dbias = layer_backward_raw(x, dy, g, s1, s2, want_dx=want_dx, want_dbias=want_db,
+                                                         relu_in=ctx.relu_in)
+        if dx is not None and x.dim() == 2:
+            dx = dx.sum(dim=0)
+        return dx, dg, ds1, ds2, dbias, None, None
+
+
+def whvi_layer_sqerr(x, g, s1, s2, bias, target, relu_in=False):
+    return WHVILayerSqErrFunction.apply(x, g, s1, s2, bias, target, relu_in)
 
 
 class ReparamFunction(Function):

@@ -27,6 +27,11 @@ class GaussianLikelihood(nn.Module, Likelihood):
         """
         m, n_out, n_mc = y_hat.size()
         sq = (y.reshape(m, n_out, 1) - y_hat).square().sum()
+        return self.mnll_from_sq_error(sq, m, n_out, n_mc, n)
+
+    def mnll_from_sq_error(self, sq: torch.Tensor, m: int, n_out: int, n_mc: int, n: int) -> torch.Tensor:
+        """The same estimator given sum_{b,i,s} (y - y_hat)^2 (which the fused last-layer
+        kernel reduces on the fly)."""
         count = m * n_out * n_mc
         log_prob_sum = -count * (torch.log(self.sigma) + 0.5 * math.log(2.0 * math.pi)) - 0.5 * sq / self.sigma ** 2
         return -n / (m * n_mc) * log_prob_sum

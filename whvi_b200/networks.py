@@ -28,7 +28,7 @@ except Exception:  # pragma: no cover
 
 class WHVINetwork(nn.Module, WHVI):
     def __init__(self, modules: Iterable[nn.Module], likelihood: Likelihood, train_samples=1, eval_samples=64, *,
-                 rng_mode="batched"):
+                 rng_mode="batched", fuse=True):
         """
         :param modules: modules for the underlying ``nn.Sequential``.
         :param likelihood: likelihood used in training.
@@ -38,6 +38,9 @@ class WHVINetwork(nn.Module, WHVI):
             "reference" draws ``randn(D)`` per (sample, layer, block) in the reference's loop
             order (``src/networks.py:48`` -> ``src/weights.py:180`` -> ``:92``) so that the same
             seed yields the same noise as the reference.
+        :param bool fuse: fold ``nn.ReLU`` between square WHVI layers and the Gaussian MNLL
+            after a final square WHVI layer into the layer kernels (same numbers, fewer HBM
+            round trips).  ``False`` runs every module as its own op, like the reference.
         """
         super().__init__()
         if rng_mode not in ("batched", "reference"):
@@ -47,6 +50,7 @@ class WHVINetwork(nn.Module, WHVI):
         self.train_samples = train_samples
         self.eval_samples = eval_samples
         self.rng_mode = rng_mode
+        self.fuse = fuse
         self.current_mnll = 0.0
         self.current_kl = 0.0
 
@@ -66,37 +70,79 @@ class WHVINetwork(nn.Module, WHVI):
         for b, d in zip(blocks, draws):
             b.inject_eps(torch.stack(d))
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x: (batch_size, in_dim) -> (batch_size, out_dim, n_samples)."""
-        assert x.dim() == 2, "Input shape must be (batch_size, in_dim)"
-        batch_size = x.size()[0]
-        n_samples = self.train_samples if self.training else self.eval_samples
+    @staticmethod
+    def _fusable_square(module):
+        from .weights import WHVISquarePow2Matrix
+        return (isinstance(module, WHVILinear) and isinstance(module.weight_submodule, WHVISquarePow2Matrix)
+                and module.weight_submodule.fusable)
+
+    def _run(self, x: torch.Tensor, n_samples: int, sqerr_target=None):
+        """Run the sequence once with the MC samples as a leading axis.  Returns the
+        (S, B, out) activations, or -- with ``sqerr_target`` and a fusable last layer --
+        ``(activations, sum of squared errors)`` with the reduction done in the last
+        layer's kernel.  ``[Square WHVI layer, nn.ReLU, Square WHVI layer]`` runs are executed
+        with the ReLU folded into the two kernels (``self.fuse``)."""
+        modules = list(self.sequential.children())
         layers = self._whvi_layers()
         if self.rng_mode == "reference":
             self._predraw_reference_order(n_samples)
         for layer in layers:
             layer.mc_samples = n_samples
+        sq = None
         try:
-            h = x
-            for module in self.sequential.children():
+            h, i, relu_in = x, 0, False
+            while i < len(modules):
+                module = modules[i]
+                last = i == len(modules) - 1
+                if self.fuse and self._fusable_square(module):
+                    w = module.weight_submodule
+                    relu_out = (i + 2 < len(modules) and type(modules[i + 1]) is nn.ReLU
+                                and self._fusable_square(modules[i + 2]))
+                    if last and sqerr_target is not None:
+                        h, sq = w.forward_sqerr(h, sqerr_target, relu_in=relu_in)
+                    else:
+                        h = w.forward(h, relu_out=relu_out, relu_in=relu_in)
+                    relu_in = relu_out
+                    i += 2 if relu_out else 1
+                    continue
                 if isinstance(module, WHVILinear) or h.dim() == 2:
                     h = module(h)
                 else:  # foreign module: fold the sample axis into the batch
                     S, B = h.shape[0], h.shape[1]
                     h = module(h.reshape(S * B, *h.shape[2:]))
                     h = h.reshape(S, B, *h.shape[1:])
+                i += 1
         finally:
             for layer in layers:
                 layer.mc_samples = None
         if h.dim() == 2:  # no WHVI layer introduced a sample axis: S identical predictions
             h = h.unsqueeze(0).expand(n_samples, *h.shape)
+        return (h, sq) if sqerr_target is not None else h
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: (batch_size, in_dim) -> (batch_size, out_dim, n_samples)."""
+        assert x.dim() == 2, "Input shape must be (batch_size, in_dim)"
+        batch_size = x.size()[0]
+        n_samples = self.train_samples if self.training else self.eval_samples
+        h = self._run(x, n_samples)
         predictions = h.reshape(n_samples, batch_size, -1).permute(1, 2, 0)
         assert predictions.dim() == 3
         return predictions
 
     def loss(self, x: torch.Tensor, y: torch.Tensor, n: int, ignore_kl=False) -> torch.Tensor:
-        """Negative ELBO: MNLL estimate + KL (``src/networks.py:56-69``)."""
-        self.current_mnll = self.likelihood.mnll_batch_estimate(y, self(x), n)
+        """Negative ELBO: MNLL estimate + KL (``src/networks.py:56-69``).  With a Gaussian
+        likelihood and a square WHVI layer at the end, the squared-error reduction and its
+        gradient are fused into that layer's kernels."""
+        modules = list(self.sequential.children())
+        fused = (self.fuse and isinstance(self.likelihood, GaussianLikelihood) and modules
+                 and self._fusable_square(modules[-1]) and x.dim() == 2 and y.dim() == 2
+                 and y.size(1) == modules[-1].weight_submodule.D and y.size(0) == x.size(0) and y.is_cuda)
+        if fused:
+            n_samples = self.train_samples if self.training else self.eval_samples
+            _, sq = self._run(x, n_samples, sqerr_target=y.contiguous().float())
+            self.current_mnll = self.likelihood.mnll_from_sq_error(sq, m=y.size(0), n_out=y.size(1), n_mc=n_samples, n=n)
+        else:
+            self.current_mnll = self.likelihood.mnll_batch_estimate(y, self(x), n)
         self.current_kl = self.kl
         return self.current_mnll + self.current_kl if not ignore_kl else self.current_mnll
 

@@ -123,16 +123,35 @@ class WHVISquarePow2Matrix(nn.Module):
             return 1, True
         return int(self.mc_samples), False
 
-    def sample_lrt(self, h):
-        """W h for a fresh draw of g per MC sample (local reparameterisation)."""
+    def sample_lrt(self, h, *, bias=None, relu_out=False, relu_in=False):
+        """W h for a fresh draw of g per MC sample (local reparameterisation).  The
+        keyword arguments are the kernel-side fusions (bias add, ReLU on the way out, ReLU
+        mask on the way back); they default to the reference's plain behaviour."""
         S, squeeze = self._resolve_samples(h)
         eps = self._draw_eps(S)
         if self.semantics == "reference":
             y = self._as_written(h, eps)
+            if bias is not None:
+                y = y + bias
+            if relu_out:
+                y = F.relu(y)
         else:
             g = WF.reparam(self.g_mu, self.g_rho, eps)
-            y = WF.whvi_layer(h, g, self.s1, self.s2, None)
+            y = WF.whvi_layer(h, g, self.s1, self.s2, None if bias is None else bias.reshape(-1), relu_out, relu_in)
         return y[0] if squeeze else y
+
+    @property
+    def fusable(self):
+        """True when the fused-neighbour paths (ReLU / MNLL folded into the kernels) apply."""
+        return self.semantics == "paper" and 4 <= self.D <= 8192
+
+    def forward_sqerr(self, h, target, *, relu_in=False):
+        """Forward pass fused with sum (y - target)^2 (see functional.WHVILayerSqErrFunction).
+        h: (B, D) or (S, B, D); target: (B, D).  Returns ((S, B, D) predictions, 0-d sum)."""
+        S, _ = self._resolve_samples(h)
+        g = WF.reparam(self.g_mu, self.g_rho, self._draw_eps(S))
+        bias = None if self.bias is None else self.bias.reshape(-1)
+        return WF.whvi_layer_sqerr(h, g, self.s1, self.s2, bias, target, relu_in)
 
     def _as_written(self, h, eps):
         """src/weights.py:93 per sample: h @ (w_bar(mu) + w_bar(sigma*eps)).T"""
@@ -144,13 +163,10 @@ class WHVISquarePow2Matrix(nn.Module):
             outs.append(hs @ W.T)
         return torch.stack(outs)
 
-    def forward(self, x, use_lrt=True):
+    def forward(self, x, use_lrt=True, *, relu_out=False, relu_in=False):
         """x: (batch, D) or (samples, batch, D).  ``use_lrt`` is kept for signature
         compatibility; both branches of the reference compute W x for a sampled W."""
-        y = self.sample_lrt(x)
-        if self.bias is not None:
-            y = y + self.bias
-        return y
+        return self.sample_lrt(x, bias=self.bias, relu_out=relu_out, relu_in=relu_in)
 
 
 class WHVIStackedMatrix(nn.Module):
