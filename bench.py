@@ -174,6 +174,7 @@ def run_ours(args):
     import whvi_b200 as W
     from whvi_b200 import functional as WF
     from whvi_b200 import fwht_
+    from whvi_b200.distributed import FlatGradAllReduce, shard_samples
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,8 +184,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    _, S_local = shard_samples(S_TOTAL, rank, world)
     assert S_TOTAL % world == 0
-    S_local = S_TOTAL // world
     chunk = min(args.chunk, S_local)
     assert S_local % chunk == 0
     n_chunks = S_local // chunk
@@ -194,7 +195,7 @@ def run_ours(args):
     model = W.WHVIRegression([W.WHVILinear(D, D), torch.nn.ReLU(), W.WHVILinear(D, D), torch.nn.ReLU(),
                               W.WHVILinear(D, D)], train_samples=chunk).to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    params = [p for p in model.parameters()]
+    grad_allreduce = FlatGradAllReduce(model.parameters())
     gen = torch.Generator().manual_seed(1)  # the same minibatch on every rank (MC-sample sharding)
     x_host = torch.randn(B, D, generator=gen).pin_memory()
     y_host = torch.randn(B, D, generator=gen).pin_memory()
@@ -208,11 +209,7 @@ def run_ours(args):
             loss = model.loss(x, y, n=B) * scale
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
-        if world > 1:
-            flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
-            dist.all_reduce(flat)
-            for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
-                p.grad.copy_(g)
+        grad_allreduce()  # one flat NCCL all-reduce of all parameter gradients (no-op at N = 1)
         opt.step()
         opt.zero_grad(set_to_none=True)
         return total

@@ -1,0 +1,425 @@
+// Kernel (3): the fused WHVILinear backward (see layer_fwd.cu for the math and layout notes).
+#include "layer_common.cuh"
+#include <cstdlib>
+
+namespace whvi {
+
+// ------------------------------------------------------------------------------ backward
+struct BwdArgs {
+    const float* x;
+    int64_t x_sample_stride;
+    const float* dy;       // (S,B,D) upstream gradient, or -- RESID -- the layer's saved output
+    const float* g;
+    const float* s1;
+    const float* s2;
+    float* dx;             // NULL: skip
+    float* ws;
+    int64_t sample_elems;
+    int ctas_per_sample;
+    int iters_per_group;
+    int k;                 // log2(D)
+    int relu_in;           // x is the output of a fused ReLU: dx *= (x > 0)
+    const float* target;   // RESID: (B,D); dy := coef[0] * (dy_buffer - target)  (fused Gaussian-MNLL gradient)
+    const float* coef;     // RESID: device scalar
+};
+
+// Stream-role specialised, TMA-staged backward.  Every tile is worked on by a PAIR of thread
+// sets running concurrently:
+//   X role:  t2 = H(s2*x) -> t4 = H(g*t2) -> ds1 += dy*t4 (+ dbias += dy)
+//   Y role:  dt3 = H(s1*dy) -> dt1 = H(g*dt3) -> ds2 += dt1*x, dx = s2*dt1
+//   both:    dg += dt3*t2, half of the coordinates each (exchanged through a half-stash)
+// Each role keeps one stream (32 floats per thread) and its accumulators in registers.
+// One CTA owns `iters_per_group * PAIRS` consecutive tiles of ONE sample; at the end every
+// role writes its partial sums to the workspace and a second kernel reduces them in a fixed
+// order (deterministic, no atomics).
+// workspace layout: [S][ctas_per_sample][PAIRS][4][TILE] floats: 0 = dg, 1 = ds1, 2 = ds2, 3 = dbias
+//
+// A producer warp streams the raw
+// x and dy tiles into a ring of shared-memory stages with bulk async copies (mbarrier
+// completion), NS tiles ahead of the compute roles.  Consequences:
+//   * global-load latency is off the critical path (no registers hold loads in flight);
+//   * each role reads BOTH raw tiles from shared memory (its own stream at the start, the
+//     other stream for its end product), so x and dy cross HBM->SM exactly once (an earlier
+//     register-staged variant re-read them through L2 and ~40% of those re-reads missed;
+//     profiles/r01_bwd_notes.md);
+//   * the dg accumulator is split between the roles (X: float4 slots 0..E/8-1, Y: the rest;
+//     each sends the other the half-stream it needs through a shared half-stash), which
+//     balances the register budgets at <= 112 so two CTAs (2 x 288 threads) fit per SM.
+// Shared memory per pair: NS x (x tile + dy tile) + X scratch + Y scratch + stash (1 tile).
+template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool WANT_DBIAS, bool RESID>
+__global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_tma_kernel(const BwdArgs p)
+{
+    constexpr int T = 1 << (N - C);
+    constexpr int E = 1 << C;
+    constexpr int H = E / 2;               // floats per thread per half-stream
+    constexpr int64_t TILE = int64_t(1) << N;
+    constexpr int SCR = SINGLE ? 1 : 2;      // scratch tiles per role
+    constexpr int PAIR_FLOATS = (2 * NS + 2 * SCR + 1) * int(TILE);
+    extern __shared__ float4 smem4[];
+    __shared__ uint64_t full_bar[PAIRS][NS], empty_bar[PAIRS][NS];
+    float* smem = reinterpret_cast<float*>(smem4);
+    const int k = KT >= 0 ? KT : p.k;
+    const uint32_t cmask = (1u << k) - 1u;
+    const int s = blockIdx.x / p.ctas_per_sample;
+    const int cta_in_sample = blockIdx.x % p.ctas_per_sample;
+    const float* __restrict__ xbase = p.x + int64_t(s) * p.x_sample_stride;
+    const float* __restrict__ dybase = p.dy + int64_t(s) * p.sample_elems;
+
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < PAIRS; ++q)
+            for (int st = 0; st < NS; ++st) {
+                mbar_init(&full_bar[q][st], 1);
+                mbar_init(&empty_bar[q][st], 2 * T);
+            }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto tile_of = [&](int it, int pr) -> int64_t {
+        return ((int64_t(cta_in_sample) * p.iters_per_group + it) * PAIRS + pr) * TILE;
+    };
+
+    if (threadIdx.x >= 2 * T * PAIRS) {
+        // ------------------------------------------------------------------ producer warp
+        if (threadIdx.x == 2 * T * PAIRS) {
+            for (int it = 0; it < p.iters_per_group; ++it) {
+                const int st = it % NS;
+                for (int pr = 0; pr < PAIRS; ++pr) {
+                    const int64_t e0 = tile_of(it, pr);
+                    if (e0 >= p.sample_elems) continue;
+                    if (it >= NS) mbar_wait(&empty_bar[pr][st], ((it / NS) & 1) ^ 1);
+                    const int64_t left = p.sample_elems - e0;
+                    const uint32_t bytes = static_cast<uint32_t>((left < TILE ? left : TILE) * sizeof(float));
+                    float* stage = smem + size_t(pr) * PAIR_FLOATS + size_t(st) * 2 * TILE;
+                    mbar_arrive_expect_tx(&full_bar[pr][st], 2 * bytes);
+                    bulk_g2s(stage, xbase + e0, bytes, &full_bar[pr][st]);
+                    bulk_g2s(stage + TILE, dybase + e0, bytes, &full_bar[pr][st]);
+                }
+            }
+        }
+        return;
+    }
+
+    const int role = threadIdx.x / (T * PAIRS);        // 0 = X, 1 = Y (warp-uniform)
+    const int pair = (threadIdx.x % (T * PAIRS)) / T;
+    const uint32_t tid = threadIdx.x % T;
+    float* pair_smem = smem + size_t(pair) * PAIR_FLOATS;
+    float* scratch = pair_smem + (2 * NS + SCR * role) * TILE;    // this role's transposition buffer(s)
+    float* scratch2 = scratch + (SINGLE ? 0 : TILE);
+    float* stash_t2 = pair_smem + (2 * NS + 2 * SCR) * TILE;      // X -> Y: upper half of t2
+    float* stash_d3 = stash_t2 + TILE / 2;                        // Y -> X: lower half of dt3
+    const int bar_role = 1 + 3 * pair + role;
+    const int bar_pair = 3 + 3 * pair;
+    const float* __restrict__ gs = p.g + (int64_t(s) << k);
+    float coef = 1.f;
+    if constexpr (RESID) coef = __ldg(p.coef);
+    const float relu_thr = p.relu_in ? 0.f : -INFINITY;
+
+    const uint32_t off_f = tile_thread_offset<N, C, V_FIRST>(tid);
+    const uint32_t off_l = tile_thread_offset<N, C, V_LAST>(tid);
+    const uint32_t wb_fm = transpose_writer_base<N, C, V_FIRST, V_MID>(tid);
+    const uint32_t wb_ml = transpose_writer_base<N, C, V_MID, V_LAST>(tid);
+    const uint32_t wb_lm = transpose_writer_base<N, C, V_LAST, V_MID2>(tid);
+    const uint32_t wb_mf = transpose_writer_base<N, C, V_MID2, V_FIRST>(tid);
+    float* __restrict__ slab = p.ws + ((int64_t(blockIdx.x) * PAIRS + pair) * 4) * TILE;
+    const uint32_t hs_base = tid << (C - 1);           // this thread's H floats in a half-stash
+    const uint32_t hs_swz = swz_of_tid(C - 1, tid);
+
+    // A partial tile (only at the tail of a sample) leaves stale data in the unfilled part of
+    // the stage; instead of masking every read, each thread zero-fills its own float4s beyond
+    // `left` in both raw tiles once per such tile (X and Y threads with the same tid own the
+    // same offsets and both write zeros, which is benign).
+    auto zero_tail = [&](float* stage_x, int64_t left) {
+        if (left < TILE) {
+            static_for<0, E / 4>([&](auto m_) {
+                constexpr int m = decltype(m_)::value;
+                const uint32_t off = off_f + tile_reg_offset<N, C, V_FIRST>(m);
+                if (off >= left) {
+                    *reinterpret_cast<float4*>(stage_x + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(stage_x + TILE + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            });
+        }
+    };
+    auto raw4 = [&](const float* stage_tile, uint32_t off) -> float4 {
+        return *reinterpret_cast<const float4*>(stage_tile + off);
+    };
+    // RESID: dy = coef * (saved output - target); the target tile is read from global memory
+    // (it is shared by all samples, so it stays L2-resident), zero beyond the valid part
+    auto to_dy = [&](float4 q, const float* tgt, uint32_t off, int64_t left) -> float4 {
+        if constexpr (RESID) {
+            float4 tg = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (off < left) tg = ldg4(tgt + off);
+            q = make_float4(coef * (q.x - tg.x), coef * (q.y - tg.y), coef * (q.z - tg.z), coef * (q.w - tg.w));
+        }
+        return q;
+    };
+
+    float acc_g[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) acc_g[i] = 0.f;
+
+    if (role == 0) {
+        // ------------------------------------------------------------------ X role
+        float acc_1[E];
+        float acc_b[WANT_DBIAS ? E : 1];
+#pragma unroll
+        for (int i = 0; i < E; ++i) acc_1[i] = 0.f;
+        if constexpr (WANT_DBIAS) {
+#pragma unroll
+            for (int i = 0; i < E; ++i) acc_b[i] = 0.f;
+        }
+#pragma unroll 1
+        for (int it = 0; it < p.iters_per_group; ++it) {
+            const int64_t e0 = tile_of(it, pair);
+            if (e0 >= p.sample_elems) break;
+            const int64_t left = p.sample_elems - e0;
+            const int st = it % NS;
+            float* stage_x = pair_smem + size_t(st) * 2 * TILE;
+            const float* stage_dy = stage_x + TILE;
+            const float* __restrict__ tgt = RESID ? p.target + e0 : nullptr;
+            mbar_wait(&full_bar[pair][st], (it / NS) & 1);
+            zero_tail(stage_x, left);
+            float a[E];
+            for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                const float4 q = raw4(stage_x, off);
+                const float4 w = ldg4(p.s2 + coord);
+                a[4 * m + 0] = q.x * w.x;
+                a[4 * m + 1] = q.y * w.y;
+                a[4 * m + 2] = q.z * w.z;
+                a[4 * m + 3] = q.w * w.w;
+            });
+            transform_in<N, C, KT, T, SINGLE>(a, scratch, scratch2, tid, bar_role, k, wb_fm, wb_ml);  // a = t2 (LAST)
+#pragma unroll
+            for (int jj = 0; jj < H / 4; ++jj)   // publish the upper half of t2
+                *reinterpret_cast<float4*>(stash_t2 + hs_base + ((jj ^ hs_swz) << 2)) =
+                    make_float4(a[H + 4 * jj], a[H + 4 * jj + 1], a[H + 4 * jj + 2], a[H + 4 * jj + 3]);
+            bar_wait<2 * T>(bar_pair);
+#pragma unroll
+            for (int jj = 0; jj < H / 4; ++jj) {  // dg (lower half) += dt3 * t2
+                const float4 d = *reinterpret_cast<const float4*>(stash_d3 + hs_base + ((jj ^ hs_swz) << 2));
+                acc_g[4 * jj + 0] = fmaf(d.x, a[4 * jj + 0], acc_g[4 * jj + 0]);
+                acc_g[4 * jj + 1] = fmaf(d.y, a[4 * jj + 1], acc_g[4 * jj + 1]);
+                acc_g[4 * jj + 2] = fmaf(d.z, a[4 * jj + 2], acc_g[4 * jj + 2]);
+                acc_g[4 * jj + 3] = fmaf(d.w, a[4 * jj + 3], acc_g[4 * jj + 3]);
+            }
+            bar_wait<2 * T>(bar_pair);  // both half-stashes consumed
+            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                const float4 w = ldg4(gs + coord);
+                a[4 * m + 0] *= w.x;
+                a[4 * m + 1] *= w.y;
+                a[4 * m + 2] *= w.z;
+                a[4 * m + 3] *= w.w;
+            });
+            transform_out<N, C, KT, T, SINGLE>(a, scratch, scratch2, tid, bar_role, k, wb_lm, wb_mf);  // a = t4 (FIRST)
+            for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t) {
+                constexpr int m = decltype(m_)::value;
+                const float4 q = to_dy(raw4(stage_dy, off), tgt, off, left);
+                acc_1[4 * m + 0] = fmaf(q.x, a[4 * m + 0], acc_1[4 * m + 0]);
+                acc_1[4 * m + 1] = fmaf(q.y, a[4 * m + 1], acc_1[4 * m + 1]);
+                acc_1[4 * m + 2] = fmaf(q.z, a[4 * m + 2], acc_1[4 * m + 2]);
+                acc_1[4 * m + 3] = fmaf(q.w, a[4 * m + 3], acc_1[4 * m + 3]);
+                if constexpr (WANT_DBIAS) {
+                    acc_b[4 * m + 0] += q.x;
+                    acc_b[4 * m + 1] += q.y;
+                    acc_b[4 * m + 2] += q.z;
+                    acc_b[4 * m + 3] += q.w;
+                }
+            });
+            mbar_arrive(&empty_bar[pair][st]);
+        }
+        for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t) {
+            constexpr int m = decltype(m_)::value;
+            *reinterpret_cast<float4*>(slab + TILE + off) = make_float4(acc_1[4 * m], acc_1[4 * m + 1], acc_1[4 * m + 2], acc_1[4 * m + 3]);
+            if constexpr (WANT_DBIAS)
+                *reinterpret_cast<float4*>(slab + 3 * TILE + off) = make_float4(acc_b[4 * m], acc_b[4 * m + 1], acc_b[4 * m + 2], acc_b[4 * m + 3]);
+        });
+        for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t off, uint32_t) {
+            constexpr int m = decltype(m_)::value;
+            if constexpr (m < H / 4)
+                *reinterpret_cast<float4*>(slab + off) = make_float4(acc_g[4 * m], acc_g[4 * m + 1], acc_g[4 * m + 2], acc_g[4 * m + 3]);
+        });
+    } else {
+        // ------------------------------------------------------------------ Y role
+        float acc_2[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) acc_2[i] = 0.f;
+#pragma unroll 1
+        for (int it = 0; it < p.iters_per_group; ++it) {
+            const int64_t e0 = tile_of(it, pair);
+            if (e0 >= p.sample_elems) break;
+            const int64_t left = p.sample_elems - e0;
+            const int st = it % NS;
+            float* stage_x = pair_smem + size_t(st) * 2 * TILE;
+            const float* stage_dy = stage_x + TILE;
+            const float* __restrict__ tgt = RESID ? p.target + e0 : nullptr;
+            mbar_wait(&full_bar[pair][st], (it / NS) & 1);
+            zero_tail(stage_x, left);
+            float b[E];
+            for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                const float4 q = to_dy(raw4(stage_dy, off), tgt, off, left);
+                const float4 w = ldg4(p.s1 + coord);
+                b[4 * m + 0] = q.x * w.x;
+                b[4 * m + 1] = q.y * w.y;
+                b[4 * m + 2] = q.z * w.z;
+                b[4 * m + 3] = q.w * w.w;
+            });
+            transform_in<N, C, KT, T, SINGLE>(b, scratch, scratch2, tid, bar_role, k, wb_fm, wb_ml);  // b = dt3 (LAST)
+#pragma unroll
+            for (int jj = 0; jj < H / 4; ++jj)   // publish the lower half of dt3
+                *reinterpret_cast<float4*>(stash_d3 + hs_base + ((jj ^ hs_swz) << 2)) =
+                    make_float4(b[4 * jj], b[4 * jj + 1], b[4 * jj + 2], b[4 * jj + 3]);
+            bar_wait<2 * T>(bar_pair);
+#pragma unroll
+            for (int jj = 0; jj < H / 4; ++jj) {  // dg (upper half) += dt3 * t2
+                const float4 t2 = *reinterpret_cast<const float4*>(stash_t2 + hs_base + ((jj ^ hs_swz) << 2));
+                acc_g[4 * jj + 0] = fmaf(b[H + 4 * jj + 0], t2.x, acc_g[4 * jj + 0]);
+                acc_g[4 * jj + 1] = fmaf(b[H + 4 * jj + 1], t2.y, acc_g[4 * jj + 1]);
+                acc_g[4 * jj + 2] = fmaf(b[H + 4 * jj + 2], t2.z, acc_g[4 * jj + 2]);
+                acc_g[4 * jj + 3] = fmaf(b[H + 4 * jj + 3], t2.w, acc_g[4 * jj + 3]);
+            }
+            bar_wait<2 * T>(bar_pair);
+            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                const float4 w = ldg4(gs + coord);
+                b[4 * m + 0] *= w.x;
+                b[4 * m + 1] *= w.y;
+                b[4 * m + 2] *= w.z;
+                b[4 * m + 3] *= w.w;
+            });
+            transform_out<N, C, KT, T, SINGLE>(b, scratch, scratch2, tid, bar_role, k, wb_lm, wb_mf);  // b = dt1 (FIRST)
+            const bool want_dx = p.dx != nullptr;
+            float* __restrict__ dxs = p.dx + int64_t(s) * p.sample_elems + e0;
+            for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                const float4 q = raw4(stage_x, off);
+                const float4 w = ldg4(p.s2 + coord);
+                acc_2[4 * m + 0] = fmaf(q.x, b[4 * m + 0], acc_2[4 * m + 0]);
+                acc_2[4 * m + 1] = fmaf(q.y, b[4 * m + 1], acc_2[4 * m + 1]);
+                acc_2[4 * m + 2] = fmaf(q.z, b[4 * m + 2], acc_2[4 * m + 2]);
+                acc_2[4 * m + 3] = fmaf(q.w, b[4 * m + 3], acc_2[4 * m + 3]);
+                const float4 o = make_float4(q.x > relu_thr ? b[4 * m] * w.x : 0.f, q.y > relu_thr ? b[4 * m + 1] * w.y : 0.f,
+                                             q.z > relu_thr ? b[4 * m + 2] * w.z : 0.f, q.w > relu_thr ? b[4 * m + 3] * w.w : 0.f);
+                if (want_dx && off < left) stg_stream(dxs + off, o);
+            });
+            mbar_arrive(&empty_bar[pair][st]);
+        }
+        for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t) {
+            constexpr int m = decltype(m_)::value;
+            *reinterpret_cast<float4*>(slab + 2 * TILE + off) = make_float4(acc_2[4 * m], acc_2[4 * m + 1], acc_2[4 * m + 2], acc_2[4 * m + 3]);
+        });
+        for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t off, uint32_t) {
+            constexpr int m = decltype(m_)::value;
+            if constexpr (m >= H / 4)
+                *reinterpret_cast<float4*>(slab + off) = make_float4(acc_g[4 * (m - H / 4)], acc_g[4 * (m - H / 4) + 1],
+                                                                     acc_g[4 * (m - H / 4) + 2], acc_g[4 * (m - H / 4) + 3]);
+        });
+    }
+}
+
+// Second stage: fixed-order sums of the per-group slabs.
+//   dg[s, i]  = sum over slabs of sample s, over the N/D row replicas inside a slab
+//   ds1/ds2/dbias[i] = the same over ALL slabs
+// One warp per output coordinate: lanes stride over (slab, replica) pairs, then a fixed
+// shuffle tree.  blockIdx.y < S: dg of that sample; blockIdx.y == S: ds1, ds2, dbias.
+__global__ void __launch_bounds__(256)
+layer_bwd_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dg, float* __restrict__ ds1,
+                        float* __restrict__ ds2, float* __restrict__ dbias, int S, int slabs_per_sample, int64_t tile, int D)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= D) return;
+    const int reps = static_cast<int>(tile / D);
+    const unsigned full = 0xffffffffu;
+    if (static_cast<int>(blockIdx.y) < S) {
+        const int s = blockIdx.y;
+        const int64_t terms = int64_t(slabs_per_sample) * reps;
+        float acc = 0.f;
+        for (int64_t t = lane; t < terms; t += 32) {
+            const int64_t slab = int64_t(s) * slabs_per_sample + t / reps;
+            acc += ws[(slab * 4) * tile + (t % reps) * D + i];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
+        if (lane == 0) dg[int64_t(s) * D + i] = acc;
+    } else {
+        const int64_t terms = int64_t(S) * slabs_per_sample * reps;
+        float a1 = 0.f, a2 = 0.f, ab = 0.f;
+        for (int64_t t = lane; t < terms; t += 32) {
+            const float* base = ws + ((t / reps) * 4) * tile + (t % reps) * D + i;
+            a1 += base[tile];
+            a2 += base[2 * tile];
+            if (dbias) ab += base[3 * tile];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a1 += __shfl_xor_sync(full, a1, o);
+            a2 += __shfl_xor_sync(full, a2, o);
+            ab += __shfl_xor_sync(full, ab, o);
+        }
+        if (lane == 0) {
+            ds1[i] = a1;
+            ds2[i] = a2;
+            if (dbias) dbias[i] = ab;
+        }
+    }
+}
+
+template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE>
+static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
+{
+    static unsigned char smem_ok[4][64] = {};
+    constexpr int threads = (2 << (N - C)) * PAIRS + 32;
+    constexpr size_t tile = size_t(1) << N;
+    constexpr size_t smem = sizeof(float) * (2 * NS + (SINGLE ? 2 : 4) + 1) * tile * PAIRS;
+    const int64_t D = int64_t(1) << k;
+    const int64_t tiles_per_sample = (c.B * D + int64_t(tile) - 1) / int64_t(tile);
+    const Plan plan = make_plan(c.S, tiles_per_sample, PAIRS, 148 * 4, 8);
+    const size_t need = sizeof(float) * size_t(c.S) * plan.ctas_per_sample * PAIRS * 4 * tile;
+    if (c.need_only) {
+        *c.need_only = need;
+        return WHVI_OK;
+    }
+    if (c.ws == nullptr || c.ws_bytes < need)
+        return fail(WHVI_E_WORKSPACE, "layer_bwd: workspace of %zu bytes needed, %zu given", need, c.ws_bytes);
+    const int64_t ctas = int64_t(plan.ctas_per_sample) * c.S;
+    if (ctas > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "layer_bwd: grid too large");
+    BwdArgs a{c.x, c.xs, c.dy, c.g, c.s1, c.s2, c.dx, c.ws, c.B * D, plan.ctas_per_sample, plan.iters_per_group, k,
+              c.relu_in, c.target, c.coef};
+    auto go = [&](auto kernel, int slot) -> int {
+        if (int rc = ensure_smem(kernel, smem, smem_ok[slot])) return rc;
+        kernel<<<static_cast<unsigned>(ctas), threads, smem, stream>>>(a);
+        return check_launch("layer_bwd_tma_kernel");
+    };
+    const bool db = c.dbias != nullptr, rs = c.target != nullptr;
+    int rc;
+    if (db && rs) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, true, true>, 0);
+    else if (db) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, true, false>, 1);
+    else if (rs) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, false, true>, 2);
+    else rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, false, false>, 3);
+    if (rc) return rc;
+    const int warps = 8;
+    dim3 rgrid(static_cast<unsigned>((D + warps - 1) / warps), static_cast<unsigned>(c.S + 1));
+    layer_bwd_reduce_kernel<<<rgrid, warps * 32, 0, stream>>>(c.ws, c.dg, c.ds1, c.ds2, c.dbias, static_cast<int>(c.S),
+                                                              plan.ctas_per_sample * PAIRS, int64_t(tile), static_cast<int>(D));
+    return check_launch("layer_bwd_reduce_kernel");
+}
+
+int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream)
+{
+    const int k = ilog2(D);
+    // TMA-staged kernels: one CTA per SM (<= 144 KB shared memory at D <= 4096, 224 KB at
+    // D = 8192), NS = 2 stages, ping-pong transposition buffers where they fit
+    if (k >= 2 && k <= 6) return launch_bwd_tma_cfg<10, 5, k_family(2, 6), 4, 1, 2, false>(c, k, stream);
+    if (k >= 7 && k <= 9) return launch_bwd_tma_cfg<10, 5, k_family(7, 9), 4, 1, 2, false>(c, k, stream);
+    if (k == 10) return launch_bwd_tma_cfg<10, 5, 10, 4, 1, 2, false>(c, k, stream);
+    if (k == 11) return launch_bwd_tma_cfg<11, 5, 11, 2, 1, 2, false>(c, k, stream);
+    if (k == 12) return launch_bwd_tma_cfg<12, 5, 12, 1, 1, 2, false>(c, k, stream);
+    if (k == 13) return launch_bwd_tma_cfg<13, 5, 13, 1, 1, 2, true>(c, k, stream);
+    return fail(WHVI_E_SHAPE, "layer_bwd: D = %lld unsupported (4 <= D <= 8192)", (long long)D);
+}
+
+}  // namespace whvi
