@@ -20,6 +20,9 @@ def main():
     ap.add_argument("--dims", default="16,128,1024,2048,4096,8192")
     ap.add_argument("--samples", type=int, default=16)
     ap.add_argument("--out", default="")
+    ap.add_argument("--mode", default="plain", choices=["plain", "shared", "target"],
+                    help="plain: per-sample x; shared: one (B,D) x block for all samples (first layer); "
+                         "target: fused MNLL residual (last layer)")
     args = ap.parse_args()
     n = 1 << args.log2n
     dev = torch.device("cuda:0")
@@ -36,8 +39,19 @@ def main():
         x, dy, y = xflat.view(S, B, D), dyflat.view(S, B, D), yflat.view(S, B, D)
         g = torch.randn(S, D, device=dev)
         s1, s2 = torch.randn(D, device=dev), torch.randn(D, device=dev)
-        f_med, _ = time_op(lambda: F.layer_forward_raw(x, g, s1, s2, out=y))
-        b_med, _ = time_op(lambda: F.layer_backward_raw(x, dy, g, s1, s2, want_dx=True), warmup=3, iters=10)
+        if args.mode == "shared":
+            xs = x[0].contiguous()
+            f_med, _ = time_op(lambda: F.layer_forward_raw(xs, g, s1, s2, out=y, relu_out=True))
+            b_med, _ = time_op(lambda: F.layer_backward_raw(xs, dy, g, s1, s2, want_dx=False), warmup=3, iters=10)
+        elif args.mode == "target":
+            tgt = torch.randn(B, D, device=dev)
+            coef = torch.tensor(0.5, device=dev)
+            f_med, _ = time_op(lambda: F.layer_forward_raw(x, g, s1, s2, out=y, target=tgt))
+            b_med, _ = time_op(lambda: F.layer_backward_raw(x, dy, g, s1, s2, want_dx=True, relu_in=True, target=tgt,
+                                                            coef=coef), warmup=3, iters=10)
+        else:
+            f_med, _ = time_op(lambda: F.layer_forward_raw(x, g, s1, s2, out=y))
+            b_med, _ = time_op(lambda: F.layer_backward_raw(x, dy, g, s1, s2, want_dx=True), warmup=3, iters=10)
         rows = S * B
         rec = {"D": D, "S": S, "B": B, "fwd_ms": f_med, "bwd_ms": b_med, "fwd_gbs": 8.0 * n / f_med / 1e6,
                "bwd_gbs": 12.0 * n / b_med / 1e6, "fwdbwd_rows_per_s": rows / ((f_med + b_med) * 1e-3),

@@ -15,6 +15,7 @@ struct BwdArgs {
     float* dx;             // NULL: skip
     float* ws;
     int64_t sample_elems;
+    int n_samples;          // S
     int ctas_per_sample;
     int iters_per_group;
     int k;                 // log2(D)
@@ -54,14 +55,18 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
     constexpr int H = E / 2;               // floats per thread per half-stream
     constexpr int64_t TILE = int64_t(1) << N;
     constexpr int SCR = SINGLE ? 1 : 2;      // scratch tiles per role
-    constexpr int PAIR_FLOATS = (2 * NS + 2 * SCR + 1) * int(TILE);
+    // RESID: the target tile rides in the stage too (third tile) when shared memory allows
+    constexpr bool STAGE_TGT = RESID && (3 * NS + 2 * SCR + 1) * sizeof(float) * size_t(TILE) * PAIRS <= 200 * 1024;
+    constexpr int SPT = STAGE_TGT ? 3 : 2;   // tiles per stage
+    constexpr int PAIR_FLOATS = (SPT * NS + 2 * SCR + 1) * int(TILE);
     extern __shared__ float4 smem4[];
     __shared__ uint64_t full_bar[PAIRS][NS], empty_bar[PAIRS][NS];
     float* smem = reinterpret_cast<float*>(smem4);
     const int k = KT >= 0 ? KT : p.k;
     const uint32_t cmask = (1u << k) - 1u;
-    const int s = blockIdx.x / p.ctas_per_sample;
-    const int cta_in_sample = blockIdx.x % p.ctas_per_sample;
+    // sample-minor CTA order (see layer_fwd.cu): shared x / target tiles are reused out of L2
+    const int s = blockIdx.x % p.n_samples;
+    const int cta_in_sample = blockIdx.x / p.n_samples;
     const float* __restrict__ xbase = p.x + int64_t(s) * p.x_sample_stride;
     const float* __restrict__ dybase = p.dy + int64_t(s) * p.sample_elems;
 
@@ -90,10 +95,11 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
                     if (it >= NS) mbar_wait(&empty_bar[pr][st], ((it / NS) & 1) ^ 1);
                     const int64_t left = p.sample_elems - e0;
                     const uint32_t bytes = static_cast<uint32_t>((left < TILE ? left : TILE) * sizeof(float));
-                    float* stage = smem + size_t(pr) * PAIR_FLOATS + size_t(st) * 2 * TILE;
-                    mbar_arrive_expect_tx(&full_bar[pr][st], 2 * bytes);
+                    float* stage = smem + size_t(pr) * PAIR_FLOATS + size_t(st) * SPT * TILE;
+                    mbar_arrive_expect_tx(&full_bar[pr][st], SPT * bytes);
                     bulk_g2s(stage, xbase + e0, bytes, &full_bar[pr][st]);
                     bulk_g2s(stage + TILE, dybase + e0, bytes, &full_bar[pr][st]);
+                    if constexpr (STAGE_TGT) bulk_g2s(stage + 2 * TILE, p.target + e0, bytes, &full_bar[pr][st]);
                 }
             }
         }
@@ -104,9 +110,9 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
     const int pair = (threadIdx.x % (T * PAIRS)) / T;
     const uint32_t tid = threadIdx.x % T;
     float* pair_smem = smem + size_t(pair) * PAIR_FLOATS;
-    float* scratch = pair_smem + (2 * NS + SCR * role) * TILE;    // this role's transposition buffer(s)
+    float* scratch = pair_smem + (SPT * NS + SCR * role) * TILE;  // this role's transposition buffer(s)
     float* scratch2 = scratch + (SINGLE ? 0 : TILE);
-    float* stash_t2 = pair_smem + (2 * NS + 2 * SCR) * TILE;      // X -> Y: upper half of t2
+    float* stash_t2 = pair_smem + (SPT * NS + 2 * SCR) * TILE;    // X -> Y: upper half of t2
     float* stash_d3 = stash_t2 + TILE / 2;                        // Y -> X: lower half of dt3
     const int bar_role = 1 + 3 * pair + role;
     const int bar_pair = 3 + 3 * pair;
@@ -121,7 +127,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
     const uint32_t wb_ml = transpose_writer_base<N, C, V_MID, V_LAST>(tid);
     const uint32_t wb_lm = transpose_writer_base<N, C, V_LAST, V_MID2>(tid);
     const uint32_t wb_mf = transpose_writer_base<N, C, V_MID2, V_FIRST>(tid);
-    float* __restrict__ slab = p.ws + ((int64_t(blockIdx.x) * PAIRS + pair) * 4) * TILE;
+    float* __restrict__ slab = p.ws + (((int64_t(s) * p.ctas_per_sample + cta_in_sample) * PAIRS + pair) * 4) * TILE;
     const uint32_t hs_base = tid << (C - 1);           // this thread's H floats in a half-stash
     const uint32_t hs_swz = swz_of_tid(C - 1, tid);
 
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
                 if (off >= left) {
                     *reinterpret_cast<float4*>(stage_x + off) = make_float4(0.f, 0.f, 0.f, 0.f);
                     *reinterpret_cast<float4*>(stage_x + TILE + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if constexpr (STAGE_TGT) *reinterpret_cast<float4*>(stage_x + 2 * TILE + off) = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             });
         }
@@ -149,7 +156,11 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
     auto to_dy = [&](float4 q, const float* tgt, uint32_t off, int64_t left) -> float4 {
         if constexpr (RESID) {
             float4 tg = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (off < left) tg = ldg4(tgt + off);
+            if constexpr (STAGE_TGT) {
+                tg = *reinterpret_cast<const float4*>(tgt + off);  // tgt = the staged target tile
+            } else if (left >= TILE || off < left) {
+                tg = ldg4(tgt + off);
+            }
             q = make_float4(coef * (q.x - tg.x), coef * (q.y - tg.y), coef * (q.z - tg.z), coef * (q.w - tg.w));
         }
         return q;
@@ -175,9 +186,9 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
             if (e0 >= p.sample_elems) break;
             const int64_t left = p.sample_elems - e0;
             const int st = it % NS;
-            float* stage_x = pair_smem + size_t(st) * 2 * TILE;
+            float* stage_x = pair_smem + size_t(st) * SPT * TILE;
             const float* stage_dy = stage_x + TILE;
-            const float* __restrict__ tgt = RESID ? p.target + e0 : nullptr;
+            const float* tgt = STAGE_TGT ? stage_x + 2 * TILE : (RESID ? p.target + e0 : nullptr);
             mbar_wait(&full_bar[pair][st], (it / NS) & 1);
             zero_tail(stage_x, left);
             float a[E];
@@ -185,10 +196,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
                 constexpr int m = decltype(m_)::value;
                 const float4 q = raw4(stage_x, off);
                 const float4 w = ldg4(p.s2 + coord);
-                a[4 * m + 0] = q.x * w.x;
-                a[4 * m + 1] = q.y * w.y;
-                a[4 * m + 2] = q.z * w.z;
-                a[4 * m + 3] = q.w * w.w;
+                mul4(a + 4 * m, q, w);
             });
             transform_in<N, C, KT, T, SINGLE>(a, scratch, scratch2, tid, bar_role, k, wb_fm, wb_ml);  // a = t2 (LAST)
 #pragma unroll
@@ -199,28 +207,19 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
 #pragma unroll
             for (int jj = 0; jj < H / 4; ++jj) {  // dg (lower half) += dt3 * t2
                 const float4 d = *reinterpret_cast<const float4*>(stash_d3 + hs_base + ((jj ^ hs_swz) << 2));
-                acc_g[4 * jj + 0] = fmaf(d.x, a[4 * jj + 0], acc_g[4 * jj + 0]);
-                acc_g[4 * jj + 1] = fmaf(d.y, a[4 * jj + 1], acc_g[4 * jj + 1]);
-                acc_g[4 * jj + 2] = fmaf(d.z, a[4 * jj + 2], acc_g[4 * jj + 2]);
-                acc_g[4 * jj + 3] = fmaf(d.w, a[4 * jj + 3], acc_g[4 * jj + 3]);
+                fma4(acc_g + 4 * jj, d, a + 4 * jj);
             }
             bar_wait<2 * T>(bar_pair);  // both half-stashes consumed
             for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
                 const float4 w = ldg4(gs + coord);
-                a[4 * m + 0] *= w.x;
-                a[4 * m + 1] *= w.y;
-                a[4 * m + 2] *= w.z;
-                a[4 * m + 3] *= w.w;
+                scale4(a + 4 * m, w);
             });
             transform_out<N, C, KT, T, SINGLE>(a, scratch, scratch2, tid, bar_role, k, wb_lm, wb_mf);  // a = t4 (FIRST)
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t) {
                 constexpr int m = decltype(m_)::value;
                 const float4 q = to_dy(raw4(stage_dy, off), tgt, off, left);
-                acc_1[4 * m + 0] = fmaf(q.x, a[4 * m + 0], acc_1[4 * m + 0]);
-                acc_1[4 * m + 1] = fmaf(q.y, a[4 * m + 1], acc_1[4 * m + 1]);
-                acc_1[4 * m + 2] = fmaf(q.z, a[4 * m + 2], acc_1[4 * m + 2]);
-                acc_1[4 * m + 3] = fmaf(q.w, a[4 * m + 3], acc_1[4 * m + 3]);
+                fma4(acc_1 + 4 * m, q, a + 4 * m);
                 if constexpr (WANT_DBIAS) {
                     acc_b[4 * m + 0] += q.x;
                     acc_b[4 * m + 1] += q.y;
@@ -252,9 +251,9 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
             if (e0 >= p.sample_elems) break;
             const int64_t left = p.sample_elems - e0;
             const int st = it % NS;
-            float* stage_x = pair_smem + size_t(st) * 2 * TILE;
+            float* stage_x = pair_smem + size_t(st) * SPT * TILE;
             const float* stage_dy = stage_x + TILE;
-            const float* __restrict__ tgt = RESID ? p.target + e0 : nullptr;
+            const float* tgt = STAGE_TGT ? stage_x + 2 * TILE : (RESID ? p.target + e0 : nullptr);
             mbar_wait(&full_bar[pair][st], (it / NS) & 1);
             zero_tail(stage_x, left);
             float b[E];
@@ -262,10 +261,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
                 constexpr int m = decltype(m_)::value;
                 const float4 q = to_dy(raw4(stage_dy, off), tgt, off, left);
                 const float4 w = ldg4(p.s1 + coord);
-                b[4 * m + 0] = q.x * w.x;
-                b[4 * m + 1] = q.y * w.y;
-                b[4 * m + 2] = q.z * w.z;
-                b[4 * m + 3] = q.w * w.w;
+                mul4(b + 4 * m, q, w);
             });
             transform_in<N, C, KT, T, SINGLE>(b, scratch, scratch2, tid, bar_role, k, wb_fm, wb_ml);  // b = dt3 (LAST)
 #pragma unroll
@@ -276,19 +272,13 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
 #pragma unroll
             for (int jj = 0; jj < H / 4; ++jj) {  // dg (upper half) += dt3 * t2
                 const float4 t2 = *reinterpret_cast<const float4*>(stash_t2 + hs_base + ((jj ^ hs_swz) << 2));
-                acc_g[4 * jj + 0] = fmaf(b[H + 4 * jj + 0], t2.x, acc_g[4 * jj + 0]);
-                acc_g[4 * jj + 1] = fmaf(b[H + 4 * jj + 1], t2.y, acc_g[4 * jj + 1]);
-                acc_g[4 * jj + 2] = fmaf(b[H + 4 * jj + 2], t2.z, acc_g[4 * jj + 2]);
-                acc_g[4 * jj + 3] = fmaf(b[H + 4 * jj + 3], t2.w, acc_g[4 * jj + 3]);
+                fma4(acc_g + 4 * jj, t2, b + H + 4 * jj);
             }
             bar_wait<2 * T>(bar_pair);
             for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
                 const float4 w = ldg4(gs + coord);
-                b[4 * m + 0] *= w.x;
-                b[4 * m + 1] *= w.y;
-                b[4 * m + 2] *= w.z;
-                b[4 * m + 3] *= w.w;
+                scale4(b + 4 * m, w);
             });
             transform_out<N, C, KT, T, SINGLE>(b, scratch, scratch2, tid, bar_role, k, wb_lm, wb_mf);  // b = dt1 (FIRST)
             const bool want_dx = p.dx != nullptr;
@@ -297,13 +287,10 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
                 constexpr int m = decltype(m_)::value;
                 const float4 q = raw4(stage_x, off);
                 const float4 w = ldg4(p.s2 + coord);
-                acc_2[4 * m + 0] = fmaf(q.x, b[4 * m + 0], acc_2[4 * m + 0]);
-                acc_2[4 * m + 1] = fmaf(q.y, b[4 * m + 1], acc_2[4 * m + 1]);
-                acc_2[4 * m + 2] = fmaf(q.z, b[4 * m + 2], acc_2[4 * m + 2]);
-                acc_2[4 * m + 3] = fmaf(q.w, b[4 * m + 3], acc_2[4 * m + 3]);
+                fma4(acc_2 + 4 * m, q, b + 4 * m);
                 const float4 o = make_float4(q.x > relu_thr ? b[4 * m] * w.x : 0.f, q.y > relu_thr ? b[4 * m + 1] * w.y : 0.f,
                                              q.z > relu_thr ? b[4 * m + 2] * w.z : 0.f, q.w > relu_thr ? b[4 * m + 3] * w.w : 0.f);
-                if (want_dx && off < left) stg_stream(dxs + off, o);
+                if (want_dx && (left >= TILE || off < left)) stg_stream(dxs + off, o);
             });
             mbar_arrive(&empty_bar[pair][st]);
         }
@@ -374,7 +361,9 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     static unsigned char smem_ok[4][64] = {};
     constexpr int threads = (2 << (N - C)) * PAIRS + 32;
     constexpr size_t tile = size_t(1) << N;
-    constexpr size_t smem = sizeof(float) * (2 * NS + (SINGLE ? 2 : 4) + 1) * tile * PAIRS;
+    constexpr size_t smem_plain = sizeof(float) * (2 * NS + (SINGLE ? 2 : 4) + 1) * tile * PAIRS;
+    constexpr size_t smem_tgt = sizeof(float) * (3 * NS + (SINGLE ? 2 : 4) + 1) * tile * PAIRS;  // RESID, target staged
+    const size_t smem = (c.target != nullptr && smem_tgt <= 200 * 1024) ? smem_tgt : smem_plain;
     const int64_t D = int64_t(1) << k;
     const int64_t tiles_per_sample = (c.B * D + int64_t(tile) - 1) / int64_t(tile);
     const Plan plan = make_plan(c.S, tiles_per_sample, PAIRS, 148 * 4, 8);
@@ -387,7 +376,7 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
         return fail(WHVI_E_WORKSPACE, "layer_bwd: workspace of %zu bytes needed, %zu given", need, c.ws_bytes);
     const int64_t ctas = int64_t(plan.ctas_per_sample) * c.S;
     if (ctas > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "layer_bwd: grid too large");
-    BwdArgs a{c.x, c.xs, c.dy, c.g, c.s1, c.s2, c.dx, c.ws, c.B * D, plan.ctas_per_sample, plan.iters_per_group, k,
+    BwdArgs a{c.x, c.xs, c.dy, c.g, c.s1, c.s2, c.dx, c.ws, c.B * D, static_cast<int>(c.S), plan.ctas_per_sample, plan.iters_per_group, k,
               c.relu_in, c.target, c.coef};
     auto go = [&](auto kernel, int slot) -> int {
         if (int rc = ensure_smem(kernel, smem, smem_ok[slot])) return rc;

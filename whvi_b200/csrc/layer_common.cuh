@@ -67,6 +67,29 @@ __device__ __forceinline__ void for_each_vec(uint32_t toff, uint32_t cmask, F&& 
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// Packed fp32x2 helpers on 4 consecutive registers (FFMA2 / FMUL2: half the issue slots).
+// acc[0..3] += q * v[0..3]
+__device__ __forceinline__ void fma4(float* acc, const float4& q, const float* v)
+{
+    const float2 r0 = __ffma2_rn(make_float2(q.x, q.y), make_float2(v[0], v[1]), make_float2(acc[0], acc[1]));
+    const float2 r1 = __ffma2_rn(make_float2(q.z, q.w), make_float2(v[2], v[3]), make_float2(acc[2], acc[3]));
+    acc[0] = r0.x;
+    acc[1] = r0.y;
+    acc[2] = r1.x;
+    acc[3] = r1.y;
+}
+// v[0..3] = q * w   /   v[0..3] *= w
+__device__ __forceinline__ void mul4(float* v, const float4& q, const float4& w)
+{
+    const float2 r0 = __fmul2_rn(make_float2(q.x, q.y), make_float2(w.x, w.y));
+    const float2 r1 = __fmul2_rn(make_float2(q.z, q.w), make_float2(w.z, w.w));
+    v[0] = r0.x;
+    v[1] = r0.y;
+    v[2] = r1.x;
+    v[3] = r1.y;
+}
+__device__ __forceinline__ void scale4(float* v, const float4& w) { mul4(v, make_float4(v[0], v[1], v[2], v[3]), w); }
+
 // ---- g in shared memory, in the MID view's physical order restricted to coordinates, so
 // that the multiply in the middle of the 2-view kernels reads conflict-free float4s --------
 template <int N, int C>

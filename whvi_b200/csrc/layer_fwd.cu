@@ -28,6 +28,7 @@ struct FwdArgs {
     const float* bias;
     float* y;
     int64_t sample_elems;  // B * D
+    int n_samples;          // S
     int ctas_per_sample;
     int iters_per_group;
     int k;                  // log2(D)
@@ -57,8 +58,11 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
     const int bar = group + 1;
     const int k = KT >= 0 ? KT : a.k;
     const uint32_t cmask = (1u << k) - 1u;
-    const int s = blockIdx.x / a.ctas_per_sample;
-    const int cta_in_sample = blockIdx.x % a.ctas_per_sample;
+    // sample-minor CTA order: the S CTAs working on the same tile range of different samples
+    // are neighbours in launch order, so sample-independent operands (a shared x block, the
+    // MNLL target) come from DRAM once and hit L2 for the other S-1 samples
+    const int s = blockIdx.x % a.n_samples;
+    const int cta_in_sample = blockIdx.x / a.n_samples;
     const float* __restrict__ gs = a.g + (int64_t(s) << k);
     float* gt = smem;  // ROUNDS == 2 only
     float* bufA = smem + (ROUNDS == 2 ? TILE : 0) + size_t(group) * BUFS * TILE;
@@ -96,20 +100,14 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
             float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
             if (off < left) q = ldg_stream(xs + off);
             const float4 w = ldg4(a.s2 + coord);
-            v[4 * m + 0] = q.x * w.x;
-            v[4 * m + 1] = q.y * w.y;
-            v[4 * m + 2] = q.z * w.z;
-            v[4 * m + 3] = q.w * w.w;
+            mul4(v + 4 * m, q, w);
         });
         if constexpr (ROUNDS == 3) {
             transform_in<N, C, KT, T, BUFS == 1>(v, bufA, bufB, tid, bar, k, wb_fm, wb_ml);
             for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
                 const float4 w = ldg4(gs + coord);
-                v[4 * m + 0] *= w.x;
-                v[4 * m + 1] *= w.y;
-                v[4 * m + 2] *= w.z;
-                v[4 * m + 3] *= w.w;
+                scale4(v + 4 * m, w);
             });
             transform_out<N, C, KT, T, BUFS == 1>(v, bufA, bufB, tid, bar, k, wb_lm, wb_mf);
         } else {
@@ -121,10 +119,7 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
             bfly_round<N, C, KT, SEQ2_IN, 1>(v, k);
             gtab_for_each<N, C>(gt, gbase, [&](auto j_, const float4 w) {
                 constexpr int j = decltype(j_)::value;
-                v[4 * j + 0] *= w.x;
-                v[4 * j + 1] *= w.y;
-                v[4 * j + 2] *= w.z;
-                v[4 * j + 3] *= w.w;
+                scale4(v + 4 * j, w);
             });
             bfly_round<N, C, KT, SEQ2_OUT, 0>(v, k);
             if constexpr (BUFS == 1) role_sync<T>(bar);
@@ -150,7 +145,9 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
             o.w = fmaxf(o.w, relu_floor);
             if (off < left) {
                 if constexpr (HAS_TARGET) {
-                    const float4 tg = ldg4(a.target + e0 + off);
+                    // streaming load: the target must not evict s1/s2 from the small L1 that is
+                    // left next to 192 KB of shared memory
+                    const float4 tg = ldg_stream(a.target + e0 + off);
                     const float d0 = o.x - tg.x, d1 = o.y - tg.y, d2 = o.z - tg.z, d3 = o.w - tg.w;
                     sq = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, sq))));
                 }
@@ -192,7 +189,7 @@ static int launch_fwd_cfg(const LayerFwdCall& c, int k, cudaStream_t stream)
         return WHVI_OK;
     }
     if (ctas > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "layer_fwd: grid too large");
-    FwdArgs a{c.x, c.xs, c.g, c.s1, c.s2, c.bias, c.y, c.B * D, plan.ctas_per_sample, plan.iters_per_group, k,
+    FwdArgs a{c.x, c.xs, c.g, c.s1, c.s2, c.bias, c.y, c.B * D, static_cast<int>(c.S), plan.ctas_per_sample, plan.iters_per_group, k,
               c.relu_out, c.target, c.sq_partials};
     auto go = [&](auto kernel, int slot) -> int {
         if (int rc = ensure_smem(kernel, smem, smem_ok[slot])) return rc;
