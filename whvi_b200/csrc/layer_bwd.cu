@@ -35,7 +35,7 @@ struct BwdArgs {
 // order (deterministic, no atomics).
 // workspace layout: [S][ctas_per_sample][PAIRS][4][TILE] floats: 0 = dg, 1 = ds1, 2 = ds2, 3 = dbias
 //
-// A producer warp streams the raw
+// One elected thread per pair streams the raw
 // x and dy tiles into a ring of shared-memory stages with bulk async copies (mbarrier
 // completion), NS tiles ahead of the compute roles.  Consequences:
 //   * global-load latency is off the critical path (no registers hold loads in flight);
@@ -48,7 +48,7 @@ struct BwdArgs {
 //     balances the register budgets at <= 112 so two CTAs (2 x 288 threads) fit per SM.
 // Shared memory per pair: NS x (x tile + dy tile) + X scratch + Y scratch + stash (1 tile).
 template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool WANT_DBIAS, bool RESID>
-__global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_tma_kernel(const BwdArgs p)
+__global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_kernel(const BwdArgs p)
 {
     constexpr int T = 1 << (N - C);
     constexpr int E = 1 << C;
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
     constexpr int64_t TILE = int64_t(1) << N;
     constexpr int SCR = SINGLE ? 1 : 2;      // scratch tiles per role
     // RESID: the target tile rides in the stage too (third tile) when shared memory allows
+    constexpr bool LEAN = false;  // (a 2-CTA/SM variant with smem accumulators measured slower; profiles/r01_bwd_notes.md)
     constexpr bool STAGE_TGT = RESID && (3 * NS + 2 * SCR + 1) * sizeof(float) * size_t(TILE) * PAIRS <= 200 * 1024;
     constexpr int SPT = STAGE_TGT ? 3 : 2;   // tiles per stage
     constexpr int PAIR_FLOATS = (SPT * NS + 2 * SCR + 1) * int(TILE);
@@ -84,27 +85,25 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
         return ((int64_t(cta_in_sample) * p.iters_per_group + it) * PAIRS + pr) * TILE;
     };
 
-    if (threadIdx.x >= 2 * T * PAIRS) {
-        // ------------------------------------------------------------------ producer warp
-        if (threadIdx.x == 2 * T * PAIRS) {
-            for (int it = 0; it < p.iters_per_group; ++it) {
-                const int st = it % NS;
-                for (int pr = 0; pr < PAIRS; ++pr) {
-                    const int64_t e0 = tile_of(it, pr);
-                    if (e0 >= p.sample_elems) continue;
-                    if (it >= NS) mbar_wait(&empty_bar[pr][st], ((it / NS) & 1) ^ 1);
-                    const int64_t left = p.sample_elems - e0;
-                    const uint32_t bytes = static_cast<uint32_t>((left < TILE ? left : TILE) * sizeof(float));
-                    float* stage = smem + size_t(pr) * PAIR_FLOATS + size_t(st) * SPT * TILE;
-                    mbar_arrive_expect_tx(&full_bar[pr][st], SPT * bytes);
-                    bulk_g2s(stage, xbase + e0, bytes, &full_bar[pr][st]);
-                    bulk_g2s(stage + TILE, dybase + e0, bytes, &full_bar[pr][st]);
-                    if constexpr (STAGE_TGT) bulk_g2s(stage + 2 * TILE, p.target + e0, bytes, &full_bar[pr][st]);
-                }
-            }
-        }
-        return;
-    }
+    // In-band producer: thread 0 of each pair's X role issues the bulk copies for tile `it`
+    // (both raw tiles, plus the target tile when staged) into stage it % NS.  It is called
+    // one tile ahead; the wait on `empty` is for the other role to have finished tile it - NS,
+    // which it does without depending on this thread (no deadlock), and this role would have
+    // to wait for the other at the next pair barrier anyway.
+    auto issue_tile = [&](int it, int pr) {
+        if (it >= p.iters_per_group) return;
+        const int64_t e0 = tile_of(it, pr);
+        if (e0 >= p.sample_elems) return;
+        const int st = it % NS;
+        if (it >= NS) mbar_wait(&empty_bar[pr][st], ((it / NS) & 1) ^ 1);
+        const int64_t left = p.sample_elems - e0;
+        const uint32_t bytes = static_cast<uint32_t>((left < TILE ? left : TILE) * sizeof(float));
+        float* stage = smem + size_t(pr) * PAIR_FLOATS + size_t(st) * SPT * TILE;
+        mbar_arrive_expect_tx(&full_bar[pr][st], SPT * bytes);
+        bulk_g2s(stage, xbase + e0, bytes, &full_bar[pr][st]);
+        bulk_g2s(stage + TILE, dybase + e0, bytes, &full_bar[pr][st]);
+        if constexpr (STAGE_TGT) bulk_g2s(stage + 2 * TILE, p.target + e0, bytes, &full_bar[pr][st]);
+    };
 
     const int role = threadIdx.x / (T * PAIRS);        // 0 = X, 1 = Y (warp-uniform)
     const int pair = (threadIdx.x % (T * PAIRS)) / T;
@@ -112,8 +111,10 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
     float* pair_smem = smem + size_t(pair) * PAIR_FLOATS;
     float* scratch = pair_smem + (SPT * NS + SCR * role) * TILE;  // this role's transposition buffer(s)
     float* scratch2 = scratch + (SINGLE ? 0 : TILE);
-    float* stash_t2 = pair_smem + (SPT * NS + 2 * SCR) * TILE;    // X -> Y: upper half of t2
-    float* stash_d3 = stash_t2 + TILE / 2;                        // Y -> X: lower half of dt3
+    // half-stashes: X -> Y upper half of t2, Y -> X lower half of dt3
+    float* stash_t2 = LEAN ? pair_smem + (SPT * NS) * TILE : pair_smem + (SPT * NS + 2 * SCR) * TILE;
+    float* stash_d3 = LEAN ? pair_smem + (SPT * NS + SCR) * TILE : stash_t2 + TILE / 2;
+    float* acc2_smem = pair_smem + (SPT * NS + 2 * SCR) * TILE + (tid << 2);  // LEAN: slot m at + m * 4 * T
     const int bar_role = 1 + 3 * pair + role;
     const int bar_pair = 3 + 3 * pair;
     const float* __restrict__ gs = p.g + (int64_t(s) << k);
@@ -180,6 +181,8 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
 #pragma unroll
             for (int i = 0; i < E; ++i) acc_b[i] = 0.f;
         }
+        if (tid == 0)
+            for (int i = 0; i < NS - 1; ++i) issue_tile(i, pair);
 #pragma unroll 1
         for (int it = 0; it < p.iters_per_group; ++it) {
             const int64_t e0 = tile_of(it, pair);
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
             float* stage_x = pair_smem + size_t(st) * SPT * TILE;
             const float* stage_dy = stage_x + TILE;
             const float* tgt = STAGE_TGT ? stage_x + 2 * TILE : (RESID ? p.target + e0 : nullptr);
+            if (tid == 0) issue_tile(it + NS - 1, pair);
             mbar_wait(&full_bar[pair][st], (it / NS) & 1);
             zero_tail(stage_x, left);
             float a[E];
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
                 mul4(a + 4 * m, q, w);
             });
             transform_in<N, C, KT, T, SINGLE>(a, scratch, scratch2, tid, bar_role, k, wb_fm, wb_ml);  // a = t2 (LAST)
+            if constexpr (LEAN) role_sync<T>(bar_role);  // scratch (now the stash) is no longer being read
 #pragma unroll
             for (int jj = 0; jj < H / 4; ++jj)   // publish the upper half of t2
                 *reinterpret_cast<float4*>(stash_t2 + hs_base + ((jj ^ hs_swz) << 2)) =
@@ -242,9 +247,14 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
         });
     } else {
         // ------------------------------------------------------------------ Y role
-        float acc_2[E];
+        float acc_2[LEAN ? 1 : E];
+        if constexpr (LEAN) {
 #pragma unroll
-        for (int i = 0; i < E; ++i) acc_2[i] = 0.f;
+            for (int m = 0; m < E / 4; ++m) *reinterpret_cast<float4*>(acc2_smem + m * 4 * T) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+            for (int i = 0; i < E; ++i) acc_2[i] = 0.f;
+        }
 #pragma unroll 1
         for (int it = 0; it < p.iters_per_group; ++it) {
             const int64_t e0 = tile_of(it, pair);
@@ -264,6 +274,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
                 mul4(b + 4 * m, q, w);
             });
             transform_in<N, C, KT, T, SINGLE>(b, scratch, scratch2, tid, bar_role, k, wb_fm, wb_ml);  // b = dt3 (LAST)
+            if constexpr (LEAN) role_sync<T>(bar_role);
 #pragma unroll
             for (int jj = 0; jj < H / 4; ++jj)   // publish the lower half of dt3
                 *reinterpret_cast<float4*>(stash_d3 + hs_base + ((jj ^ hs_swz) << 2)) =
@@ -287,7 +298,14 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
                 constexpr int m = decltype(m_)::value;
                 const float4 q = raw4(stage_x, off);
                 const float4 w = ldg4(p.s2 + coord);
-                fma4(acc_2 + 4 * m, q, b + 4 * m);
+                if constexpr (LEAN) {
+                    float4 t = *reinterpret_cast<float4*>(acc2_smem + m * 4 * T);
+                    float tv[4] = {t.x, t.y, t.z, t.w};
+                    fma4(tv, q, b + 4 * m);
+                    *reinterpret_cast<float4*>(acc2_smem + m * 4 * T) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+                } else {
+                    fma4(acc_2 + 4 * m, q, b + 4 * m);
+                }
                 const float4 o = make_float4(q.x > relu_thr ? b[4 * m] * w.x : 0.f, q.y > relu_thr ? b[4 * m + 1] * w.y : 0.f,
                                              q.z > relu_thr ? b[4 * m + 2] * w.z : 0.f, q.w > relu_thr ? b[4 * m + 3] * w.w : 0.f);
                 if (want_dx && (left >= TILE || off < left)) stg_stream(dxs + off, o);
@@ -296,7 +314,10 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS + 32, MINB) layer_bwd_t
         }
         for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t) {
             constexpr int m = decltype(m_)::value;
-            *reinterpret_cast<float4*>(slab + 2 * TILE + off) = make_float4(acc_2[4 * m], acc_2[4 * m + 1], acc_2[4 * m + 2], acc_2[4 * m + 3]);
+            if constexpr (LEAN)
+                *reinterpret_cast<float4*>(slab + 2 * TILE + off) = *reinterpret_cast<float4*>(acc2_smem + m * 4 * T);
+            else
+                *reinterpret_cast<float4*>(slab + 2 * TILE + off) = make_float4(acc_2[4 * m], acc_2[4 * m + 1], acc_2[4 * m + 2], acc_2[4 * m + 3]);
         });
         for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t off, uint32_t) {
             constexpr int m = decltype(m_)::value;
@@ -359,7 +380,7 @@ template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE>
 static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
 {
     static unsigned char smem_ok[4][64] = {};
-    constexpr int threads = (2 << (N - C)) * PAIRS + 32;
+    constexpr int threads = (2 << (N - C)) * PAIRS;
     constexpr size_t tile = size_t(1) << N;
     constexpr size_t smem_plain = sizeof(float) * (2 * NS + (SINGLE ? 2 : 4) + 1) * tile * PAIRS;
     constexpr size_t smem_tgt = sizeof(float) * (3 * NS + (SINGLE ? 2 : 4) + 1) * tile * PAIRS;  // RESID, target staged
