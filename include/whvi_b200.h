@@ -54,7 +54,8 @@ typedef void* whvi_stream_t; /* a cudaStream_t */
 WHVI_API int whvi_abi_version(void);
 /* Message for the last non-zero return on this thread ("" if none). */
 WHVI_API const char* whvi_last_error(void);
-/* Largest D (power of two) the FWHT and the fused layer kernels accept. */
+/* Largest D (power of two) the FWHT accepts (single pass in shared memory up to 2^15,
+ * multi-pass through global memory beyond).  The fused layer kernels state their own limits. */
 WHVI_API int64_t whvi_max_dim(void);
 
 /*
@@ -72,7 +73,7 @@ WHVI_API int whvi_fwht_f32(const float* in, float* out, int64_t rows, int64_t D,
  * x: rows (s,b) at x + s*x_sample_stride + b*D; x_sample_stride is B*D for a contiguous
  *    (S,B,D) tensor or 0 when all samples share one (B,D) block (first layer of a net).
  * g: (S,D), one reparameterised vector per MC sample; s1, s2: (D); bias: (D) or NULL;
- * y: (S,B,D) contiguous.  4 <= D <= 8192, power of two.  Replaces the chain of ~20 torch
+ * y: (S,B,D) contiguous.  4 <= D <= 32768, power of two (the backward supports D <= 8192).  Replaces the chain of ~20 torch
  * ops and the B x D x D GEMM of WHVISquarePow2Matrix.sample_lrt (src/weights.py:87-93).
  */
 WHVI_API int whvi_layer_fwd_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1,

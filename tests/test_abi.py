@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, name), f"{name} declared in include/whvi_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in whvi_b200/_lib.py"
     assert _lib.lib().whvi_abi_version() == 1
-    assert _lib.lib().whvi_max_dim() >= 1 << 15
+    assert _lib.lib().whvi_max_dim() >= 1 << 20
 
 
 def test_fwht_frontend_rejects_like_the_reference():

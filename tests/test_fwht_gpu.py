@@ -90,8 +90,14 @@ def test_non_contiguous_and_errors():
         FWHTFunction.apply(torch.randn(2, 3, 4, device=dev()))
     with pytest.raises(RuntimeError, match="power of 2"):
         FWHTFunction.apply(torch.randn(2, 12, device=dev()))
-    with pytest.raises(RuntimeError, match="exceeds"):
-        FWHTFunction.apply(torch.randn(1, 1 << 16, device=dev()))
+
+
+@pytest.mark.parametrize("k,rows", [(16, 3), (17, 2), (19, 1), (20, 2), (22, 1)])
+def test_multi_pass_large_dims(k, rows):
+    """D > 2^15: single pass over the low 15 bits + strided passes over the rest."""
+    rng = np.random.default_rng(k)
+    a = rng.standard_normal((rows, 1 << k)).astype(np.float32)
+    assert rel_err(run(a), O.fwht(a.astype(np.float64))) < FWHT_TOL
 
 
 def test_autograd_backward_is_the_transform():

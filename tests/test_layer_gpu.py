@@ -84,6 +84,19 @@ def test_fused_flags(S, B, D):
     assert rel_err(db.cpu().numpy(), rdb) < TOL
 
 
+@pytest.mark.parametrize("S,B,D", [(2, 3, 16384), (2, 2, 32768)])
+def test_forward_large_dims(S, B, D):
+    """D = 2^14, 2^15: forward only (MC predictive evaluation, BASELINE config 5)."""
+    from whvi_b200 import functional as F
+    x, g, s1, s2, dy, bias = make_case(S, B, D, D + S)
+    y = F.layer_forward_raw(t(x), t(g), t(s1), t(s2), t(bias), relu_out=False)
+    assert rel_err(y.cpu().numpy(), O.layer_fwd(x, g, s1, s2, bias)) < TOL
+    ys = F.layer_forward_raw(t(x[0]), t(g), t(s1), t(s2))
+    assert rel_err(ys.cpu().numpy(), O.layer_fwd(x[0], g, s1, s2)) < TOL
+    with pytest.raises(RuntimeError, match="outside"):
+        F.layer_backward_raw(t(x), t(dy), t(g), t(s1), t(s2))
+
+
 def test_backward_without_dx_and_bias_and_determinism():
     from whvi_b200 import functional as F
     x, g, s1, s2, dy, _ = make_case(3, 41, 256, 5)

@@ -18,7 +18,7 @@ int whvi_abi_version(void) { return WHVI_ABI_VERSION; }
 
 const char* whvi_last_error(void) { return error_buffer(); }
 
-int64_t whvi_max_dim(void) { return int64_t(1) << kMaxLog2D; }
+int64_t whvi_max_dim(void) { return int64_t(1) << kMaxLog2Dmulti; }
 
 int whvi_fwht_f32(const float* in, float* out, int64_t rows, int64_t D, whvi_stream_t stream)
 {
@@ -30,11 +30,11 @@ int whvi_fwht_f32(const float* in, float* out, int64_t rows, int64_t D, whvi_str
     return launch_fwht(in, out, rows, D, static_cast<cudaStream_t>(stream));
 }
 
-static int check_layer_shape(const char* who, int64_t S, int64_t B, int64_t D, int64_t xs)
+static int check_layer_shape(const char* who, int64_t S, int64_t B, int64_t D, int64_t xs, int64_t max_d = 8192)
 {
     if (S < 0 || B < 0 || D < 1) return fail(WHVI_E_SHAPE, "%s: S=%lld B=%lld D=%lld", who, (long long)S, (long long)B, (long long)D);
     if (!is_pow2(D)) return fail(WHVI_E_SHAPE, "%s: D must be a power of 2 (got %lld)", who, (long long)D);
-    if (D < 4 || D > 8192) return fail(WHVI_E_SHAPE, "%s: D = %lld outside [4, 8192]", who, (long long)D);
+    if (D < 4 || D > max_d) return fail(WHVI_E_SHAPE, "%s: D = %lld outside [4, %lld]", who, (long long)D, (long long)max_d);
     if (xs != 0 && xs != B * D) return fail(WHVI_E_SHAPE, "%s: x_sample_stride must be 0 or B*D", who);
     return WHVI_OK;
 }
@@ -42,7 +42,7 @@ static int check_layer_shape(const char* who, int64_t S, int64_t B, int64_t D, i
 int whvi_layer_fwd_partials(int64_t S, int64_t B, int64_t D, int64_t* count)
 {
     if (!count) return fail(WHVI_E_NULL, "layer_fwd_partials: null pointer");
-    if (int rc = check_layer_shape("layer_fwd_partials", S, B, D, 0)) return rc;
+    if (int rc = check_layer_shape("layer_fwd_partials", S, B, D, 0, 32768)) return rc;
     *count = 0;
     if (S == 0 || B == 0) return WHVI_OK;
     size_t n = 0;
@@ -59,7 +59,7 @@ int whvi_layer_fwd_fused_f32(const float* x, int64_t x_sample_stride, const floa
                              const float* bias, float* y, int64_t S, int64_t B, int64_t D, int flags,
                              const float* target, float* sq_partials, whvi_stream_t stream)
 {
-    if (int rc = check_layer_shape("layer_fwd", S, B, D, x_sample_stride)) return rc;
+    if (int rc = check_layer_shape("layer_fwd", S, B, D, x_sample_stride, 32768)) return rc;
     if (flags & ~WHVI_LAYER_RELU_OUT) return fail(WHVI_E_MODE, "layer_fwd: unknown flags %d", flags);
     if (S == 0 || B == 0) return WHVI_OK;
     if (!x || !g || !s1 || !s2 || !y) return fail(WHVI_E_NULL, "layer_fwd: null pointer");

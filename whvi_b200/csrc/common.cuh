@@ -50,7 +50,8 @@ inline int ensure_smem(Kernel kernel, size_t bytes, unsigned char* done_flags /*
     return WHVI_OK;
 }
 
-constexpr int kMaxLog2D = 15;  // single-pass kernels keep a whole row in one CTA's shared memory
+constexpr int kMaxLog2D = 15;       // single-pass kernels keep a whole row in one CTA's shared memory
+constexpr int kMaxLog2Dmulti = 30;  // multi-pass global variant beyond that
 
 int launch_fwht(const float* in, float* out, int64_t rows, int64_t D, cudaStream_t stream);
 struct LayerFwdCall {

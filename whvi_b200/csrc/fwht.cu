@@ -86,6 +86,57 @@ __global__ void fwht_tiny_kernel(const float* __restrict__ in, float* __restrict
     }
 }
 
+// Multi-pass global variant for D > 2^15: after the low 15 bits have been transformed row
+// segment by row segment with the single-pass kernel, the remaining high bits are done in
+// place, R = 2^r (r <= 4) bits per pass.  A thread owns one float4 column and the R values
+// that differ in the bit group [log2_stride, log2_stride + r): lanes run along the
+// contiguous dimension, so every access is a coalesced 128-bit access.  Each extra pass costs
+// one more read + write of the data (8 B/elt).
+template <int R>
+__global__ void __launch_bounds__(256)
+fwht_strided_kernel(float4* __restrict__ data, int64_t n_threads, int log2_stride4 /* stride in float4 units */)
+{
+    constexpr int r = R == 2 ? 1 : (R == 4 ? 2 : (R == 8 ? 3 : 4));
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= n_threads) return;
+    const int64_t low = idx & ((int64_t(1) << log2_stride4) - 1);
+    const int64_t high = idx >> log2_stride4;
+    float4* base = data + ((high << (log2_stride4 + r)) | low);
+    const int64_t stride = int64_t(1) << log2_stride4;
+    float4 v[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = base[j * stride];
+#pragma unroll
+    for (int h = 1; h < R; h <<= 1) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (j & h) continue;
+            const float4 a = v[j], b = v[j | h];
+            v[j] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+            v[j | h] = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) base[j * stride] = v[j];
+}
+
+static int launch_strided(float* data, int64_t total, int log2_stride, int r, cudaStream_t stream)
+{
+    const int64_t n_threads = (total / 4) >> r;
+    const int threads = 256;
+    const int64_t blocks = (n_threads + threads - 1) / threads;
+    if (blocks > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "fwht: strided pass exceeds the grid limit");
+    float4* d4 = reinterpret_cast<float4*>(data);
+    const unsigned g = static_cast<unsigned>(blocks);
+    switch (r) {
+    case 1: fwht_strided_kernel<2><<<g, threads, 0, stream>>>(d4, n_threads, log2_stride - 2); break;
+    case 2: fwht_strided_kernel<4><<<g, threads, 0, stream>>>(d4, n_threads, log2_stride - 2); break;
+    case 3: fwht_strided_kernel<8><<<g, threads, 0, stream>>>(d4, n_threads, log2_stride - 2); break;
+    default: fwht_strided_kernel<16><<<g, threads, 0, stream>>>(d4, n_threads, log2_stride - 2); break;
+    }
+    return check_launch("fwht_strided_kernel");
+}
+
 template <int N, int C, int K, int GROUPS>
 static int launch_cfg(const float* in, float* out, int64_t total, cudaStream_t stream)
 {
@@ -131,7 +182,15 @@ int launch_fwht(const float* in, float* out, int64_t rows, int64_t D, cudaStream
     case 15: return launch_cfg<15, 6, 15, 1>(in, out, total, stream);
     default: break;
     }
-    return fail(WHVI_E_SHAPE, "fwht: D = %lld exceeds the single-pass limit 2^%d", (long long)D, kMaxLog2D);
+    if (K > kMaxLog2Dmulti) return fail(WHVI_E_SHAPE, "fwht: D = %lld exceeds the limit 2^%d", (long long)D, kMaxLog2Dmulti);
+    // D > 2^15: low 15 bits in one pass (every 2^15-float segment is a "row"), then the high bits
+    if (int rc = launch_cfg<15, 6, 15, 1>(in, out, total, stream)) return rc;
+    for (int b = kMaxLog2D; b < K;) {
+        const int r = (K - b) < 4 ? (K - b) : 4;
+        if (int rc = launch_strided(out, total, b, r, stream)) return rc;
+        b += r;
+    }
+    return WHVI_OK;
 }
 
 }  // namespace whvi

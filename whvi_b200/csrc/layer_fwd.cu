@@ -217,7 +217,11 @@ int launch_layer_fwd(const LayerFwdCall& c, int64_t D, cudaStream_t stream)
     if (k == 12) return launch_fwd_cfg<12, 6, 12, 2, 2, 1, 4>(c, k, stream);
     // D = 8192: three views, 32 floats per thread
     if (k == 13) return launch_fwd_cfg<13, 5, 13, 1, 3, 2, 3>(c, k, stream);
-    return fail(WHVI_E_SHAPE, "layer_fwd: D = %lld unsupported (4 <= D <= 8192)", (long long)D);
+    // D = 16384, 32768 (forward only: MC predictive evaluation, BASELINE config 5): three views,
+    // 64 floats per thread, one in-place transposition buffer (64 / 128 KB)
+    if (k == 14) return launch_fwd_cfg<14, 6, 14, 1, 3, 1, 1>(c, k, stream);
+    if (k == 15) return launch_fwd_cfg<15, 6, 15, 1, 3, 1, 1>(c, k, stream);
+    return fail(WHVI_E_SHAPE, "layer_fwd: D = %lld unsupported (4 <= D <= 32768)", (long long)D);
 }
 
 }  // namespace whvi

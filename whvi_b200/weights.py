@@ -143,7 +143,7 @@ class WHVISquarePow2Matrix(nn.Module):
     @property
     def fusable(self):
         """True when the fused-neighbour paths (ReLU / MNLL folded into the kernels) apply."""
-        return self.semantics == "paper" and 4 <= self.D <= 8192
+        return self.semantics == "paper" and 4 <= self.D <= 8192  # the backward kernel's range
 
     def forward_sqerr(self, h, target, *, relu_in=False):
         """Forward pass fused with sum (y - target)^2 (see functional.WHVILayerSqErrFunction).
