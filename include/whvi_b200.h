@@ -128,9 +128,14 @@ WHVI_API int whvi_layer_bwd_fused_f32(const float* x, int64_t x_sample_stride, c
 /*
  * Reparameterisation (src/weights.py:43-50, :82-83, :92-93), one eps row per MC sample:
  *   mode 0:  g[s,:] = mu + softplus(rho) * eps[s,:]              (diagonal; the reference)
+ *   mode 1:  g[s,:] = mu + L eps[s,:], L (D,D) row-major lower triangular passed in `rho`
+ *            (entries above the diagonal are ignored); a tcgen05 tensor-core GEMM with a
+ *            3xTF32 operand split (fp32-level accuracy); D must be a multiple of 128.  Not in
+ *            the reference (its posterior is diagonal) -- a superset feature.
  * eps, g: (S,D); mu, rho: (D).
  */
 #define WHVI_REPARAM_DIAG 0
+#define WHVI_REPARAM_DENSE 1
 WHVI_API int whvi_reparam_f32(const float* mu, const float* rho, const float* eps, float* g, int64_t S, int64_t D,
                               int mode, whvi_stream_t stream);
 /* dmu = sum_s dg[s];  drho = (sum_s dg[s]*eps[s]) * sigmoid(rho).  accumulate != 0: += */

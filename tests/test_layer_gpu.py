@@ -205,3 +205,22 @@ def test_layer_full_size_properties():
         ref = O.layer_fwd(xs[i][None, None], g[s].cpu().numpy().astype(np.float64)[None], s1.cpu().numpy().astype(np.float64),
                           s2.cpu().numpy().astype(np.float64))[0, 0]
         assert rel_err(y[s, b].cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("S,D", [(16, 128), (64, 256), (37, 512), (128, 1024), (300, 256)])
+def test_reparam_dense_tcgen05_vs_oracle(S, D):
+    """Kernel (4): g = mu + eps @ L^T on the tcgen05 tensor cores (3xTF32 split).  Not in the
+    reference (parity unpinned): checked against the fp64 oracle formula and torch autograd."""
+    from whvi_b200 import functional as F
+    rng = np.random.default_rng(S + D)
+    mu, eps = rng.standard_normal(D), rng.standard_normal((S, D))
+    L = np.tril(rng.standard_normal((D, D))) / np.sqrt(D)
+    Lgarbage = L + np.triu(rng.standard_normal((D, D)), 1)  # entries above the diagonal must be ignored
+    mt, Lt = t(mu).requires_grad_(), t(Lgarbage).requires_grad_()
+    g = F.reparam_dense(mt, Lt, t(eps))
+    ref = O.reparam(mu, L, eps, dense=True)
+    assert rel_err(g.detach().cpu().numpy(), ref) < 1e-5
+    dg = rng.standard_normal((S, D))
+    (g * t(dg)).sum().backward()
+    assert rel_err(mt.grad.cpu().numpy(), dg.sum(0)) < 1e-5
+    assert rel_err(Lt.grad.cpu().numpy(), np.tril(dg.T @ eps)) < 1e-5

@@ -128,9 +128,14 @@ int whvi_reparam_f32(const float* mu, const float* rho, const float* eps, float*
                      whvi_stream_t stream)
 {
     if (S < 0 || D < 1) return fail(WHVI_E_SHAPE, "reparam: S=%lld D=%lld", (long long)S, (long long)D);
-    if (mode != WHVI_REPARAM_DIAG) return fail(WHVI_E_MODE, "reparam: unknown mode %d", mode);
+    if (mode != WHVI_REPARAM_DIAG && mode != WHVI_REPARAM_DENSE) return fail(WHVI_E_MODE, "reparam: unknown mode %d", mode);
     if (S == 0) return WHVI_OK;
     if (!mu || !rho || !eps || !g) return fail(WHVI_E_NULL, "reparam: null pointer");
+    if (mode == WHVI_REPARAM_DENSE) {
+        if (D % 128 != 0) return fail(WHVI_E_SHAPE, "reparam(dense): D = %lld must be a multiple of 128", (long long)D);
+        if (!aligned16(rho) || !aligned16(eps)) return fail(WHVI_E_ALIGN, "reparam(dense): pointers must be 16-byte aligned");
+        return launch_reparam_dense(mu, rho, eps, g, S, D, static_cast<cudaStream_t>(stream));
+    }
     return launch_reparam_diag(mu, rho, eps, g, S, D, static_cast<cudaStream_t>(stream));
 }
 

@@ -73,6 +73,7 @@ int launch_layer_fwd(const LayerFwdCall& c, int64_t D, cudaStream_t stream);
 int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream);
 int launch_reparam_diag(const float* mu, const float* rho, const float* eps, float* g, int64_t S, int64_t D,
                         cudaStream_t stream);
+int launch_reparam_dense(const float* mu, const float* L, const float* eps, float* g, int64_t S, int64_t D, cudaStream_t stream);
 int launch_reparam_diag_bwd(const float* rho, const float* eps, const float* dg, float* dmu, float* drho, int64_t S,
                             int64_t D, int accumulate, cudaStream_t stream);
 int launch_kl(const float* mu, const float* rho, float lambda_, int64_t D, int mode, float* out, float* dmu, float* drho,

@@ -259,6 +259,35 @@ def reparam(mu, rho, eps):
     return ReparamFunction.apply(mu, rho, eps)
 
 
+class ReparamDenseFunction(Function):
+    """g[s] = mu + L eps[s] with a dense lower-triangular L (D, D): the tcgen05 tensor-core
+    kernel (3xTF32 split).  Superset of the reference (whose posterior is diagonal).  The
+    backward is two plain library ops (column sum and one cuBLAS GEMM, dL = tril(dg^T eps))."""
+
+    @staticmethod
+    def forward(ctx, mu, L, eps):
+        mu, L, eps = _f32c(mu, "g_mu"), _f32c(L, "g_L"), _f32c(eps, "eps")
+        S, D = eps.shape
+        if L.shape != (D, D):
+            raise RuntimeError(f"L must be {(D, D)}, got {tuple(L.shape)}")
+        g = torch.empty_like(eps)
+        with torch.cuda.device(eps.device), _Timed("whvi_reparam_f32"):
+            rc = _lib.lib().whvi_reparam_f32(mu.data_ptr(), L.data_ptr(), eps.data_ptr(), g.data_ptr(), S, D, 1,
+                                             _stream(eps.device))
+        _lib.check(rc, "whvi_reparam_f32(dense)")
+        ctx.save_for_backward(eps)
+        return g
+
+    @staticmethod
+    def backward(ctx, dg):
+        (eps,) = ctx.saved_tensors
+        return dg.sum(dim=0), torch.tril(dg.t() @ eps), None
+
+
+def reparam_dense(mu, L, eps):
+    return ReparamDenseFunction.apply(mu, L, eps)
+
+
 class KLFunction(Function):
     """KL(N(mu, softplus(rho)) || N(0, lambda)) value + gradient in one kernel.
     mode 0 = the reference's formula (src/utils.py:49-71), mode 1 = sigma^2 form."""
