@@ -264,8 +264,17 @@ def run_ours(args):
     fwd_avg = sum(fwd_ms) / len(fwd_ms)
     bwd_gbs = 12.0 * D * rows_per_launch / (bwd_avg * 1e-3) / 1e9
     fwd_gbs = 8.0 * D * rows_per_launch / (fwd_avg * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "layer_bwd_kernel (+ reduce)", "achieved": bwd_gbs, "peak": peak,
-                "unit": "GB/s", "frac": bwd_gbs / peak, "frac_of_8TBs_nominal": bwd_gbs / 8000.0, "traffic": None,
+    traffic = None  # DRAM bytes per launch of that kernel, from the committed ncu --set full capture
+    tp = ROOT / "profiles" / "r01_bwd_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text())["dram_bytes_per_row"] * rows_per_launch
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "layer_bwd_tma_kernel (+ layer_bwd_reduce_kernel)", "achieved": bwd_gbs, "peak": peak,
+                "unit": "GB/s", "frac": bwd_gbs / peak, "frac_of_8TBs_nominal": bwd_gbs / 8000.0, "traffic": traffic,
+                "traffic_source": "profiles/r01_bwd_traffic.json (ncu dram__bytes_read+write per row x rows per launch)",
+                "algorithmic_bytes_per_launch": 12.0 * D * rows_per_launch,
                 "peak_source": peak_src, "algorithmic_bytes_per_row": 12 * D, "rows_per_launch": rows_per_launch,
                 "avg_launch_ms": bwd_avg, "launches_timed": len(bwd_ms),
                 "share_of_step": sum(bwd_ms) / ms_total,
