@@ -36,3 +36,40 @@ def build_H(D, device):
 
 
 kl_gaussian = WF.kl_gaussian
+
+
+class DevicePrefetcher:
+    """Iterate over host batches (tuples of pinned tensors) with the host->device copy of
+    batch i+1 running on a side stream while batch i is being computed on."""
+
+    def __init__(self, batches, device):
+        self.batches = iter(batches)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._next = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            host = next(self.batches)
+        except StopIteration:
+            self._next = None
+            return
+        with torch.cuda.stream(self.stream):
+            dev = tuple(t.to(self.device, non_blocking=True) for t in host)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._next = (dev, ev)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        dev, ev = self._next
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        for t in dev:
+            t.record_stream(torch.cuda.current_stream(self.device))
+        self._preload()
+        return dev
