@@ -40,36 +40,51 @@ kl_gaussian = WF.kl_gaussian
 
 class DevicePrefetcher:
     """Iterate over host batches (tuples of pinned tensors) with the host->device copy of
-    batch i+1 running on a side stream while batch i is being computed on."""
+    batch i+1 running on a side stream while batch i is being computed on.  Two fixed sets of
+    device buffers are reused (no allocator traffic); a batch handed out stays valid until the
+    next one is requested."""
 
     def __init__(self, batches, device):
         self.batches = iter(batches)
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
-        self._next = None
+        self.bufs = [None, None]
+        self.ready = [None, None]   # copy finished (recorded on the side stream)
+        self.done = [None, None]    # consumer finished with the slot (recorded on its stream)
+        self.i = 0                  # index of the next batch to hand out
+        self.loaded = 0             # number of batches whose copy has been issued
         self._preload()
 
     def _preload(self):
         try:
             host = next(self.batches)
         except StopIteration:
-            self._next = None
             return
+        k = self.loaded % 2
+        if self.bufs[k] is None:
+            self.bufs[k] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host)
         with torch.cuda.stream(self.stream):
-            dev = tuple(t.to(self.device, non_blocking=True) for t in host)
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        self._next = (dev, ev)
+            if self.done[k] is not None:
+                self.stream.wait_event(self.done[k])
+            for d, h in zip(self.bufs[k], host):
+                d.copy_(h, non_blocking=True)
+            self.ready[k] = torch.cuda.Event()
+            self.ready[k].record(self.stream)
+        self.loaded += 1
 
     def __iter__(self):
         return self
 
     def __next__(self):
-        if self._next is None:
+        cur = torch.cuda.current_stream(self.device)
+        if self.i > 0:  # the consumer has issued all its work on the previous batch
+            p = (self.i - 1) % 2
+            self.done[p] = torch.cuda.Event()
+            self.done[p].record(cur)
+        if self.i >= self.loaded:
             raise StopIteration
-        dev, ev = self._next
-        torch.cuda.current_stream(self.device).wait_event(ev)
-        for t in dev:
-            t.record_stream(torch.cuda.current_stream(self.device))
+        k = self.i % 2
+        cur.wait_event(self.ready[k])
+        self.i += 1
         self._preload()
-        return dev
+        return self.bufs[k]
