@@ -47,7 +47,7 @@ struct BwdArgs {
 //     each sends the other the half-stream it needs through a shared half-stash), which
 //     balances the register budgets at <= 112 so two CTAs (2 x 288 threads) fit per SM.
 // Shared memory per pair: NS x (x tile + dy tile) + X scratch + Y scratch + stash (1 tile).
-template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool WANT_DBIAS, bool RESID>
+template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS, bool PREG, bool WANT_DBIAS, bool RESID>
 __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_kernel(const BwdArgs p)
 {
     constexpr int T = 1 << (N - C);
@@ -57,9 +57,14 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     constexpr int SCR = SINGLE ? 1 : 2;      // scratch tiles per role
     // RESID: the target tile rides in the stage too (third tile) when shared memory allows
     constexpr bool LEAN = false;  // (a 2-CTA/SM variant with smem accumulators measured slower; profiles/r01_bwd_notes.md)
-    constexpr bool STAGE_TGT = RESID && (3 * NS + 2 * SCR + 1) * sizeof(float) * size_t(TILE) * PAIRS <= 200 * 1024;
+    // ALIAS (needs ping-pong scratch): the half-stashes live in each role's idle first scratch
+    // buffer instead of a tile of their own (every read of it precedes the barrier that followed
+    // the second buffer's write), which makes room for two CTAs per SM.
+    static_assert(!ALIAS || !SINGLE, "stash aliasing needs ping-pong scratch buffers");
+    constexpr int STASH = ALIAS ? 0 : 1;
+    constexpr bool STAGE_TGT = RESID && (3 * NS + 2 * SCR + STASH) * sizeof(float) * size_t(TILE) * PAIRS <= (MINB == 2 ? 112 : 200) * 1024;
     constexpr int SPT = STAGE_TGT ? 3 : 2;   // tiles per stage
-    constexpr int PAIR_FLOATS = (SPT * NS + 2 * SCR + 1) * int(TILE);
+    constexpr int PAIR_FLOATS = (SPT * NS + 2 * SCR + STASH) * int(TILE);
     extern __shared__ float4 smem4[];
     __shared__ uint64_t full_bar[PAIRS][NS], empty_bar[PAIRS][NS];
     float* smem = reinterpret_cast<float*>(smem4);
@@ -112,8 +117,8 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     float* scratch = pair_smem + (SPT * NS + SCR * role) * TILE;  // this role's transposition buffer(s)
     float* scratch2 = scratch + (SINGLE ? 0 : TILE);
     // half-stashes: X -> Y upper half of t2, Y -> X lower half of dt3
-    float* stash_t2 = LEAN ? pair_smem + (SPT * NS) * TILE : pair_smem + (SPT * NS + 2 * SCR) * TILE;
-    float* stash_d3 = LEAN ? pair_smem + (SPT * NS + SCR) * TILE : stash_t2 + TILE / 2;
+    float* stash_t2 = (LEAN || ALIAS) ? pair_smem + (SPT * NS) * TILE : pair_smem + (SPT * NS + 2 * SCR) * TILE;
+    float* stash_d3 = (LEAN || ALIAS) ? pair_smem + (SPT * NS + SCR) * TILE : stash_t2 + TILE / 2;
     float* acc2_smem = pair_smem + (SPT * NS + 2 * SCR) * TILE + (tid << 2);  // LEAN: slot m at + m * 4 * T
     const int bar_role = 1 + 3 * pair + role;
     const int bar_pair = 3 + 3 * pair;
@@ -173,6 +178,22 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
 
     if (role == 0) {
         // ------------------------------------------------------------------ X role
+        // PREG: this thread's s2 and g values never change from tile to tile (its coordinates are
+        // fixed), so they are loaded once; each per-tile parameter load otherwise costs as many
+        // L1 wavefronts as a raw-tile read, and the L1/shared data pipe is what bounds this kernel
+        float s2r[PREG ? E : 1], gr[PREG ? E : 1];
+        if constexpr (PREG) {
+            for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                const float4 w = ldg4(p.s2 + coord);
+                s2r[4 * m] = w.x, s2r[4 * m + 1] = w.y, s2r[4 * m + 2] = w.z, s2r[4 * m + 3] = w.w;
+            });
+            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                const float4 w = ldg4(gs + coord);
+                gr[4 * m] = w.x, gr[4 * m + 1] = w.y, gr[4 * m + 2] = w.z, gr[4 * m + 3] = w.w;
+            });
+        }
         float acc_1[E];
         float acc_b[WANT_DBIAS ? E : 1];
 #pragma unroll
@@ -199,7 +220,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
                 const float4 q = raw4(stage_x, off);
-                const float4 w = ldg4(p.s2 + coord);
+                const float4 w = PREG ? make_float4(s2r[4 * m], s2r[4 * m + 1], s2r[4 * m + 2], s2r[4 * m + 3]) : ldg4(p.s2 + coord);
                 mul4(a + 4 * m, q, w);
             });
             transform_in<N, C, KT, T, SINGLE>(a, scratch, scratch2, tid, bar_role, k, wb_fm, wb_ml);  // a = t2 (LAST)
@@ -217,7 +238,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
             bar_wait<2 * T>(bar_pair);  // both half-stashes consumed
             for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
-                const float4 w = ldg4(gs + coord);
+                const float4 w = PREG ? make_float4(gr[4 * m], gr[4 * m + 1], gr[4 * m + 2], gr[4 * m + 3]) : ldg4(gs + coord);
                 scale4(a + 4 * m, w);
             });
             transform_out<N, C, KT, T, SINGLE>(a, scratch, scratch2, tid, bar_role, k, wb_lm, wb_mf);  // a = t4 (FIRST)
@@ -247,6 +268,19 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
         });
     } else {
         // ------------------------------------------------------------------ Y role
+        float s1r[PREG ? E : 1], gr[PREG ? E : 1];
+        if constexpr (PREG) {
+            for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                const float4 w = ldg4(p.s1 + coord);
+                s1r[4 * m] = w.x, s1r[4 * m + 1] = w.y, s1r[4 * m + 2] = w.z, s1r[4 * m + 3] = w.w;
+            });
+            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                const float4 w = ldg4(gs + coord);
+                gr[4 * m] = w.x, gr[4 * m + 1] = w.y, gr[4 * m + 2] = w.z, gr[4 * m + 3] = w.w;
+            });
+        }
         float acc_2[LEAN ? 1 : E];
         if constexpr (LEAN) {
 #pragma unroll
@@ -270,7 +304,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
                 const float4 q = to_dy(raw4(stage_dy, off), tgt, off, left);
-                const float4 w = ldg4(p.s1 + coord);
+                const float4 w = PREG ? make_float4(s1r[4 * m], s1r[4 * m + 1], s1r[4 * m + 2], s1r[4 * m + 3]) : ldg4(p.s1 + coord);
                 mul4(b + 4 * m, q, w);
             });
             transform_in<N, C, KT, T, SINGLE>(b, scratch, scratch2, tid, bar_role, k, wb_fm, wb_ml);  // b = dt3 (LAST)
@@ -288,7 +322,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
             bar_wait<2 * T>(bar_pair);
             for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
-                const float4 w = ldg4(gs + coord);
+                const float4 w = PREG ? make_float4(gr[4 * m], gr[4 * m + 1], gr[4 * m + 2], gr[4 * m + 3]) : ldg4(gs + coord);
                 scale4(b + 4 * m, w);
             });
             transform_out<N, C, KT, T, SINGLE>(b, scratch, scratch2, tid, bar_role, k, wb_lm, wb_mf);  // b = dt1 (FIRST)
@@ -376,15 +410,15 @@ layer_bwd_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dg, fl
     }
 }
 
-template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE>
+template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS = false, bool PREG = false>
 static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
 {
     static unsigned char smem_ok[4][64] = {};
     constexpr int threads = (2 << (N - C)) * PAIRS;
     constexpr size_t tile = size_t(1) << N;
-    constexpr size_t smem_plain = sizeof(float) * (2 * NS + (SINGLE ? 2 : 4) + 1) * tile * PAIRS;
-    constexpr size_t smem_tgt = sizeof(float) * (3 * NS + (SINGLE ? 2 : 4) + 1) * tile * PAIRS;  // RESID, target staged
-    const size_t smem = (c.target != nullptr && smem_tgt <= 200 * 1024) ? smem_tgt : smem_plain;
+    constexpr size_t smem_plain = sizeof(float) * (2 * NS + (SINGLE ? 2 : 4) + (ALIAS ? 0 : 1)) * tile * PAIRS;
+    constexpr size_t smem_tgt = sizeof(float) * (3 * NS + (SINGLE ? 2 : 4) + (ALIAS ? 0 : 1)) * tile * PAIRS;  // RESID, target staged
+    const size_t smem = (c.target != nullptr && smem_tgt <= (MINB == 2 ? 112 : 200) * 1024) ? smem_tgt : smem_plain;
     const int64_t D = int64_t(1) << k;
     const int64_t tiles_per_sample = (c.B * D + int64_t(tile) - 1) / int64_t(tile);
     const Plan plan = make_plan(c.S, tiles_per_sample, PAIRS, 148 * 4, 8);
@@ -406,10 +440,10 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     };
     const bool db = c.dbias != nullptr, rs = c.target != nullptr;
     int rc;
-    if (db && rs) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, true, true>, 0);
-    else if (db) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, true, false>, 1);
-    else if (rs) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, false, true>, 2);
-    else rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, false, false>, 3);
+    if (db && rs) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, true, true>, 0);
+    else if (db) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, true, false>, 1);
+    else if (rs) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, false, true>, 2);
+    else rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, false, false>, 3);
     if (rc) return rc;
     const int warps = 8;
     dim3 rgrid(static_cast<unsigned>((D + warps - 1) / warps), static_cast<unsigned>(c.S + 1));
@@ -421,14 +455,15 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
 int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream)
 {
     const int k = ilog2(D);
-    // TMA-staged kernels: one CTA per SM (<= 144 KB shared memory at D <= 4096, 224 KB at
-    // D = 8192), NS = 2 stages, ping-pong transposition buffers where they fit
-    if (k >= 2 && k <= 6) return launch_bwd_tma_cfg<10, 5, k_family(2, 6), 4, 1, 2, false>(c, k, stream);
-    if (k >= 7 && k <= 9) return launch_bwd_tma_cfg<10, 5, k_family(7, 9), 4, 1, 2, false>(c, k, stream);
-    if (k == 10) return launch_bwd_tma_cfg<10, 5, 10, 4, 1, 2, false>(c, k, stream);
-    if (k == 11) return launch_bwd_tma_cfg<11, 5, 11, 2, 1, 2, false>(c, k, stream);
-    if (k == 12) return launch_bwd_tma_cfg<12, 5, 12, 1, 1, 2, false>(c, k, stream);
-    if (k == 13) return launch_bwd_tma_cfg<13, 5, 13, 1, 1, 2, true>(c, k, stream);
+    // TMA-staged kernels: one CTA per SM (<= 176 KB shared memory at D <= 4096, 224 KB at
+    // D = 8192), NS = 2 stages, ping-pong transposition buffers where they fit, parameters
+    // register-resident where the register file allows (256 threads per CTA)
+    if (k >= 2 && k <= 6) return launch_bwd_tma_cfg<10, 5, k_family(2, 6), 4, 1, 2, false, false, true>(c, k, stream);
+    if (k >= 7 && k <= 9) return launch_bwd_tma_cfg<10, 5, k_family(7, 9), 4, 1, 2, false, false, true>(c, k, stream);
+    if (k == 10) return launch_bwd_tma_cfg<10, 5, 10, 4, 1, 2, false, false, true>(c, k, stream);
+    if (k == 11) return launch_bwd_tma_cfg<11, 5, 11, 2, 1, 2, false, false, true>(c, k, stream);
+    if (k == 12) return launch_bwd_tma_cfg<12, 5, 12, 1, 1, 2, false, false, true>(c, k, stream);
+    if (k == 13) return launch_bwd_tma_cfg<13, 5, 13, 1, 1, 2, true, false, false>(c, k, stream);
     return fail(WHVI_E_SHAPE, "layer_bwd: D = %lld unsupported (4 <= D <= 8192)", (long long)D);
 }
 
