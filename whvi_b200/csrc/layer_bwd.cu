@@ -1,10 +1,21 @@
 // Kernel (3): the fused WHVILinear backward (see layer_fwd.cu for the math and layout notes).
 #include "layer_common.cuh"
-#include <cstdlib>
 
 namespace whvi {
 
 // ------------------------------------------------------------------------------ backward
+// Does the MNLL target tile ride in the TMA stage (RESID kernels)?  One definition for the
+// kernel's shared-memory carve-up and the launcher's size computation.
+constexpr size_t bwd_smem_bytes(int n, int pairs, int ns, bool single, bool alias, bool gtab, int spt)
+{
+    return sizeof(float) * ((size_t(spt) * ns + (single ? 2 : 4) + (alias ? 0 : 1)) * (size_t(1) << n) * pairs +
+                            (gtab ? (size_t(1) << n) : 0));
+}
+constexpr bool bwd_stage_target(int n, int pairs, int ns, bool single, bool alias, bool gtab, int minb)
+{
+    return bwd_smem_bytes(n, pairs, ns, single, alias, gtab, 3) <= size_t(minb == 2 ? 112 : 200) * 1024;
+}
+
 struct BwdArgs {
     const float* x;
     int64_t x_sample_stride;
@@ -47,7 +58,7 @@ struct BwdArgs {
 //     each sends the other the half-stream it needs through a shared half-stash), which
 //     balances the register budgets at <= 112 so two CTAs (2 x 288 threads) fit per SM.
 // Shared memory per pair: NS x (x tile + dy tile) + X scratch + Y scratch + stash (1 tile).
-template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS, bool PREG, bool WANT_DBIAS, bool RESID>
+template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS, bool PREG, int ROUNDS, bool WANT_DBIAS, bool RESID>
 __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_kernel(const BwdArgs p)
 {
     constexpr int T = 1 << (N - C);
@@ -60,14 +71,19 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     // ALIAS (needs ping-pong scratch): the half-stashes live in each role's idle first scratch
     // buffer instead of a tile of their own (every read of it precedes the barrier that followed
     // the second buffer's write), which makes room for two CTAs per SM.
-    static_assert(!ALIAS || !SINGLE, "stash aliasing needs ping-pong scratch buffers");
+    // ROUNDS == 3: FIRST -> MID -> LAST, the middle of the layer (g multiply, dg products) in the
+    // LAST view.  ROUNDS == 2 (configurations where FIRST + MID cover every bit): the middle is
+    // the MID view -- half the transpositions, hence half of the dominant L1/shared wavefronts.
+    static_assert(ROUNDS == 3 || rounds_needed(N, C, N) <= 2, "2-view kernel needs FIRST+MID to cover all bits");
+    constexpr bool GTAB = ROUNDS == 2 && !PREG;  // g in shared memory in MID order (one table per CTA)
     constexpr int STASH = ALIAS ? 0 : 1;
-    constexpr bool STAGE_TGT = RESID && (3 * NS + 2 * SCR + STASH) * sizeof(float) * size_t(TILE) * PAIRS <= (MINB == 2 ? 112 : 200) * 1024;
+    constexpr bool STAGE_TGT = RESID && bwd_stage_target(N, PAIRS, NS, SINGLE, ALIAS, ROUNDS == 2 && !PREG, MINB);
     constexpr int SPT = STAGE_TGT ? 3 : 2;   // tiles per stage
     constexpr int PAIR_FLOATS = (SPT * NS + 2 * SCR + STASH) * int(TILE);
     extern __shared__ float4 smem4[];
     __shared__ uint64_t full_bar[PAIRS][NS], empty_bar[PAIRS][NS];
-    float* smem = reinterpret_cast<float*>(smem4);
+    float* gt = reinterpret_cast<float*>(smem4);                      // GTAB only
+    float* smem = reinterpret_cast<float*>(smem4) + (ROUNDS == 2 && !PREG ? (size_t(1) << N) : 0);
     const int k = KT >= 0 ? KT : p.k;
     const uint32_t cmask = (1u << k) - 1u;
     // sample-minor CTA order (see layer_fwd.cu): shared x / target tiles are reused out of L2
@@ -132,7 +148,91 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     const uint32_t wb_fm = transpose_writer_base<N, C, V_FIRST, V_MID>(tid);
     const uint32_t wb_ml = transpose_writer_base<N, C, V_MID, V_LAST>(tid);
     const uint32_t wb_lm = transpose_writer_base<N, C, V_LAST, V_MID2>(tid);
-    const uint32_t wb_mf = transpose_writer_base<N, C, V_MID2, V_FIRST>(tid);
+    const uint32_t wb_mf = ROUNDS == 3 ? transpose_writer_base<N, C, V_MID2, V_FIRST>(tid)
+                                       : transpose_writer_base<N, C, V_MID, V_FIRST>(tid);
+    const uint32_t mid_logical = view_tid_logical(view_mid(N, C), tid);  // ROUNDS == 2: this thread's MID-view index bits
+    uint32_t gbase = 0;
+    if constexpr (GTAB) {
+        gbase = gtab_base<N, C>(tid, k);
+        gtab_fill<N, C>(gt, gs, 2 * T * PAIRS, k);
+        __syncthreads();
+    }
+    // stream -> middle layout (t2 / dt3) and back (t4 / dt1)
+    auto to_mid = [&](float (&v)[E]) {
+        if constexpr (ROUNDS == 3) {
+            transform_in<N, C, KT, T, SINGLE>(v, scratch, scratch2, tid, bar_role, k, wb_fm, wb_ml);
+        } else {
+            bfly_round<N, C, KT, SEQ2_IN, 0>(v, k);
+            if constexpr (SINGLE) role_sync<T>(bar_role);
+            transpose_write<N, C, V_FIRST, V_MID>(v, scratch, wb_fm);
+            role_sync<T>(bar_role);
+            transpose_read<C>(v, scratch, tid);
+            bfly_round<N, C, KT, SEQ2_IN, 1>(v, k);
+        }
+    };
+    auto from_mid = [&](float (&v)[E]) {
+        if constexpr (ROUNDS == 3) {
+            transform_out<N, C, KT, T, SINGLE>(v, scratch, scratch2, tid, bar_role, k, wb_lm, wb_mf);
+        } else {
+            bfly_round<N, C, KT, SEQ2_OUT, 0>(v, k);
+            if constexpr (SINGLE) role_sync<T>(bar_role);
+            transpose_write<N, C, V_MID, V_FIRST>(v, scratch2, wb_mf);
+            role_sync<T>(bar_role);
+            transpose_read<C>(v, scratch2, tid);
+            bfly_round<N, C, KT, SEQ2_OUT, 1>(v, k);
+        }
+    };
+    // g in the middle layout: once into registers (PREG) ...
+    auto load_g_regs = [&](float* gr) {
+        if constexpr (ROUNDS == 3) {
+            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                const float4 w = ldg4(gs + coord);
+                gr[4 * m] = w.x, gr[4 * m + 1] = w.y, gr[4 * m + 2] = w.z, gr[4 * m + 3] = w.w;
+            });
+        } else {
+            static_for<0, E>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                constexpr uint32_t rl = view_reg_logical(view_mid(N, C), r);
+                gr[r] = __ldg(gs + ((mid_logical | rl) & cmask));
+            });
+        }
+    };
+    // ... or per tile from global memory (LAST view) / the shared-memory table (MID view)
+    auto apply_g = [&](float (&v)[E], const float* gr) {
+        if constexpr (PREG) {
+#pragma unroll
+            for (int m = 0; m < E / 4; ++m) scale4(v + 4 * m, make_float4(gr[4 * m], gr[4 * m + 1], gr[4 * m + 2], gr[4 * m + 3]));
+        } else if constexpr (ROUNDS == 3) {
+            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                scale4(v + 4 * m, ldg4(gs + coord));
+            });
+        } else {
+            gtab_for_each<N, C>(gt, gbase, [&](auto j_, const float4 w) {
+                constexpr int j = decltype(j_)::value;
+                scale4(v + 4 * j, w);
+            });
+        }
+    };
+    // this role's half of the dg partial sums -> workspace (registers [half*H, half*H + H))
+    auto store_dg_half = [&](const float (&acc)[E / 2], int half_is_upper, float* dst) {
+        if constexpr (ROUNDS == 3) {
+            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t off, uint32_t) {
+                constexpr int m = decltype(m_)::value;
+                constexpr int mh = m % (E / 8);
+                if ((m >= E / 8) == (half_is_upper != 0))
+                    *reinterpret_cast<float4*>(dst + off) = make_float4(acc[4 * mh], acc[4 * mh + 1], acc[4 * mh + 2], acc[4 * mh + 3]);
+            });
+        } else {
+            static_for<0, E / 2>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                constexpr uint32_t rl_lo = view_reg_logical(view_mid(N, C), r);
+                constexpr uint32_t rl_hi = view_reg_logical(view_mid(N, C), r + E / 2);
+                dst[mid_logical | (half_is_upper ? rl_hi : rl_lo)] = acc[r];
+            });
+        }
+    };
     float* __restrict__ slab = p.ws + (((int64_t(s) * p.ctas_per_sample + cta_in_sample) * PAIRS + pair) * 4) * TILE;
     const uint32_t hs_base = tid << (C - 1);           // this thread's H floats in a half-stash
     const uint32_t hs_swz = swz_of_tid(C - 1, tid);
@@ -188,11 +288,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
                 const float4 w = ldg4(p.s2 + coord);
                 s2r[4 * m] = w.x, s2r[4 * m + 1] = w.y, s2r[4 * m + 2] = w.z, s2r[4 * m + 3] = w.w;
             });
-            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
-                constexpr int m = decltype(m_)::value;
-                const float4 w = ldg4(gs + coord);
-                gr[4 * m] = w.x, gr[4 * m + 1] = w.y, gr[4 * m + 2] = w.z, gr[4 * m + 3] = w.w;
-            });
+            load_g_regs(gr);
         }
         float acc_1[E];
         float acc_b[WANT_DBIAS ? E : 1];
@@ -223,8 +319,8 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
                 const float4 w = PREG ? make_float4(s2r[4 * m], s2r[4 * m + 1], s2r[4 * m + 2], s2r[4 * m + 3]) : ldg4(p.s2 + coord);
                 mul4(a + 4 * m, q, w);
             });
-            transform_in<N, C, KT, T, SINGLE>(a, scratch, scratch2, tid, bar_role, k, wb_fm, wb_ml);  // a = t2 (LAST)
-            if constexpr (LEAN) role_sync<T>(bar_role);  // scratch (now the stash) is no longer being read
+            to_mid(a);  // a = t2 (middle layout)
+            if constexpr (LEAN || (ALIAS && SINGLE)) role_sync<T>(bar_role);  // scratch (now the stash) is no longer being read
 #pragma unroll
             for (int jj = 0; jj < H / 4; ++jj)   // publish the upper half of t2
                 *reinterpret_cast<float4*>(stash_t2 + hs_base + ((jj ^ hs_swz) << 2)) =
@@ -236,12 +332,8 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
                 fma4(acc_g + 4 * jj, d, a + 4 * jj);
             }
             bar_wait<2 * T>(bar_pair);  // both half-stashes consumed
-            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
-                constexpr int m = decltype(m_)::value;
-                const float4 w = PREG ? make_float4(gr[4 * m], gr[4 * m + 1], gr[4 * m + 2], gr[4 * m + 3]) : ldg4(gs + coord);
-                scale4(a + 4 * m, w);
-            });
-            transform_out<N, C, KT, T, SINGLE>(a, scratch, scratch2, tid, bar_role, k, wb_lm, wb_mf);  // a = t4 (FIRST)
+            apply_g(a, gr);
+            from_mid(a);  // a = t4 (FIRST layout)
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t) {
                 constexpr int m = decltype(m_)::value;
                 const float4 q = to_dy(raw4(stage_dy, off), tgt, off, left);
@@ -261,11 +353,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
             if constexpr (WANT_DBIAS)
                 *reinterpret_cast<float4*>(slab + 3 * TILE + off) = make_float4(acc_b[4 * m], acc_b[4 * m + 1], acc_b[4 * m + 2], acc_b[4 * m + 3]);
         });
-        for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t off, uint32_t) {
-            constexpr int m = decltype(m_)::value;
-            if constexpr (m < H / 4)
-                *reinterpret_cast<float4*>(slab + off) = make_float4(acc_g[4 * m], acc_g[4 * m + 1], acc_g[4 * m + 2], acc_g[4 * m + 3]);
-        });
+        store_dg_half(acc_g, 0, slab);
     } else {
         // ------------------------------------------------------------------ Y role
         float s1r[PREG ? E : 1], gr[PREG ? E : 1];
@@ -275,11 +363,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
                 const float4 w = ldg4(p.s1 + coord);
                 s1r[4 * m] = w.x, s1r[4 * m + 1] = w.y, s1r[4 * m + 2] = w.z, s1r[4 * m + 3] = w.w;
             });
-            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
-                constexpr int m = decltype(m_)::value;
-                const float4 w = ldg4(gs + coord);
-                gr[4 * m] = w.x, gr[4 * m + 1] = w.y, gr[4 * m + 2] = w.z, gr[4 * m + 3] = w.w;
-            });
+            load_g_regs(gr);
         }
         float acc_2[LEAN ? 1 : E];
         if constexpr (LEAN) {
@@ -307,8 +391,8 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
                 const float4 w = PREG ? make_float4(s1r[4 * m], s1r[4 * m + 1], s1r[4 * m + 2], s1r[4 * m + 3]) : ldg4(p.s1 + coord);
                 mul4(b + 4 * m, q, w);
             });
-            transform_in<N, C, KT, T, SINGLE>(b, scratch, scratch2, tid, bar_role, k, wb_fm, wb_ml);  // b = dt3 (LAST)
-            if constexpr (LEAN) role_sync<T>(bar_role);
+            to_mid(b);  // b = dt3 (middle layout)
+            if constexpr (LEAN || (ALIAS && SINGLE)) role_sync<T>(bar_role);
 #pragma unroll
             for (int jj = 0; jj < H / 4; ++jj)   // publish the lower half of dt3
                 *reinterpret_cast<float4*>(stash_d3 + hs_base + ((jj ^ hs_swz) << 2)) =
@@ -320,12 +404,8 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
                 fma4(acc_g + 4 * jj, t2, b + H + 4 * jj);
             }
             bar_wait<2 * T>(bar_pair);
-            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
-                constexpr int m = decltype(m_)::value;
-                const float4 w = PREG ? make_float4(gr[4 * m], gr[4 * m + 1], gr[4 * m + 2], gr[4 * m + 3]) : ldg4(gs + coord);
-                scale4(b + 4 * m, w);
-            });
-            transform_out<N, C, KT, T, SINGLE>(b, scratch, scratch2, tid, bar_role, k, wb_lm, wb_mf);  // b = dt1 (FIRST)
+            apply_g(b, gr);
+            from_mid(b);  // b = dt1 (FIRST layout)
             const bool want_dx = p.dx != nullptr;
             float* __restrict__ dxs = p.dx + int64_t(s) * p.sample_elems + e0;
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
@@ -353,12 +433,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
             else
                 *reinterpret_cast<float4*>(slab + 2 * TILE + off) = make_float4(acc_2[4 * m], acc_2[4 * m + 1], acc_2[4 * m + 2], acc_2[4 * m + 3]);
         });
-        for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t off, uint32_t) {
-            constexpr int m = decltype(m_)::value;
-            if constexpr (m >= H / 4)
-                *reinterpret_cast<float4*>(slab + off) = make_float4(acc_g[4 * (m - H / 4)], acc_g[4 * (m - H / 4) + 1],
-                                                                     acc_g[4 * (m - H / 4) + 2], acc_g[4 * (m - H / 4) + 3]);
-        });
+        store_dg_half(acc_g, 1, slab);
     }
 }
 
@@ -410,15 +485,16 @@ layer_bwd_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dg, fl
     }
 }
 
-template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS = false, bool PREG = false>
+template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS = false, bool PREG = false, int ROUNDS = 3>
 static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
 {
     static unsigned char smem_ok[4][64] = {};
     constexpr int threads = (2 << (N - C)) * PAIRS;
     constexpr size_t tile = size_t(1) << N;
-    constexpr size_t smem_plain = sizeof(float) * (2 * NS + (SINGLE ? 2 : 4) + (ALIAS ? 0 : 1)) * tile * PAIRS;
-    constexpr size_t smem_tgt = sizeof(float) * (3 * NS + (SINGLE ? 2 : 4) + (ALIAS ? 0 : 1)) * tile * PAIRS;  // RESID, target staged
-    const size_t smem = (c.target != nullptr && smem_tgt <= (MINB == 2 ? 112 : 200) * 1024) ? smem_tgt : smem_plain;
+    constexpr bool gtab = ROUNDS == 2 && !PREG;
+    constexpr size_t smem_plain = bwd_smem_bytes(N, PAIRS, NS, SINGLE, ALIAS, gtab, 2);
+    constexpr size_t smem_tgt = bwd_smem_bytes(N, PAIRS, NS, SINGLE, ALIAS, gtab, 3);  // RESID with the target staged
+    const size_t smem = (c.target != nullptr && bwd_stage_target(N, PAIRS, NS, SINGLE, ALIAS, gtab, MINB)) ? smem_tgt : smem_plain;
     const int64_t D = int64_t(1) << k;
     const int64_t tiles_per_sample = (c.B * D + int64_t(tile) - 1) / int64_t(tile);
     const Plan plan = make_plan(c.S, tiles_per_sample, PAIRS, 148 * 4, 8);
@@ -440,10 +516,10 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     };
     const bool db = c.dbias != nullptr, rs = c.target != nullptr;
     int rc;
-    if (db && rs) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, true, true>, 0);
-    else if (db) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, true, false>, 1);
-    else if (rs) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, false, true>, 2);
-    else rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, false, false>, 3);
+    if (db && rs) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, ROUNDS, true, true>, 0);
+    else if (db) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, ROUNDS, true, false>, 1);
+    else if (rs) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, ROUNDS, false, true>, 2);
+    else rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, ROUNDS, false, false>, 3);
     if (rc) return rc;
     const int warps = 8;
     dim3 rgrid(static_cast<unsigned>((D + warps - 1) / warps), static_cast<unsigned>(c.S + 1));
@@ -455,15 +531,17 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
 int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream)
 {
     const int k = ilog2(D);
-    // TMA-staged kernels: one CTA per SM (<= 176 KB shared memory at D <= 4096, 224 KB at
-    // D = 8192), NS = 2 stages, ping-pong transposition buffers where they fit, parameters
-    // register-resident where the register file allows (256 threads per CTA)
-    if (k >= 2 && k <= 6) return launch_bwd_tma_cfg<10, 5, k_family(2, 6), 4, 1, 2, false, false, true>(c, k, stream);
-    if (k >= 7 && k <= 9) return launch_bwd_tma_cfg<10, 5, k_family(7, 9), 4, 1, 2, false, false, true>(c, k, stream);
-    if (k == 10) return launch_bwd_tma_cfg<10, 5, 10, 4, 1, 2, false, false, true>(c, k, stream);
-    if (k == 11) return launch_bwd_tma_cfg<11, 5, 11, 2, 1, 2, false, false, true>(c, k, stream);
-    if (k == 12) return launch_bwd_tma_cfg<12, 5, 12, 1, 1, 2, false, false, true>(c, k, stream);
-    if (k == 13) return launch_bwd_tma_cfg<13, 5, 13, 1, 1, 2, true, false, false>(c, k, stream);
+    // TMA-staged kernels, one CTA per SM, NS = 2 stages, ping-pong transposition buffers where
+    // they fit, parameters register-resident where the register file allows.
+    // D <= 1024: two views (FIRST + MID cover all 10 tile bits), one warp per role, 4 pairs per CTA
+    if (k >= 2 && k <= 6) return launch_bwd_tma_cfg<10, 5, k_family(2, 6), 4, 1, 2, false, false, true, 2>(c, k, stream);
+    if (k >= 7 && k <= 9) return launch_bwd_tma_cfg<10, 5, k_family(7, 9), 4, 1, 2, false, false, true, 2>(c, k, stream);
+    if (k == 10) return launch_bwd_tma_cfg<10, 5, 10, 4, 1, 2, false, false, true, 2>(c, k, stream);
+    // D >= 2048: three views (a 64-float-per-thread two-view variant measured slower at D = 4096:
+    // 1.16 ms vs 1.08 ms -- too few warps and no room for register-resident parameters)
+    if (k == 11) return launch_bwd_tma_cfg<11, 5, 11, 2, 1, 2, false, false, true, 3>(c, k, stream);
+    if (k == 12) return launch_bwd_tma_cfg<12, 5, 12, 1, 1, 2, false, false, true, 3>(c, k, stream);
+    if (k == 13) return launch_bwd_tma_cfg<13, 5, 13, 1, 1, 2, true, false, false, 3>(c, k, stream);
     return fail(WHVI_E_SHAPE, "layer_bwd: D = %lld unsupported (4 <= D <= 8192)", (long long)D);
 }
 
