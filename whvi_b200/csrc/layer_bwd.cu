@@ -58,7 +58,7 @@ struct BwdArgs {
 //     each sends the other the half-stream it needs through a shared half-stash), which
 //     balances the register budgets at <= 112 so two CTAs (2 x 288 threads) fit per SM.
 // Shared memory per pair: NS x (x tile + dy tile) + X scratch + Y scratch + stash (1 tile).
-template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS, bool PREG, int ROUNDS, bool WANT_DBIAS, bool RESID>
+template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS, int PREG, int ROUNDS, bool WANT_DBIAS, bool RESID>
 __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_kernel(const BwdArgs p)
 {
     constexpr int T = 1 << (N - C);
@@ -356,12 +356,16 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
         store_dg_half(acc_g, 0, slab);
     } else {
         // ------------------------------------------------------------------ Y role
-        float s1r[PREG ? E : 1], gr[PREG ? E : 1];
+        float s1r[PREG ? E : 1], s2r[PREG == 2 ? E : 1], gr[PREG ? E : 1];  // PREG == 2: s2 (for dx) as well
         if constexpr (PREG) {
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
                 const float4 w = ldg4(p.s1 + coord);
                 s1r[4 * m] = w.x, s1r[4 * m + 1] = w.y, s1r[4 * m + 2] = w.z, s1r[4 * m + 3] = w.w;
+                if constexpr (PREG == 2) {
+                    const float4 u = ldg4(p.s2 + coord);
+                    s2r[4 * m] = u.x, s2r[4 * m + 1] = u.y, s2r[4 * m + 2] = u.z, s2r[4 * m + 3] = u.w;
+                }
             });
             load_g_regs(gr);
         }
@@ -411,7 +415,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
                 const float4 q = raw4(stage_x, off);
-                const float4 w = ldg4(p.s2 + coord);
+                const float4 w = PREG == 2 ? make_float4(s2r[4 * m], s2r[4 * m + 1], s2r[4 * m + 2], s2r[4 * m + 3]) : ldg4(p.s2 + coord);
                 if constexpr (LEAN) {
                     float4 t = *reinterpret_cast<float4*>(acc2_smem + m * 4 * T);
                     float tv[4] = {t.x, t.y, t.z, t.w};
@@ -485,7 +489,7 @@ layer_bwd_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dg, fl
     }
 }
 
-template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS = false, bool PREG = false, int ROUNDS = 3>
+template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS = false, int PREG = 0, int ROUNDS = 3>
 static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
 {
     static unsigned char smem_ok[4][64] = {};
@@ -534,14 +538,14 @@ int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream)
     // TMA-staged kernels, one CTA per SM, NS = 2 stages, ping-pong transposition buffers where
     // they fit, parameters register-resident where the register file allows.
     // D <= 1024: two views (FIRST + MID cover all 10 tile bits), one warp per role, 4 pairs per CTA
-    if (k >= 2 && k <= 6) return launch_bwd_tma_cfg<10, 5, k_family(2, 6), 4, 1, 2, false, false, true, 2>(c, k, stream);
-    if (k >= 7 && k <= 9) return launch_bwd_tma_cfg<10, 5, k_family(7, 9), 4, 1, 2, false, false, true, 2>(c, k, stream);
-    if (k == 10) return launch_bwd_tma_cfg<10, 5, 10, 4, 1, 2, false, false, true, 2>(c, k, stream);
+    if (k >= 2 && k <= 6) return launch_bwd_tma_cfg<10, 5, k_family(2, 6), 4, 1, 2, false, false, 1, 2>(c, k, stream);
+    if (k >= 7 && k <= 9) return launch_bwd_tma_cfg<10, 5, k_family(7, 9), 4, 1, 2, false, false, 1, 2>(c, k, stream);
+    if (k == 10) return launch_bwd_tma_cfg<10, 5, 10, 4, 1, 2, false, false, 1, 2>(c, k, stream);
     // D >= 2048: three views (a 64-float-per-thread two-view variant measured slower at D = 4096:
     // 1.16 ms vs 1.08 ms -- too few warps and no room for register-resident parameters)
-    if (k == 11) return launch_bwd_tma_cfg<11, 5, 11, 2, 1, 2, false, false, true, 3>(c, k, stream);
-    if (k == 12) return launch_bwd_tma_cfg<12, 5, 12, 1, 1, 2, false, false, true, 3>(c, k, stream);
-    if (k == 13) return launch_bwd_tma_cfg<13, 5, 13, 1, 1, 2, true, false, false, 3>(c, k, stream);
+    if (k == 11) return launch_bwd_tma_cfg<11, 5, 11, 2, 1, 2, false, false, 2, 3>(c, k, stream);
+    if (k == 12) return launch_bwd_tma_cfg<12, 5, 12, 1, 1, 2, false, false, 2, 3>(c, k, stream);
+    if (k == 13) return launch_bwd_tma_cfg<13, 5, 13, 1, 1, 2, true, false, 0, 3>(c, k, stream);
     return fail(WHVI_E_SHAPE, "layer_bwd: D = %lld unsupported (4 <= D <= 8192)", (long long)D);
 }
 
