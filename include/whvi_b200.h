@@ -125,6 +125,32 @@ WHVI_API int whvi_layer_bwd_fused_f32(const float* x, int64_t x_sample_stride, c
                                       int64_t D, int flags, const float* target, const float* coef,
                                       whvi_stream_t stream);
 
+/* whvi_layer_bwd_f32 with the upstream gradient taken as dy_scale[0] * dy (dy_scale: device
+ * scalar).  Lets a producer that computed its dx for a unit loss coefficient (whvi_layer_loss_f32)
+ * hand it on without a separate scaling pass over the activations. */
+WHVI_API int whvi_layer_bwd_scaled_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* dy_scale,
+                                       const float* g, const float* s1, const float* s2, float* dx, float* dg,
+                                       float* ds1, float* ds2, float* dbias, void* workspace, size_t workspace_bytes,
+                                       int64_t S, int64_t B, int64_t D, int flags, whvi_stream_t stream);
+
+/*
+ * Fused LAST layer of a regression network: forward + Gaussian-MNLL residual + backward in one
+ * pass over x (the predictions never touch HBM):
+ *   y_hat = s1*H(g[s]*H(s2*x)) (+bias);  r = y_hat - target (target (B,D), shared by the samples)
+ *   sq_partials[i], i < sq_count: partial sums of r^2 (their sum is the data term of
+ *       GaussianLikelihood.mnll_batch_estimate, src/likelihoods.py:18-29)
+ *   dx, dg, ds1, ds2, dbias: the layer's gradients for the upstream gradient dy = r, i.e. for a
+ *       unit coefficient; the caller multiplies by 2 * dLoss/d(sum r^2) (the small vectors
+ *       directly, dx through whvi_layer_bwd_scaled_f32 of the previous layer).
+ * 128 <= D <= 4096.  flags: WHVI_LAYER_RELU_IN.  dx may be NULL; dbias is required iff bias.
+ */
+WHVI_API int whvi_layer_loss_sizes(int64_t S, int64_t B, int64_t D, size_t* workspace_bytes, int64_t* sq_count);
+WHVI_API int whvi_layer_loss_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1,
+                                 const float* s2, const float* bias, const float* target, float* dx, float* dg,
+                                 float* ds1, float* ds2, float* dbias, float* sq_partials, void* workspace,
+                                 size_t workspace_bytes, int64_t S, int64_t B, int64_t D, int flags,
+                                 whvi_stream_t stream);
+
 /*
  * Reparameterisation (src/weights.py:43-50, :82-83, :92-93), one eps row per MC sample:
  *   mode 0:  g[s,:] = mu + softplus(rho) * eps[s,:]              (diagonal; the reference)

@@ -224,3 +224,33 @@ def test_reparam_dense_tcgen05_vs_oracle(S, D):
     (g * t(dg)).sum().backward()
     assert rel_err(mt.grad.cpu().numpy(), dg.sum(0)) < 1e-5
     assert rel_err(Lt.grad.cpu().numpy(), np.tril(dg.T @ eps)) < 1e-5
+
+
+@pytest.mark.parametrize("S,B,D,bias,shared", [(2, 37, 128, True, False), (3, 9, 512, False, False), (2, 21, 1024, True, False),
+                                                (2, 5, 2048, False, False), (2, 5, 4096, True, False), (3, 6, 1024, False, True)])
+def test_loss_layer_vs_oracle(S, B, D, bias, shared):
+    """whvi_layer_loss_f32: forward + residual + backward for a unit coefficient in one pass."""
+    from whvi_b200 import functional as F
+    x, g, s1, s2, _, bvec = make_case(S, B, D, 7 * D + B, shared)
+    rng = np.random.default_rng(D + 1)
+    target = rng.standard_normal((B, D))
+    bb = bvec if bias else None
+    sq, dx, dg, ds1, ds2, db = F.layer_loss_raw(t(x), t(g), t(s1), t(s2), None if bb is None else t(bb), t(target),
+                                                want_dx=True, relu_in=True)
+    y = O.layer_fwd(x, g, s1, s2, bb)
+    r = y - target[None]
+    assert abs(sq.item() - float((r ** 2).sum())) < 1e-4 * float((r ** 2).sum())
+    rdx, rdg, rds1, rds2, rdb = O.layer_bwd(x, r, g, s1, s2, want_dbias=True)
+    x32 = x.astype(np.float32)
+    dxn = dx.cpu().numpy()
+    if shared:
+        mask = (x32 > 0)[None]
+        ref_dx = (O.layer_bwd(np.broadcast_to(x, (S, B, D)).copy(), r, g, s1, s2)[0] * mask)
+        assert rel_err(dxn, ref_dx) < TOL
+    else:
+        assert rel_err(dxn, rdx * (x32 > 0)) < TOL
+    assert rel_err(dg.cpu().numpy(), rdg) < TOL
+    assert rel_err(ds1.cpu().numpy(), rds1) < TOL
+    assert rel_err(ds2.cpu().numpy(), rds2) < TOL
+    if bias:
+        assert rel_err(db.cpu().numpy(), rdb) < TOL

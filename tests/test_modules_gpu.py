@@ -207,7 +207,7 @@ def test_train_and_eval_model_run_and_learn():
     assert last < first
 
 
-@pytest.mark.parametrize("D,bias", [(64, False), (128, True), (1024, False)])
+@pytest.mark.parametrize("D,bias", [(64, False), (128, True), (1024, False), (2048, True), (4096, False)])
 def test_fused_relu_and_mnll_match_unfused(D, bias):
     """fuse=True (ReLU and Gaussian MNLL folded into the layer kernels) must give the same
     loss and gradients as fuse=False (every module its own op, like the reference)."""

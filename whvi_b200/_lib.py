@@ -32,6 +32,13 @@ SIGNATURES = {
     "whvi_layer_bwd_fused_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_int64, c_int64,
                                          c_int, c_void_p, c_void_p, c_void_p]),
+    "whvi_layer_bwd_scaled_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_int64,
+                                          c_int64, c_int, c_void_p]),
+    "whvi_layer_loss_sizes": (c_int, [c_int64, c_int64, c_int64, POINTER(c_size_t), POINTER(c_int64)]),
+    "whvi_layer_loss_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64,
+                                    c_int64, c_int64, c_int, c_void_p]),
     "whvi_reparam_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "whvi_reparam_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                      c_void_p]),

@@ -90,10 +90,10 @@ int whvi_layer_bwd_workspace_bytes(int64_t S, int64_t B, int64_t D, size_t* byte
     return launch_layer_bwd(c, D, nullptr);
 }
 
-int whvi_layer_bwd_fused_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* g, const float* s1,
-                             const float* s2, float* dx, float* dg, float* ds1, float* ds2, float* dbias,
-                             void* workspace, size_t workspace_bytes, int64_t S, int64_t B, int64_t D, int flags,
-                             const float* target, const float* coef, whvi_stream_t stream)
+static int layer_bwd_common(const float* x, int64_t x_sample_stride, const float* dy, const float* g, const float* s1,
+                            const float* s2, float* dx, float* dg, float* ds1, float* ds2, float* dbias,
+                            void* workspace, size_t workspace_bytes, int64_t S, int64_t B, int64_t D, int flags,
+                            const float* target, const float* coef, const float* dy_scale, whvi_stream_t stream)
 {
     if (int rc = check_layer_shape("layer_bwd", S, B, D, x_sample_stride)) return rc;
     if (flags & ~WHVI_LAYER_RELU_IN) return fail(WHVI_E_MODE, "layer_bwd: unknown flags %d", flags);
@@ -111,9 +111,63 @@ int whvi_layer_bwd_fused_f32(const float* x, int64_t x_sample_stride, const floa
     if (!aligned16(x) || !aligned16(dy) || !aligned16(g) || !aligned16(s1) || !aligned16(s2) || !aligned16(dx) ||
         !aligned16(workspace) || !aligned16(target))
         return fail(WHVI_E_ALIGN, "layer_bwd: pointers must be 16-byte aligned");
-    LayerBwdCall c{x, dy, g, s1, s2, target, coef, dx, dg, ds1, ds2, dbias, static_cast<float*>(workspace),
+    LayerBwdCall c{x, dy, g, s1, s2, target, coef, nullptr, dx, dg, ds1, ds2, dbias, static_cast<float*>(workspace),
                    workspace_bytes, x_sample_stride, S, B, flags & WHVI_LAYER_RELU_IN, nullptr};
+    c.dy_scale = dy_scale;
     return launch_layer_bwd(c, D, st);
+}
+
+int whvi_layer_bwd_fused_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* g, const float* s1,
+                             const float* s2, float* dx, float* dg, float* ds1, float* ds2, float* dbias,
+                             void* workspace, size_t workspace_bytes, int64_t S, int64_t B, int64_t D, int flags,
+                             const float* target, const float* coef, whvi_stream_t stream)
+{
+    return layer_bwd_common(x, x_sample_stride, dy, g, s1, s2, dx, dg, ds1, ds2, dbias, workspace, workspace_bytes, S, B, D,
+                            flags, target, coef, nullptr, stream);
+}
+
+int whvi_layer_bwd_scaled_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* dy_scale,
+                              const float* g, const float* s1, const float* s2, float* dx, float* dg, float* ds1,
+                              float* ds2, float* dbias, void* workspace, size_t workspace_bytes, int64_t S, int64_t B,
+                              int64_t D, int flags, whvi_stream_t stream)
+{
+    return layer_bwd_common(x, x_sample_stride, dy, g, s1, s2, dx, dg, ds1, ds2, dbias, workspace, workspace_bytes, S, B, D,
+                            flags, nullptr, nullptr, dy_scale, stream);
+}
+
+int whvi_layer_loss_sizes(int64_t S, int64_t B, int64_t D, size_t* workspace_bytes, int64_t* sq_count)
+{
+    if (!workspace_bytes || !sq_count) return fail(WHVI_E_NULL, "layer_loss_sizes: null pointer");
+    if (int rc = check_layer_shape("layer_loss_sizes", S, B, D, 0, 4096)) return rc;
+    if (D < 128) return fail(WHVI_E_SHAPE, "layer_loss: D = %lld outside [128, 4096]", (long long)D);
+    *workspace_bytes = 0;
+    *sq_count = 0;
+    if (S == 0 || B == 0) return WHVI_OK;
+    LayerLossCall c{};
+    c.S = S;
+    c.B = B;
+    c.need_ws = workspace_bytes;
+    c.need_sq = sq_count;
+    return launch_layer_loss(c, D, nullptr);
+}
+
+int whvi_layer_loss_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1, const float* s2,
+                        const float* bias, const float* target, float* dx, float* dg, float* ds1, float* ds2,
+                        float* dbias, float* sq_partials, void* workspace, size_t workspace_bytes, int64_t S, int64_t B,
+                        int64_t D, int flags, whvi_stream_t stream)
+{
+    if (int rc = check_layer_shape("layer_loss", S, B, D, x_sample_stride, 4096)) return rc;
+    if (D < 128) return fail(WHVI_E_SHAPE, "layer_loss: D = %lld outside [128, 4096]", (long long)D);
+    if (flags & ~WHVI_LAYER_RELU_IN) return fail(WHVI_E_MODE, "layer_loss: unknown flags %d", flags);
+    if (S == 0 || B == 0) return fail(WHVI_E_SHAPE, "layer_loss: empty batch");
+    if (!x || !g || !s1 || !s2 || !target || !dg || !ds1 || !ds2 || !sq_partials || (bias && !dbias))
+        return fail(WHVI_E_NULL, "layer_loss: null pointer");
+    if (!aligned16(x) || !aligned16(g) || !aligned16(s1) || !aligned16(s2) || !aligned16(bias) || !aligned16(target) ||
+        !aligned16(dx) || !aligned16(workspace))
+        return fail(WHVI_E_ALIGN, "layer_loss: pointers must be 16-byte aligned");
+    LayerLossCall c{x, g, s1, s2, bias, target, dx, dg, ds1, ds2, dbias, sq_partials, static_cast<float*>(workspace),
+                    workspace_bytes, x_sample_stride, S, B, flags & WHVI_LAYER_RELU_IN, nullptr, nullptr};
+    return launch_layer_loss(c, D, static_cast<cudaStream_t>(stream));
 }
 
 int whvi_layer_bwd_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* g, const float* s1,

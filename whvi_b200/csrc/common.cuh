@@ -62,13 +62,25 @@ struct LayerFwdCall {
     size_t* partials_needed;  // query mode: number of floats of sq_partials
 };
 struct LayerBwdCall {
-    const float *x, *dy, *g, *s1, *s2, *target, *coef;
+    const float *x, *dy, *g, *s1, *s2, *target, *coef, *dy_scale;
     float *dx, *dg, *ds1, *ds2, *dbias, *ws;
     size_t ws_bytes;
     int64_t xs, S, B;
     int relu_in;
     size_t* need_only;  // query mode: workspace bytes
 };
+struct LayerLossCall {  // fused last layer: forward + Gaussian-MNLL residual + backward in one pass
+    const float *x, *g, *s1, *s2, *bias, *target;
+    float *dx, *dg, *ds1, *ds2, *dbias, *sq_partials, *ws;
+    size_t ws_bytes;
+    int64_t xs, S, B;
+    int relu_in;
+    size_t* need_ws;      // query mode
+    int64_t* need_sq;     // query mode
+};
+int launch_layer_loss(const LayerLossCall& c, int64_t D, cudaStream_t stream);
+int launch_bwd_reduce(const float* ws, float* dg, float* ds1, float* ds2, float* dbias, int64_t S, int slabs_per_sample,
+                      int64_t tile, int64_t D, cudaStream_t stream);
 int launch_layer_fwd(const LayerFwdCall& c, int64_t D, cudaStream_t stream);
 int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream);
 int launch_reparam_diag(const float* mu, const float* rho, const float* eps, float* g, int64_t S, int64_t D,

@@ -33,6 +33,8 @@ struct BwdArgs {
     int relu_in;           // x is the output of a fused ReLU: dx *= (x > 0)
     const float* target;   // RESID: (B,D); dy := coef[0] * (dy_buffer - target)  (fused Gaussian-MNLL gradient)
     const float* coef;     // RESID: device scalar
+    const float* dy_scale; // optional device scalar: the upstream gradient is dy_scale[0] * dy (deferred
+                           // scaling of a producer that computed its dx for a unit loss coefficient)
 };
 
 // Stream-role specialised, TMA-staged backward.  Every tile is worked on by a PAIR of thread
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     const float* __restrict__ gs = p.g + (int64_t(s) << k);
     float coef = 1.f;
     if constexpr (RESID) coef = __ldg(p.coef);
+    const float dysc = p.dy_scale != nullptr ? __ldg(p.dy_scale) : 1.f;
     const float relu_thr = p.relu_in ? 0.f : -INFINITY;
 
     const uint32_t off_f = tile_thread_offset<N, C, V_FIRST>(tid);
@@ -268,6 +271,8 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
                 tg = ldg4(tgt + off);
             }
             q = make_float4(coef * (q.x - tg.x), coef * (q.y - tg.y), coef * (q.z - tg.z), coef * (q.w - tg.w));
+        } else {
+            q = make_float4(dysc * q.x, dysc * q.y, dysc * q.z, dysc * q.w);
         }
         return q;
     };
@@ -489,6 +494,16 @@ layer_bwd_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dg, fl
     }
 }
 
+int launch_bwd_reduce(const float* ws, float* dg, float* ds1, float* ds2, float* dbias, int64_t S, int slabs_per_sample,
+                      int64_t tile, int64_t D, cudaStream_t stream)
+{
+    const int warps = 8;
+    dim3 rgrid(static_cast<unsigned>((D + warps - 1) / warps), static_cast<unsigned>(S + 1));
+    layer_bwd_reduce_kernel<<<rgrid, warps * 32, 0, stream>>>(ws, dg, ds1, ds2, dbias, static_cast<int>(S), slabs_per_sample,
+                                                              tile, static_cast<int>(D));
+    return check_launch("layer_bwd_reduce_kernel");
+}
+
 template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS = false, int PREG = 0, int ROUNDS = 3>
 static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
 {
@@ -512,7 +527,7 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     const int64_t ctas = int64_t(plan.ctas_per_sample) * c.S;
     if (ctas > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "layer_bwd: grid too large");
     BwdArgs a{c.x, c.xs, c.dy, c.g, c.s1, c.s2, c.dx, c.ws, c.B * D, static_cast<int>(c.S), plan.ctas_per_sample, plan.iters_per_group, k,
-              c.relu_in, c.target, c.coef};
+              c.relu_in, c.target, c.coef, c.dy_scale};
     auto go = [&](auto kernel, int slot) -> int {
         if (int rc = ensure_smem(kernel, smem, smem_ok[slot])) return rc;
         kernel<<<static_cast<unsigned>(ctas), threads, smem, stream>>>(a);
@@ -525,11 +540,7 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     else if (rs) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, ROUNDS, false, true>, 2);
     else rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, ROUNDS, false, false>, 3);
     if (rc) return rc;
-    const int warps = 8;
-    dim3 rgrid(static_cast<unsigned>((D + warps - 1) / warps), static_cast<unsigned>(c.S + 1));
-    layer_bwd_reduce_kernel<<<rgrid, warps * 32, 0, stream>>>(c.ws, c.dg, c.ds1, c.ds2, c.dbias, static_cast<int>(c.S),
-                                                              plan.ctas_per_sample * PAIRS, int64_t(tile), static_cast<int>(D));
-    return check_launch("layer_bwd_reduce_kernel");
+    return launch_bwd_reduce(c.ws, c.dg, c.ds1, c.ds2, c.dbias, c.S, plan.ctas_per_sample * PAIRS, int64_t(tile), D, stream);
 }
 
 int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream)

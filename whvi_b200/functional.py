@@ -20,7 +20,8 @@ _WORKSPACES: dict[tuple[int, int], torch.Tensor] = {}
 # Kernel-launch accounting (bench.py reads it): launches issued by each C-ABI call.
 LAUNCH_COUNTS: dict[str, int] = {}
 _LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_layer_fwd_f32": 1, "whvi_layer_bwd_f32": 2,
-                      "whvi_layer_fwd_fused_f32": 1, "whvi_layer_bwd_fused_f32": 2, "whvi_reparam_f32": 1,
+                      "whvi_layer_fwd_fused_f32": 1, "whvi_layer_bwd_fused_f32": 2,
+                      "whvi_layer_bwd_scaled_f32": 2, "whvi_layer_loss_f32": 2, "whvi_reparam_f32": 1,
                       "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1}
 # When set to a dict {"name": [(start_event, stop_event), ...]}, the named calls are bracketed
 # by CUDA events on the launching stream (bench.py's per-kernel roofline timing).
@@ -122,7 +123,8 @@ def layer_forward_raw(x, g, s1, s2, bias=None, out=None, relu_out=False, target=
     return out
 
 
-def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False, relu_in=False, target=None, coef=None):
+def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False, relu_in=False, target=None, coef=None,
+                       dy_scale=None):
     """Returns (dx | None, dg, ds1, ds2, dbias | None); dx is (S,B,D) even for shared x.
     ``relu_in``: x came out of a fused ReLU, dx is masked by x > 0.  ``target``/``coef``:
     ``dy`` holds the layer's saved output and the upstream gradient is
@@ -143,6 +145,17 @@ def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False, relu_in
     need = ctypes.c_size_t(0)
     _lib.check(L.whvi_layer_bwd_workspace_bytes(S, B, D, ctypes.byref(need)), "whvi_layer_bwd_workspace_bytes")
     ws = _workspace(dev, need.value)
+    if dy_scale is not None:  # upstream gradient = dy_scale * dy (see WHVILayerLossFunction)
+        if target is not None:
+            raise RuntimeError("dy_scale and target are mutually exclusive")
+        dy_scale = _f32c(dy_scale, "dy_scale").reshape(1)
+        with torch.cuda.device(dev), _Timed("whvi_layer_bwd_scaled_f32"):
+            rc = L.whvi_layer_bwd_scaled_f32(x.data_ptr(), xs, dy.data_ptr(), dy_scale.data_ptr(), g.data_ptr(),
+                                             s1.data_ptr(), s2.data_ptr(), _ptr(dx), dg.data_ptr(), ds1.data_ptr(),
+                                             ds2.data_ptr(), _ptr(dbias), ws.data_ptr(), ws.numel(), S, B, D,
+                                             1 if relu_in else 0, _stream(dev))
+        _lib.check(rc, "whvi_layer_bwd_scaled_f32")
+        return dx, dg, ds1, ds2, dbias
     with torch.cuda.device(dev), _Timed("whvi_layer_bwd_fused_f32"):
         rc = L.whvi_layer_bwd_fused_f32(x.data_ptr(), xs, dy.data_ptr(), g.data_ptr(), s1.data_ptr(), s2.data_ptr(),
                                         _ptr(dx), dg.data_ptr(), ds1.data_ptr(), ds2.data_ptr(), _ptr(dbias),
@@ -150,6 +163,43 @@ def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False, relu_in
                                         _ptr(coef), _stream(dev))
     _lib.check(rc, "whvi_layer_bwd_fused_f32")
     return dx, dg, ds1, ds2, dbias
+
+
+LOSS_LAYER_MIN_D, LOSS_LAYER_MAX_D = 128, 4096
+
+# dx tensors handed out by WHVILayerLossFunction for a UNIT loss coefficient, keyed by data_ptr,
+# with the scalar they still have to be multiplied by; consumed by WHVILayerFunction.backward.
+_PENDING_DY_SCALE: dict[int, torch.Tensor] = {}
+
+
+def layer_loss_raw(x, g, s1, s2, bias, target, want_dx=True, relu_in=False):
+    """Fused last layer (forward + squared-error residual + backward for a unit coefficient).
+    Returns (sum r^2 as a 0-d tensor, dx | None, dg, ds1, ds2, dbias | None)."""
+    x, g, s1, s2 = _f32c(x, "x"), _f32c(g, "g"), _f32c(s1, "s1"), _f32c(s2, "s2")
+    S, B, D, xs = _layer_dims(x, g, s1, s2)
+    target = _f32c(target, "target")
+    if target.shape != (B, D):
+        raise RuntimeError(f"target must be {(B, D)}, got {tuple(target.shape)}")
+    if bias is not None:
+        bias = _f32c(bias, "bias").reshape(-1)
+    dev = x.device
+    L = _lib.lib()
+    need, nsq = ctypes.c_size_t(0), ctypes.c_int64(0)
+    _lib.check(L.whvi_layer_loss_sizes(S, B, D, ctypes.byref(need), ctypes.byref(nsq)), "whvi_layer_loss_sizes")
+    ws = _workspace(dev, need.value)
+    sqp = torch.empty(max(nsq.value, 1), dtype=torch.float32, device=dev)
+    dx = torch.empty((S, B, D), dtype=torch.float32, device=dev) if want_dx else None
+    dg = torch.empty((S, D), dtype=torch.float32, device=dev)
+    ds1 = torch.empty(D, dtype=torch.float32, device=dev)
+    ds2 = torch.empty(D, dtype=torch.float32, device=dev)
+    dbias = torch.empty(D, dtype=torch.float32, device=dev) if bias is not None else None
+    with torch.cuda.device(dev), _Timed("whvi_layer_loss_f32"):
+        rc = L.whvi_layer_loss_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
+                                   target.data_ptr(), _ptr(dx), dg.data_ptr(), ds1.data_ptr(), ds2.data_ptr(),
+                                   _ptr(dbias), sqp.data_ptr(), ws.data_ptr(), ws.numel(), S, B, D,
+                                   1 if relu_in else 0, _stream(dev))
+    _lib.check(rc, "whvi_layer_loss_f32")
+    return sqp.sum(), dx, dg, ds1, ds2, dbias
 
 
 class WHVILayerFunction(Function):
@@ -175,8 +225,9 @@ class WHVILayerFunction(Function):
         x, g, s1, s2 = ctx.saved_tensors
         want_dx = ctx.needs_input_grad[0]
         want_db = ctx.has_bias and ctx.needs_input_grad[4]
+        scale = _PENDING_DY_SCALE.pop(dy.data_ptr(), None)  # dy came from a fused loss layer, still unscaled
         dx, dg, ds1, ds2, dbias = layer_backward_raw(x, dy, g, s1, s2, want_dx=want_dx, want_dbias=want_db,
-                                                     relu_in=ctx.relu_in)
+                                                     relu_in=ctx.relu_in, dy_scale=scale)
         if dx is not None and x.dim() == 2:
             dx = dx.sum(dim=0)
         return dx, dg, ds1, ds2, dbias, None, None
@@ -224,6 +275,46 @@ class WHVILayerSqErrFunction(Function):
 
 def whvi_layer_sqerr(x, g, s1, s2, bias, target, relu_in=False):
     return WHVILayerSqErrFunction.apply(x, g, s1, s2, bias, target, relu_in)
+
+
+class WHVILayerLossFunction(Function):
+    """Training-time last layer fused with the Gaussian-MNLL data term: returns only
+    ``sum (y_hat - target)^2``; the predictions never exist in HBM and the layer's whole backward
+    is computed in the same pass (for a unit loss coefficient) and kept for ``backward``.
+
+    ``defer_dx_scale``: the producer of ``x`` is a fused ``WHVILayerFunction`` (set by
+    ``WHVINetwork`` in matching pairs, like relu_out/relu_in); ``dx`` is then handed on unscaled
+    and the consumer's backward kernel applies the scalar on load, saving a pass over dx."""
+
+    @staticmethod
+    def forward(ctx, x, g, s1, s2, bias, target, relu_in=False, defer_dx_scale=False):
+        want_dx = ctx.needs_input_grad[0]
+        sq, dx, dg, ds1, ds2, dbias = layer_loss_raw(x, g, s1, s2, bias, target, want_dx=want_dx, relu_in=relu_in)
+        ctx.shared_x = x.dim() == 2
+        ctx.defer = bool(defer_dx_scale) and want_dx and not ctx.shared_x
+        ctx.has_dx, ctx.has_db = dx is not None, dbias is not None
+        ctx.save_for_backward(*[t for t in (dx, dg, ds1, ds2, dbias) if t is not None])
+        return sq
+
+    @staticmethod
+    def backward(ctx, d_sq):
+        saved = list(ctx.saved_tensors)
+        dx = saved.pop(0) if ctx.has_dx else None
+        dg, ds1, ds2 = saved[0], saved[1], saved[2]
+        dbias = saved[3] if ctx.has_db else None
+        c = (2.0 * d_sq).to(torch.float32)
+        if dx is not None:
+            if ctx.shared_x:
+                dx = dx.sum(dim=0) * c
+            elif ctx.defer:
+                _PENDING_DY_SCALE[dx.data_ptr()] = c.reshape(1)
+            else:
+                dx = dx.mul_(c)
+        return dx, dg * c, ds1 * c, ds2 * c, None if dbias is None else dbias * c, None, None, None
+
+
+def whvi_layer_loss(x, g, s1, s2, bias, target, relu_in=False, defer_dx_scale=False):
+    return WHVILayerLossFunction.apply(x, g, s1, s2, bias, target, relu_in, defer_dx_scale)
 
 
 class ReparamFunction(Function):

@@ -98,7 +98,11 @@ class WHVINetwork(nn.Module, WHVI):
                     w = module.weight_submodule
                     relu_out = (i + 2 < len(modules) and type(modules[i + 1]) is nn.ReLU
                                 and self._fusable_square(modules[i + 2]))
-                    if last and sqerr_target is not None:
+                    if last and sqerr_target is not None and w.loss_fusable and torch.is_grad_enabled():
+                        # training: forward + residual + backward of the last layer in one pass
+                        sq = w.forward_loss(h, sqerr_target, relu_in=relu_in, defer_dx_scale=relu_in)
+                        h = None
+                    elif last and sqerr_target is not None:
                         h, sq = w.forward_sqerr(h, sqerr_target, relu_in=relu_in)
                     else:
                         h = w.forward(h, relu_out=relu_out, relu_in=relu_in)
@@ -115,7 +119,7 @@ class WHVINetwork(nn.Module, WHVI):
         finally:
             for layer in layers:
                 layer.mc_samples = None
-        if h.dim() == 2:  # no WHVI layer introduced a sample axis: S identical predictions
+        if h is not None and h.dim() == 2:  # no WHVI layer introduced a sample axis: S identical predictions
             h = h.unsqueeze(0).expand(n_samples, *h.shape)
         return (h, sq) if sqerr_target is not None else h
 

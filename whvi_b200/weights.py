@@ -153,6 +153,18 @@ class WHVISquarePow2Matrix(nn.Module):
         bias = None if self.bias is None else self.bias.reshape(-1)
         return WF.whvi_layer_sqerr(h, g, self.s1, self.s2, bias, target, relu_in)
 
+    def forward_loss(self, h, target, *, relu_in=False, defer_dx_scale=False):
+        """Training-time fused last layer: sum (y - target)^2 with the layer's backward computed in
+        the same pass (functional.WHVILayerLossFunction).  Returns the 0-d sum only."""
+        S, _ = self._resolve_samples(h)
+        g = WF.reparam(self.g_mu, self.g_rho, self._draw_eps(S))
+        bias = None if self.bias is None else self.bias.reshape(-1)
+        return WF.whvi_layer_loss(h, g, self.s1, self.s2, bias, target, relu_in, defer_dx_scale)
+
+    @property
+    def loss_fusable(self):
+        return self.fusable and WF.LOSS_LAYER_MIN_D <= self.D <= WF.LOSS_LAYER_MAX_D
+
     def _as_written(self, h, eps):
         """src/weights.py:93 per sample: h @ (w_bar(mu) + w_bar(sigma*eps)).T"""
         outs = []
