@@ -236,7 +236,8 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
     WF.LAUNCH_COUNTS.clear()
-    WF.EVENT_SINK = {"whvi_layer_bwd_fused_f32": [], "whvi_layer_fwd_fused_f32": []}
+    WF.EVENT_SINK = {"whvi_layer_bwd_fused_f32": [], "whvi_layer_bwd_scaled_f32": [], "whvi_layer_fwd_fused_f32": [],
+                     "whvi_layer_loss_f32": []}
     with ClockSampler(local_rank) as clk:
         ms_total = timed(lambda: step(x_dev, y_dev), args.steps)
     sink, WF.EVENT_SINK = WF.EVENT_SINK, None
@@ -277,8 +278,9 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (fused backward) from events inside the timed region
     peak, peak_src = measured_peaks()
-    bwd_ms = [a.elapsed_time(b) for a, b in sink["whvi_layer_bwd_fused_f32"]]
+    bwd_ms = [a.elapsed_time(b) for a, b in sink["whvi_layer_bwd_fused_f32"] + sink["whvi_layer_bwd_scaled_f32"]]
     fwd_ms = [a.elapsed_time(b) for a, b in sink["whvi_layer_fwd_fused_f32"]]
+    loss_ms = [a.elapsed_time(b) for a, b in sink["whvi_layer_loss_f32"]]
     rows_per_launch = chunk * B
     bwd_avg = sum(bwd_ms) / len(bwd_ms)
     fwd_avg = sum(fwd_ms) / len(fwd_ms)
@@ -300,6 +302,13 @@ def run_ours(args):
                 "share_of_step": sum(bwd_ms) / ms_total,
                 "fwd_kernel": {"achieved": fwd_gbs, "frac": fwd_gbs / peak, "avg_launch_ms": fwd_avg,
                                "algorithmic_bytes_per_row": 8 * D, "share_of_step": sum(fwd_ms) / ms_total}}
+    if loss_ms:  # fused last layer (forward + MNLL residual + backward in one pass: x in, dx out)
+        loss_avg = sum(loss_ms) / len(loss_ms)
+        loss_gbs = 8.0 * D * rows_per_launch / (loss_avg * 1e-3) / 1e9
+        roofline["loss_kernel"] = {"kernel": "layer_loss_kernel (+ layer_bwd_reduce_kernel)", "achieved": loss_gbs,
+                                   "frac": loss_gbs / peak, "avg_launch_ms": loss_avg, "algorithmic_bytes_per_row": 8 * D,
+                                   "share_of_step": sum(loss_ms) / ms_total,
+                                   "note": "replaces a forward (8 B/elt) + backward (12 B/elt) pair of the last layer"}
 
     out = None
     if rank == 0:
@@ -332,7 +341,8 @@ def run_ours(args):
                "config": {"workload": WORKLOAD, "D": D, "B": B, "S": S_TOTAL, "layers": N_LAYERS,
                           "rows_counted": "S*B*layers per step", "parallelism": f"mc-sample-shard x{world}",
                           "samples_per_launch": chunk, "l2": "inputs larger than L2 (2 GiB activations per launch)",
-                          "step": "fwd + MNLL + KL + bwd + grad all-reduce (N>1) + Adam"},
+                          "step": "fwd + MNLL + KL + bwd + grad all-reduce (N>1) + Adam",
+                          "fusion": "ReLU folded into the layer kernels; last layer fwd+MNLL+bwd in one kernel"},
                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                        "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4},
                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--dims", default="16,128,1024,2048,4096,8192")
     ap.add_argument("--samples", type=int, default=16)
     ap.add_argument("--out", default="")
-    ap.add_argument("--mode", default="plain", choices=["plain", "shared", "target"],
+    ap.add_argument("--mode", default="plain", choices=["plain", "shared", "target", "loss"],
                     help="plain: per-sample x; shared: one (B,D) x block for all samples (first layer); "
                          "target: fused MNLL residual (last layer)")
     args = ap.parse_args()
@@ -49,6 +49,10 @@ def main():
             f_med, _ = time_op(lambda: F.layer_forward_raw(x, g, s1, s2, out=y, target=tgt))
             b_med, _ = time_op(lambda: F.layer_backward_raw(x, dy, g, s1, s2, want_dx=True, relu_in=True, target=tgt,
                                                             coef=coef), warmup=3, iters=10)
+        elif args.mode == "loss":  # fused last layer: the "forward" column is 0, "bwd" is the whole fused pass
+            tgt = torch.randn(B, D, device=dev)
+            f_med = 1e-9
+            b_med, _ = time_op(lambda: F.layer_loss_raw(x, g, s1, s2, None, tgt, want_dx=True, relu_in=True), warmup=3, iters=10)
         else:
             f_med, _ = time_op(lambda: F.layer_forward_raw(x, g, s1, s2, out=y))
             b_med = float("inf")

@@ -17,8 +17,13 @@
 //            dbias += r -> publishes r in the stage's second tile
 //   Y role:  (one half-tile behind) dt3 = H(s1*r) -> dg += dt3*t2 -> dt1 = H(g*dt3) -> ds2 += dt1*x,
 //            dx = s2*dt1 (masked by x > 0 after a fused ReLU)
-// Stage = [x tile | r tile | target tile]; x and target arrive by bulk async copy, r is written by X.
-// mbarriers per stage: full (TMA landed), ready (X -> Y: r and t2 published), empty (Y -> producer).
+// Stage = [x tile | target tile]; both arrive by bulk async copy and X overwrites the target tile
+// in place with r.  mbarriers per stage: full (TMA landed), ready (X -> Y: r and t2 published),
+// empty (Y -> producer).  Because Y works one tile behind X, the ring is NS = 3 deep and the
+// producer (thread 0 of X) refills a stage at the END of its iteration: the stage it needs was
+// released by Y one tile ago, so it does not stall, and the copy still has a whole tile of lead
+// time.  (With 2 stages and the refill at the start of an iteration X waits for Y and the two
+// roles serialise: measured 2x slower.)
 #include "layer_common.cuh"
 
 namespace whvi {
@@ -49,7 +54,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, 1) layer_loss_kernel(c
     constexpr int E = 1 << C;
     constexpr int64_t TILE = int64_t(1) << N;
     constexpr int SCR = SINGLE ? 1 : 2;
-    constexpr int PAIR_FLOATS = (3 * NS + 2 * SCR + NS) * int(TILE);  // stages, scratch, one full t2 stash per stage
+    constexpr int PAIR_FLOATS = (2 * NS + 2 * SCR + NS) * int(TILE);  // stages, scratch, one full t2 stash per stage
     static_assert(ROUNDS == 3 || rounds_needed(N, C, N) <= 2, "2-view kernel needs FIRST+MID to cover all bits");
     static_assert(ROUNDS == 3 || PREG > 0, "the 2-view loss kernel keeps g in registers");
     extern __shared__ float4 smem4[];
@@ -83,19 +88,19 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, 1) layer_loss_kernel(c
         if (it >= NS) mbar_wait(&empty_bar[pr][st], ((it / NS) & 1) ^ 1);
         const int64_t left = p.sample_elems - e0;
         const uint32_t bytes = static_cast<uint32_t>((left < TILE ? left : TILE) * sizeof(float));
-        float* stage = smem + size_t(pr) * PAIR_FLOATS + size_t(st) * 3 * TILE;
+        float* stage = smem + size_t(pr) * PAIR_FLOATS + size_t(st) * 2 * TILE;
         mbar_arrive_expect_tx(&full_bar[pr][st], 2 * bytes);
         bulk_g2s(stage, xbase + e0, bytes, &full_bar[pr][st]);
-        bulk_g2s(stage + 2 * TILE, p.target + e0, bytes, &full_bar[pr][st]);
+        bulk_g2s(stage + TILE, p.target + e0, bytes, &full_bar[pr][st]);
     };
 
     const int role = threadIdx.x / (T * PAIRS);        // 0 = X, 1 = Y (warp-uniform)
     const int pair = (threadIdx.x % (T * PAIRS)) / T;
     const uint32_t tid = threadIdx.x % T;
     float* pair_smem = smem + size_t(pair) * PAIR_FLOATS;
-    float* scratch = pair_smem + (3 * NS + SCR * role) * TILE;
+    float* scratch = pair_smem + (2 * NS + SCR * role) * TILE;
     float* scratch2 = scratch + (SINGLE ? 0 : TILE);
-    float* stash0 = pair_smem + (3 * NS + 2 * SCR) * TILE;       // + st * TILE
+    float* stash0 = pair_smem + (2 * NS + 2 * SCR) * TILE;       // + st * TILE
     const int bar_role = 1 + 2 * pair + role;
     const float* __restrict__ gs = p.g + (int64_t(s) << k);
     const float relu_thr = p.relu_in ? 0.f : -INFINITY;
@@ -199,11 +204,10 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, 1) layer_loss_kernel(c
             if (e0 >= p.sample_elems) break;
             const int64_t left = p.sample_elems - e0;
             const int st = it % NS;
-            float* stage_x = pair_smem + size_t(st) * 3 * TILE;
-            float* stage_r = stage_x + TILE;
-            float* stage_t = stage_x + 2 * TILE;
+            float* stage_x = pair_smem + size_t(st) * 2 * TILE;
+            float* stage_t = stage_x + TILE;   // target on arrival ...
+            float* stage_r = stage_t;          // ... overwritten in place with r
             float* stash = stash0 + size_t(st) * TILE;
-            if (tid == 0) issue_tile(it + NS - 1, pair);
             mbar_wait(&full_bar[pair][st], (it / NS) & 1);
             if (left < TILE) {  // partial tile: zero this thread's float4s beyond the valid part (x and target)
                 static_for<0, E / 4>([&](auto m_) {
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, 1) layer_loss_kernel(c
                 *reinterpret_cast<float4*>(stage_r + off) = r;  // the Y role's upstream gradient
             });
             mbar_arrive(&ready_bar[pair][st]);  // release: r and t2 of this tile are published
+            if (tid == 0) issue_tile(it + NS - 1, pair);  // refill the stage Y released one tile ago
         }
         for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t) {
             constexpr int m = decltype(m_)::value;
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, 1) layer_loss_kernel(c
             if (e0 >= p.sample_elems) break;
             const int64_t left = p.sample_elems - e0;
             const int st = it % NS;
-            const float* stage_x = pair_smem + size_t(st) * 3 * TILE;
+            const float* stage_x = pair_smem + size_t(st) * 2 * TILE;
             const float* stage_r = stage_x + TILE;
             const float* stash = stash0 + size_t(st) * TILE;
             mbar_wait(&ready_bar[pair][st], (it / NS) & 1);  // r, t2 (and, transitively, the TMA data) are visible
@@ -331,7 +336,7 @@ static int launch_loss_cfg(const LayerLossCall& c, int k, cudaStream_t stream)
     constexpr int T = 1 << (N - C);
     constexpr int threads = 2 * T * PAIRS;
     constexpr size_t tile = size_t(1) << N;
-    constexpr size_t smem = sizeof(float) * (3 * NS + (SINGLE ? 2 : 4) + NS) * tile * PAIRS;
+    constexpr size_t smem = sizeof(float) * (2 * NS + (SINGLE ? 2 : 4) + NS) * tile * PAIRS;
     static_assert(smem <= 227 * 1024, "loss kernel shared memory");
     const int64_t D = int64_t(1) << k;
     const int64_t tiles_per_sample = (c.B * D + int64_t(tile) - 1) / int64_t(tile);
@@ -363,10 +368,10 @@ static int launch_loss_cfg(const LayerLossCall& c, int k, cudaStream_t stream)
 int launch_layer_loss(const LayerLossCall& c, int64_t D, cudaStream_t stream)
 {
     const int k = ilog2(D);
-    if (k >= 7 && k <= 9) return launch_loss_cfg<10, 5, k_family(7, 9), 4, 2, false, 1, 2>(c, k, stream);
-    if (k == 10) return launch_loss_cfg<10, 5, 10, 4, 2, false, 1, 2>(c, k, stream);
-    if (k == 11) return launch_loss_cfg<11, 5, 11, 2, 2, false, 1, 3>(c, k, stream);
-    if (k == 12) return launch_loss_cfg<12, 5, 12, 1, 2, false, 1, 3>(c, k, stream);
+    if (k >= 7 && k <= 9) return launch_loss_cfg<10, 5, k_family(7, 9), 4, 3, false, 1, 2>(c, k, stream);
+    if (k == 10) return launch_loss_cfg<10, 5, 10, 4, 3, false, 1, 2>(c, k, stream);
+    if (k == 11) return launch_loss_cfg<11, 5, 11, 2, 3, false, 1, 3>(c, k, stream);
+    if (k == 12) return launch_loss_cfg<12, 5, 12, 1, 3, false, 1, 3>(c, k, stream);
     return fail(WHVI_E_SHAPE, "layer_loss: D = %lld unsupported (128 <= D <= 4096)", (long long)D);
 }
 
