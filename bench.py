@@ -137,6 +137,44 @@ def cpu_fwht_baseline(threads: int):
     return {"gbs": 8.0 * rows * D / dt / 1e9, "kind": kind, "D": D, "rows": rows, "cores": threads, "seconds": dt}
 
 
+def gpu_fwht_reference_baseline(fwht_ours, dev, log2n: int = 28):
+    """The reference's own CUDA FWHT (src/fwht/cuda, recompiled for sm_100a into oracle/_ref/fwht_cuda.so
+    with the torch-API renames of SURVEY F3 only) timed on this GPU next to this repo's kernel, same
+    inputs, through its public entry (which clones its input, fwht_cuda.cpp:11).  D <= 2^12 only: its
+    launch shape is invalid beyond.  Baseline leg: the one other place bench.py may execute
+    oracle/."""
+    import torch
+    from oracle import ref_torch
+    mod = ref_torch.fwht_cuda_module()
+    if mod is None:
+        return None
+    n = 1 << log2n
+    x = torch.randn(n, device=dev)
+    out = []
+    for k in (6, 10, 12):
+        Dk = 1 << k
+        xv = x.view(n // Dk, Dk)
+        try:
+            got = mod.fwht(xv)
+            ours = fwht_ours(xv)
+            diff = float((got - ours).abs().max() / ours.abs().max())
+            del got, ours
+            for _ in range(2):
+                mod.fwht(xv)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                mod.fwht(xv)
+            b.record()
+            b.synchronize()
+            ms = a.elapsed_time(b) / 5
+            out.append({"D": Dk, "ms": round(ms, 3), "gbs": round(8.0 * n / ms / 1e6, 1), "max_rel_diff_vs_ours": diff})
+        except Exception as e:  # a baseline must never take the bench down
+            out.append({"D": Dk, "error": str(e)[:120]})
+    return {"kind": "reference CUDA kernel recompiled for sm_100a (oracle/_ref/fwht_cuda.so)", "elements": n, "sweep": out}
+
+
 # --------------------------------------------------------------------------- reference arm
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -335,6 +373,7 @@ def run_ours(args):
         threads = os.cpu_count() or 1
         cpu = cpu_layer_baseline(threads) if not args.no_cpu_baseline else None
         cpu_f = cpu_fwht_baseline(threads) if not args.no_cpu_baseline else None
+        gpu_f = gpu_fwht_reference_baseline(fwht_, dev) if not args.no_cpu_baseline else None
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -346,7 +385,7 @@ def run_ours(args):
                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                        "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4},
                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-               "fwht": {"elements": n, "unit": "GB/s", "sweep": fw, "cpu_baseline": cpu_f},
+               "fwht": {"elements": n, "unit": "GB/s", "sweep": fw, "cpu_baseline": cpu_f, "ref_cuda_baseline": gpu_f},
                "clocks": clk.summary()}
         print(json.dumps(out))
     if world > 1:

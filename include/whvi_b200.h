@@ -112,8 +112,13 @@ WHVI_API int whvi_layer_bwd_f32(const float* x, int64_t x_sample_stride, const f
  *            target != NULL -> `dy` points at the layer's saved OUTPUT and the upstream
  *            gradient is formed on the fly as coef[0] * (output - target) (coef: device
  *            scalar), the gradient of the Gaussian MNLL, so it never exists in HBM.
+ *  forward:  flags & WHVI_LAYER_FROM_T2   -> `x` already holds t2 = H(s2 * x) (one whvi_fwht_f32 of
+ *            the scaled inputs, shared by all samples: the first transform is sample-independent,
+ *            SURVEY 8d C5), so only y = s1 * H(g_s * t2) (+ bias) is left; s2 is not read.
+ *            Not combinable with `target`.
  */
 #define WHVI_LAYER_RELU_OUT 1
+#define WHVI_LAYER_FROM_T2 2
 #define WHVI_LAYER_RELU_IN 1
 WHVI_API int whvi_layer_fwd_partials(int64_t S, int64_t B, int64_t D, int64_t* count);
 WHVI_API int whvi_layer_fwd_fused_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1,
@@ -177,6 +182,16 @@ WHVI_API int whvi_reparam_bwd_f32(const float* rho, const float* eps, const floa
  * out_kl: device float[1].  dmu/drho: (D) or both NULL; they receive grad_scale * dKL/d.
  * (accumulate != 0: added to the existing contents).
  */
+/*
+ * MC predictive moments (the reduction WHVIRegression.eval_model does over the
+ * sample axis of WHVINetwork.forward's (B, out, S) output, src/networks.py:36-54, :131-132):
+ *   sum_y[i] (+)= sum_s y[s*n + i],  sum_y2[i] (+)= sum_s y[s*n + i]^2,   i < n (= B*D), n % 4 == 0.
+ * accumulate != 0 adds to the existing contents (sample chunks); s ascending, so results are
+ * bit-reproducible.  sum_y2 may be NULL.
+ */
+WHVI_API int whvi_mc_moments_f32(const float* y, float* sum_y, float* sum_y2, int64_t S, int64_t n, int accumulate,
+                                 whvi_stream_t stream);
+
 #define WHVI_KL_REFERENCE 0
 #define WHVI_KL_CONSISTENT 1
 WHVI_API int whvi_kl_f32(const float* mu, const float* rho, float lambda_, int64_t D, int mode, float* out_kl,

@@ -9,7 +9,18 @@
   GPU box with ``gpurun``.  It is only attempted when ``/root/reference`` exists (this
   container); the GPU box uses the prebuilt file.
 
-Run ``python oracle/build.py`` to build both.
+* ``build_ref_cuda()`` compiles the reference's CUDA FWHT extension
+  (``/root/reference/src/fwht/cuda/fwht_cuda.cpp`` + ``fwht_cuda_kernel.cu``) for sm_100a
+  into ``oracle/_ref/fwht_cuda.so`` -- the GPU baseline "recompiled reference kernel"
+  and a parity cross-check for D <= 2^12.  The sources do not compile against torch
+  2.11 as they are (``X.type()`` / ``X.data<T>()`` were removed), so the
+  recipe streams them through the 2-expression ``sed`` SURVEY App. C documents into a
+  temporary directory OUTSIDE the repo (deleted afterwards) and runs ``nvcc`` on that;
+  the kernels themselves are untouched.  Slow (torch headers through nvcc, ~3 min):
+  only built on request (``python oracle/build.py --ref-cuda``) or by
+  ``__graft_entry__.build()`` when the file is missing.
+
+Run ``python oracle/build.py`` to build the first two.
 """
 from __future__ import annotations
 
@@ -25,6 +36,8 @@ REF_DIR = HERE / "_ref"
 ORACLE_SO = BUILD_DIR / "libwhvi_oracle.so"
 REF_SO = REF_DIR / "fwht_cpp.so"
 REF_SRC = Path("/root/reference/src/fwht/cpp/fwht.cpp")
+REF_CUDA_SO = REF_DIR / "fwht_cuda.so"
+REF_CUDA_DIR = Path("/root/reference/src/fwht/cuda")
 
 
 def _newer(target: Path, *sources: Path) -> bool:
@@ -71,9 +84,52 @@ def build_ref(force: bool = False) -> Path | None:
     return REF_SO
 
 
+def build_ref_cuda(force: bool = False) -> Path | None:
+    """Compile the reference CUDA FWHT (API-renames only) into oracle/_ref/fwht_cuda.so."""
+    srcs = [REF_CUDA_DIR / "fwht_cuda.cpp", REF_CUDA_DIR / "fwht_cuda_kernel.cu"]
+    if not all(p.exists() for p in srcs):
+        return REF_CUDA_SO if REF_CUDA_SO.exists() else None
+    if not force and _newer(REF_CUDA_SO, *srcs):
+        return REF_CUDA_SO
+    import re
+    import tempfile
+
+    import torch
+    from torch.utils import cpp_extension
+
+    REF_DIR.mkdir(exist_ok=True)
+    torch_lib = Path(torch.__file__).resolve().parent / "lib"
+    inc = [f"-I{p}" for p in cpp_extension.include_paths(device_type="cuda")]
+    inc.append(f"-I{sysconfig.get_paths()['include']}")
+    with tempfile.TemporaryDirectory(prefix="whvi_refcuda_") as tmp:
+        patched = []
+        for p in srcs:
+            text = p.read_text()
+            # torch >= 1.? API renames only (SURVEY F3 / App. C); kernels are untouched
+            text = re.sub(r"\bX\.type\(\)", "X.scalar_type()", text)
+            text = re.sub(r"\bX\.data<scalar_t>\(\)", "X.data_ptr<scalar_t>()", text)
+            q = Path(tmp) / p.name
+            q.write_text(text)
+            patched.append(str(q))
+        cmd = [
+            "nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+            "-gencode", "arch=compute_100a,code=sm_100a",
+            "-DTORCH_EXTENSION_NAME=fwht_cuda", "-DTORCH_API_INCLUDE_EXTENSION_H",
+            f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+            "--expt-relaxed-constexpr", "-diag-suppress=20012,20013,20014,20015",
+            *inc, *patched, "-o", str(REF_CUDA_SO),
+            f"-L{torch_lib}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
+            "-Xlinker", f"-rpath={torch_lib}",
+        ]
+        subprocess.run(cmd, check=True)
+    return REF_CUDA_SO
+
+
 def main() -> int:
     print("oracle:", build_oracle(force="--force" in sys.argv))
     print("reference fwht_cpp:", build_ref(force="--force" in sys.argv))
+    if "--ref-cuda" in sys.argv:
+        print("reference fwht_cuda:", build_ref_cuda(force="--force" in sys.argv))
     return 0
 
 

@@ -91,3 +91,19 @@ def fwht_cpp_module():
         return fwht_cpp
     except Exception:
         return None
+
+
+def fwht_cuda_module():
+    """The reference's CUDA FWHT extension recompiled for sm_100a (oracle/_ref/fwht_cuda.so, built by
+    oracle/build.py --ref-cuda with the torch-API renames of SURVEY F3 only) or None.  A GPU
+    baseline and parity cross-check for D <= 2^12 (its launch shape is invalid beyond)."""
+    ref_dir = Path(__file__).resolve().parent / "_ref"
+    if not (ref_dir / "fwht_cuda.so").exists():
+        return None
+    if str(ref_dir) not in sys.path:
+        sys.path.insert(0, str(ref_dir))
+    try:
+        import fwht_cuda
+        return fwht_cuda
+    except Exception:
+        return None

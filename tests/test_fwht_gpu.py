@@ -147,3 +147,23 @@ def test_full_size_properties(k):
     idx = [0, 1, rows // 2, rows - 1]
     ref = O.fwht(x[idx].cpu().numpy().astype(np.float64))
     assert rel_err(y[idx].cpu().numpy(), ref) < FWHT_TOL
+
+
+@pytest.mark.parametrize("k,rows", [(2, 7), (5, 33), (6, 1000), (10, 19), (11, 40), (12, 9)])
+def test_against_reference_cuda_kernel(k, rows):
+    """The reference's own CUDA kernel (src/fwht/cuda, recompiled for sm_100a by oracle/build.py
+    --ref-cuda) run on this GPU on the same inputs: D <= 2^12, the range where its launch shape is
+    valid.  Tolerance = the reference's own CUDA test (test/walsh.py:61-79: atol 1e-4 at
+    D = 1024) restated as the north_star's 1e-5 relative."""
+    from oracle import ref_torch
+    mod = ref_torch.fwht_cuda_module()
+    if mod is None:
+        pytest.skip("oracle/_ref/fwht_cuda.so not built (python oracle/build.py --ref-cuda)")
+    from whvi_b200 import fwht_
+    D = 1 << k
+    g = torch.Generator(device="cuda").manual_seed(k * 100 + rows)
+    x = torch.randn(rows, D, device="cuda", generator=g)
+    ref = mod.fwht(x)
+    torch.cuda.synchronize()
+    got = fwht_(x)
+    assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5

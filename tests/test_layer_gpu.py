@@ -97,6 +97,67 @@ def test_forward_large_dims(S, B, D):
         F.layer_backward_raw(t(x), t(dy), t(g), t(s1), t(s2))
 
 
+@pytest.mark.parametrize("S,B,D", [(2, 5, 4), (3, 7, 64), (2, 9, 128), (2, 5, 1024), (2, 3, 2048), (2, 3, 4096), (2, 3, 8192),
+                                   (2, 3, 16384), (3, 2, 32768)])
+def test_forward_from_t2(S, B, D):
+    """FROM_T2: the sample-independent first transform hoisted out -- same result as
+    the full chain, checked against the oracle."""
+    from whvi_b200 import functional as F
+    from whvi_b200.fwht import fwht_
+    x, g, s1, s2, dy, bias = make_case(S, B, D, 3 * D + S, shared=True)
+    t2 = fwht_(t(x) * t(s2))
+    for b in (None, bias):
+        y = F.layer_forward_raw(t2, t(g), t(s1), t(s2), None if b is None else t(b), from_t2=True)
+        assert rel_err(y.cpu().numpy(), O.layer_fwd(x, g, s1, s2, b)) < TOL
+    with pytest.raises(RuntimeError, match="FROM_T2"):
+        F.layer_forward_raw(t2, t(g), t(s1), t(s2), target=t(x), from_t2=True)
+
+
+@pytest.mark.parametrize("S,n", [(1, 4), (5, 1028), (16, 40000), (0, 64), (7, 12)])
+def test_mc_moments(S, n):
+    from whvi_b200 import functional as F
+    rng = np.random.default_rng(S * 1000 + n)
+    y = rng.standard_normal((S, n)).astype(np.float32)
+    a0, b0 = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    a, b = t(a0), t(b0)
+    F.mc_moments_(t(y).reshape(S, n), a, b, accumulate=True)
+    y64 = y.astype(np.float64)
+    assert rel_err(a.cpu().numpy(), a0 + y64.sum(0)) < 1e-6
+    assert rel_err(b.cpu().numpy(), b0 + (y64 * y64).sum(0)) < 1e-6
+    F.mc_moments_(t(y).reshape(S, n), a, None, accumulate=False)
+    assert rel_err(a.cpu().numpy(), y64.sum(0)) < 1e-6 or S == 0
+    with pytest.raises(RuntimeError):
+        F.mc_moments_(t(y).reshape(S, n), a[:-1].clone(), None)
+
+
+@pytest.mark.parametrize("S,B,D,chunk", [(8, 5, 64, 3), (6, 3, 4096, 4), (5, 2, 32768, 2)])
+def test_predictive_moments_vs_oracle(S, B, D, chunk):
+    """BASELINE config 5 path: predictive mean/variance over MC samples without the (S,B,D) tensor."""
+    import whvi_b200 as W
+    rng = np.random.default_rng(D + S)
+    layer = W.WHVISquarePow2Matrix(D, lambda_=1.0, bias=True).to(dev())
+    with torch.no_grad():
+        for p in (layer.s1, layer.s2, layer.g_mu):
+            p.copy_(t(rng.standard_normal(D)))
+        layer.bias.copy_(t(rng.standard_normal((1, D))))
+    x, eps = rng.standard_normal((B, D)), rng.standard_normal((S, D))
+    layer.inject_eps(t(eps))
+    sy, sy2, n = layer.predictive_moments(t(x), chunk_samples=chunk)
+    assert n == S
+    p64 = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in layer.named_parameters()}
+    g = O.reparam(p64["g_mu"], p64["g_rho"], eps)
+    y = O.layer_fwd(x, g, p64["s1"], p64["s2"], p64["bias"].reshape(-1))
+    assert rel_err(sy.cpu().numpy(), y.sum(0)) < TOL
+    assert rel_err(sy2.cpu().numpy(), (y * y).sum(0)) < TOL
+    # sample shards add up (what reduce_predictive_moments all-reduces)
+    layer.inject_eps(t(eps))
+    a1, b1, n1 = layer.predictive_moments(t(x), chunk_samples=chunk, sample_range=(0, S // 2))
+    layer.inject_eps(t(eps))
+    a2, b2, n2 = layer.predictive_moments(t(x), chunk_samples=chunk, sample_range=(S // 2, S))
+    assert n1 + n2 == S
+    assert rel_err((a1 + a2).cpu().numpy(), y.sum(0)) < TOL
+
+
 def test_backward_without_dx_and_bias_and_determinism():
     from whvi_b200 import functional as F
     x, g, s1, s2, dy, _ = make_case(3, 41, 256, 5)

@@ -96,10 +96,12 @@ def c3():
 
 
 def c5(n_inputs: int):
+    """MC predictive mean/variance, D = 2^15, S = 256: per input chunk t2 = H(s2 x) once, then per
+    sample chunk one FROM_T2 forward (one transform per (s, b) pair) and one moments pass."""
     D, S, chunk_b, chunk_s = 1 << 15, 256, 256, 16
     torch.manual_seed(0)
     layer = W.WHVISquarePow2Matrix(D, lambda_=1.0).to(dev)
-    mean_abs = 0.0
+    mean_abs = torch.zeros((), device=dev)
     t0 = time.perf_counter()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -107,23 +109,19 @@ def c5(n_inputs: int):
     with torch.no_grad():
         for b0 in range(0, n_inputs, chunk_b):
             x = torch.randn(chunk_b, D, device=dev)          # inputs generated on the device, never materialised in full
-            s_y = torch.zeros(chunk_b, D, device=dev)
-            s_y2 = torch.zeros(chunk_b, D, device=dev)
-            for s0 in range(0, S, chunk_s):
-                g = F.reparam(layer.g_mu, layer.g_rho, torch.randn(chunk_s, D, device=dev))
-                y = F.layer_forward_raw(x, g, layer.s1, layer.s2)   # (chunk_s, chunk_b, D), x shared by the samples
-                s_y += y.sum(0)
-                s_y2 += (y * y).sum(0)
-            mean = s_y / S
-            var = s_y2 / S - mean * mean
-            mean_abs += float(mean.abs().mean()) + float(var.mean()) * 0.0
+            s_y, s_y2, n = layer.predictive_moments(x, S, chunk_samples=chunk_s)
+            mean = s_y / n
+            var = s_y2 / n - mean * mean
+            mean_abs += mean.abs().mean() + var.mean() * 0.0
     b.record()
     b.synchronize()
     ms = a.elapsed_time(b)
     rows = n_inputs * S
     return {"config": f"C5 WHVILinear(32768,32768) MC predictive mean/var, {n_inputs} inputs x {S} samples (bounded sample of 1M inputs)",
             "ms": ms, "mc_rows_per_s": rows / (ms * 1e-3), "fwd_algorithmic_gbs": 8.0 * D * rows / ms / 1e6,
-            "wall_s": time.perf_counter() - t0}
+            "note": "first transform hoisted out of the sample loop (1 transform per (s,b) pair); 8*D B/row is the "
+                    "unhoisted layer's algorithmic traffic, kept as the common yardstick",
+            "wall_s": time.perf_counter() - t0, "checksum": float(mean_abs)}
 
 
 def main():

@@ -35,6 +35,10 @@ def main():
     ap.add_argument("--kmin", type=int, default=2)
     ap.add_argument("--kmax", type=int, default=15)
     ap.add_argument("--out", default="")
+    ap.add_argument("--baselines", action="store_true",
+                    help="also time torch's dense fp32 H @ x (what the reference layer uses below D = 2^12, "
+                         "src/fwht/python/fwht.py:17-32) on the same inputs; the reference's own CUDA kernel is "
+                         "timed by bench.py's baseline leg")
     args = ap.parse_args()
     n = 1 << args.log2n
     dev = torch.device("cuda:0")
@@ -49,8 +53,23 @@ def main():
         xv, yv = x.view(n // D, D), y.view(n // D, D)
         med, best = time_op(lambda: fwht_(xv, out=yv))
         gbs = nbytes / med / 1e6
-        res["sweep"].append({"D": D, "rows": n // D, "ms_median": med, "ms_best": best, "gbs_median": gbs,
-                             "gbs_best": nbytes / best / 1e6})
+        row = {"D": D, "rows": n // D, "ms_median": med, "ms_best": best, "gbs_median": gbs,
+               "gbs_best": nbytes / best / 1e6}
+        if args.baselines and 2 <= k <= 12:
+            if k >= 6:
+                sgn = torch.tensor([[1.0, 1.0], [1.0, -1.0]], device=dev)
+                H = sgn
+                while H.size(0) < D:
+                    H = torch.kron(H, sgn)
+                prev = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = False
+                m3, _ = time_op(lambda: torch.matmul(xv, H, out=yv), 2, 5)
+                torch.backends.cuda.matmul.allow_tf32 = prev
+                row["torch_matmul_fp32_ms"] = m3
+                row["torch_matmul_fp32_gbs"] = nbytes / m3 / 1e6
+                del H
+            print("      baselines:", {a: round(b, 3) for a, b in row.items() if a.startswith("torch_")})
+        res["sweep"].append(row)
         print(f"D=2^{k:<2d} rows={n // D:>9d}  {med:8.3f} ms  {gbs:7.0f} GB/s  (best {nbytes / best / 1e6:7.0f})"
               f"  {gbs / res['copy_gbs_median'] * 100:5.1f}% of copy")
     if args.out:

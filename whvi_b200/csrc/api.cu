@@ -60,7 +60,7 @@ int whvi_layer_fwd_fused_f32(const float* x, int64_t x_sample_stride, const floa
                              const float* target, float* sq_partials, whvi_stream_t stream)
 {
     if (int rc = check_layer_shape("layer_fwd", S, B, D, x_sample_stride, 32768)) return rc;
-    if (flags & ~WHVI_LAYER_RELU_OUT) return fail(WHVI_E_MODE, "layer_fwd: unknown flags %d", flags);
+    if (flags & ~(WHVI_LAYER_RELU_OUT | WHVI_LAYER_FROM_T2)) return fail(WHVI_E_MODE, "layer_fwd: unknown flags %d", flags);
     if (S == 0 || B == 0) return WHVI_OK;
     if (!x || !g || !s1 || !s2 || !y) return fail(WHVI_E_NULL, "layer_fwd: null pointer");
     if (target && !sq_partials) return fail(WHVI_E_NULL, "layer_fwd: target given without sq_partials");
@@ -68,6 +68,7 @@ int whvi_layer_fwd_fused_f32(const float* x, int64_t x_sample_stride, const floa
         !aligned16(target))
         return fail(WHVI_E_ALIGN, "layer_fwd: pointers must be 16-byte aligned");
     LayerFwdCall c{x, g, s1, s2, bias, target, y, sq_partials, x_sample_stride, S, B, flags & WHVI_LAYER_RELU_OUT, nullptr};
+    c.from_t2 = (flags & WHVI_LAYER_FROM_T2) ? 1 : 0;
     return launch_layer_fwd(c, D, static_cast<cudaStream_t>(stream));
 }
 
@@ -211,6 +212,16 @@ int whvi_kl_f32(const float* mu, const float* rho, float lambda_, int64_t D, int
     if (!mu || !rho || !out_kl) return fail(WHVI_E_NULL, "kl: null pointer");
     if ((dmu == nullptr) != (drho == nullptr)) return fail(WHVI_E_NULL, "kl: dmu and drho must both be given or both NULL");
     return launch_kl(mu, rho, lambda_, D, mode, out_kl, dmu, drho, grad_scale, accumulate, static_cast<cudaStream_t>(stream));
+}
+
+int whvi_mc_moments_f32(const float* y, float* sum_y, float* sum_y2, int64_t S, int64_t n, int accumulate,
+                        whvi_stream_t stream)
+{
+    if (S < 0 || n < 0 || (n & 3)) return fail(WHVI_E_SHAPE, "mc_moments: S=%lld n=%lld (n must be a multiple of 4)", (long long)S, (long long)n);
+    if (n == 0) return WHVI_OK;
+    if (!sum_y || (S > 0 && !y)) return fail(WHVI_E_NULL, "mc_moments: null pointer");
+    if (!aligned16(y) || !aligned16(sum_y) || !aligned16(sum_y2)) return fail(WHVI_E_ALIGN, "mc_moments: pointers must be 16-byte aligned");
+    return launch_mc_moments(y, sum_y, sum_y2, S, n, accumulate, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

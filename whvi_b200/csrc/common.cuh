@@ -60,6 +60,7 @@ struct LayerFwdCall {
     int64_t xs, S, B;
     int relu_out;
     size_t* partials_needed;  // query mode: number of floats of sq_partials
+    int from_t2 = 0;          // x already holds H(s2 * x)
 };
 struct LayerBwdCall {
     const float *x, *dy, *g, *s1, *s2, *target, *coef, *dy_scale;
@@ -88,6 +89,7 @@ int launch_reparam_diag(const float* mu, const float* rho, const float* eps, flo
 int launch_reparam_dense(const float* mu, const float* L, const float* eps, float* g, int64_t S, int64_t D, cudaStream_t stream);
 int launch_reparam_diag_bwd(const float* rho, const float* eps, const float* dg, float* dmu, float* drho, int64_t S,
                             int64_t D, int accumulate, cudaStream_t stream);
+int launch_mc_moments(const float* y, float* sum_y, float* sum_y2, int64_t S, int64_t n, int accumulate, cudaStream_t stream);
 int launch_kl(const float* mu, const float* rho, float lambda_, int64_t D, int mode, float* out, float* dmu, float* drho,
               float grad_scale, int accumulate, cudaStream_t stream);
 

@@ -33,6 +33,8 @@ struct FwdArgs {
     int iters_per_group;
     int k;                  // log2(D)
     int relu_out;           // y = max(y, 0)
+    // FROM_T2: x already holds t2 = H(s2 * x) (sample-independent by linearity, SURVEY 8d C5:
+    // computed once per input row with whvi_fwht_f32), so one transform per (sample, row) is left
     const float* target;    // HAS_TARGET: (B, D); sum (y - target)^2 goes to sq_partials[cta]
     float* sq_partials;
 };
@@ -44,7 +46,7 @@ struct FwdArgs {
 // transposition but half the shared memory).
 // Flags that guard LOADS are template parameters: a run-time branch around a load inside the
 // unrolled float4 loops stops the compiler from batching the loads (measured: 2x slower).
-template <int N, int C, int KT, int GROUPS, int ROUNDS, int BUFS, int MINB, bool HAS_BIAS, bool HAS_TARGET>
+template <int N, int C, int KT, int GROUPS, int ROUNDS, int BUFS, int MINB, bool HAS_BIAS, bool HAS_TARGET, bool FROM_T2>
 __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kernel(const FwdArgs a)
 {
     constexpr int T = 1 << (N - C);
@@ -102,38 +104,55 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
         }
 
         float v[E];
-        for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
-            constexpr int m = decltype(m_)::value;
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (off < left) q = ldg_stream(xs + off);
-            const float4 w = ldg4(a.s2 + coord);
-            mul4(v + 4 * m, q, w);
-        });
-        if constexpr (ROUNDS == 3) {
-            transform_in<N, C, KT, T, BUFS == 1>(v, bufA, bufB, tid, bar, k, wb_fm, wb_ml);
-            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+        if constexpr (FROM_T2 && ROUNDS == 3) {
+            // t2 read straight in the LAST view (also float4-coalesced), times g, then H
+            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (off < left) q = ldg_stream(xs + off);
                 const float4 w = ldg4(gs + coord);
-                scale4(v + 4 * m, w);
+                mul4(v + 4 * m, q, w);
             });
             transform_out<N, C, KT, T, BUFS == 1>(v, bufA, bufB, tid, bar, k, wb_lm, wb_mf);
         } else {
-            bfly_round<N, C, KT, SEQ2_IN, 0>(v, k);
-            if constexpr (BUFS == 1) role_sync<T>(bar);  // previous tile's reads of bufA are done
-            transpose_write<N, C, V_FIRST, V_MID>(v, bufA, wb_fm);
-            role_sync<T>(bar);
-            transpose_read<C>(v, bufA, tid);
-            bfly_round<N, C, KT, SEQ2_IN, 1>(v, k);
-            gtab_for_each<N, C>(gt, gbase, [&](auto j_, const float4 w) {
-                constexpr int j = decltype(j_)::value;
-                scale4(v + 4 * j, w);
+            for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (off < left) q = ldg_stream(xs + off);
+                if constexpr (FROM_T2) {
+                    v[4 * m] = q.x, v[4 * m + 1] = q.y, v[4 * m + 2] = q.z, v[4 * m + 3] = q.w;
+                } else {
+                    const float4 w = ldg4(a.s2 + coord);
+                    mul4(v + 4 * m, q, w);
+                }
             });
-            bfly_round<N, C, KT, SEQ2_OUT, 0>(v, k);
-            if constexpr (BUFS == 1) role_sync<T>(bar);
-            transpose_write<N, C, V_MID, V_FIRST>(v, bufB, wb_mf);
-            role_sync<T>(bar);
-            transpose_read<C>(v, bufB, tid);
-            bfly_round<N, C, KT, SEQ2_OUT, 1>(v, k);
+            if constexpr (ROUNDS == 3) {
+                transform_in<N, C, KT, T, BUFS == 1>(v, bufA, bufB, tid, bar, k, wb_fm, wb_ml);
+                for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+                    constexpr int m = decltype(m_)::value;
+                    const float4 w = ldg4(gs + coord);
+                    scale4(v + 4 * m, w);
+                });
+                transform_out<N, C, KT, T, BUFS == 1>(v, bufA, bufB, tid, bar, k, wb_lm, wb_mf);
+            } else {
+                // FROM_T2: the first transform is already done; only the move to the MID view is left
+                if constexpr (!FROM_T2) bfly_round<N, C, KT, SEQ2_IN, 0>(v, k);
+                if constexpr (BUFS == 1) role_sync<T>(bar);  // previous tile's reads of bufA are done
+                transpose_write<N, C, V_FIRST, V_MID>(v, bufA, wb_fm);
+                role_sync<T>(bar);
+                transpose_read<C>(v, bufA, tid);
+                if constexpr (!FROM_T2) bfly_round<N, C, KT, SEQ2_IN, 1>(v, k);
+                gtab_for_each<N, C>(gt, gbase, [&](auto j_, const float4 w) {
+                    constexpr int j = decltype(j_)::value;
+                    scale4(v + 4 * j, w);
+                });
+                bfly_round<N, C, KT, SEQ2_OUT, 0>(v, k);
+                if constexpr (BUFS == 1) role_sync<T>(bar);
+                transpose_write<N, C, V_MID, V_FIRST>(v, bufB, wb_mf);
+                role_sync<T>(bar);
+                transpose_read<C>(v, bufB, tid);
+                bfly_round<N, C, KT, SEQ2_OUT, 1>(v, k);
+            }
         }
         for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
             constexpr int m = decltype(m_)::value;
@@ -180,7 +199,7 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
 template <int N, int C, int KT, int GROUPS, int ROUNDS, int BUFS, int MINB>
 static int launch_fwd_cfg(const LayerFwdCall& c, int k, cudaStream_t stream)
 {
-    static unsigned char smem_ok[4][64] = {};
+    static unsigned char smem_ok[6][64] = {};
     constexpr int threads = (1 << (N - C)) * GROUPS;
     constexpr size_t tile = size_t(1) << N;
     constexpr size_t smem = sizeof(float) * (tile * BUFS * GROUPS + (ROUNDS == 2 ? tile : 0));
@@ -203,10 +222,15 @@ static int launch_fwd_cfg(const LayerFwdCall& c, int k, cudaStream_t stream)
         return check_launch("layer_fwd_kernel");
     };
     const bool hb = c.bias != nullptr, ht = c.target != nullptr;
-    if (hb && ht) return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, true, true>, 0);
-    if (hb) return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, true, false>, 1);
-    if (ht) return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, false, true>, 2);
-    return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, false, false>, 3);
+    if (c.from_t2) {
+        if (ht) return fail(WHVI_E_MODE, "layer_fwd: FROM_T2 cannot be combined with a target");
+        if (hb) return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, true, false, true>, 4);
+        return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, false, false, true>, 5);
+    }
+    if (hb && ht) return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, true, true, false>, 0);
+    if (hb) return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, true, false, false>, 1);
+    if (ht) return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, false, true, false>, 2);
+    return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, false, false, false>, 3);
 }
 
 int launch_layer_fwd(const LayerFwdCall& c, int64_t D, cudaStream_t stream)

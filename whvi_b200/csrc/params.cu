@@ -7,6 +7,7 @@
 // All are O(S*D) or O(D): noise next to the activation traffic, so they are written for
 // determinism (fixed reduction order, no atomics), not for speed-of-light.
 #include "common.cuh"
+#include "engine.cuh"
 
 namespace whvi {
 
@@ -131,6 +132,47 @@ int launch_kl(const float* mu, const float* rho, float lambda_, int64_t D, int m
     while (threads < D && threads < 1024) threads <<= 1;
     kl_kernel<<<1, threads, 0, stream>>>(mu, rho, lambda_, D, mode, out, dmu, drho, grad_scale, accumulate);
     return check_launch("kl_kernel");
+}
+
+// ---- MC predictive moments: sum over the sample axis of y and y^2 ----------------
+// One float4 column per thread, samples ascending (bit-reproducible), 4 independent loads in
+// flight per thread; HBM-bound: reads 4*S*n bytes, touches 2 (or 4 when accumulating) * 4*n more.
+__global__ void __launch_bounds__(256) mc_moments_kernel(const float4* __restrict__ y, float4* __restrict__ sum_y,
+                                                         float4* __restrict__ sum_y2, int64_t S, int64_t n4, int accumulate)
+{
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (accumulate) {
+        a = sum_y[i];
+        if (sum_y2) b = sum_y2[i];
+    }
+    auto add = [&](const float4 q) {
+        a.x += q.x, a.y += q.y, a.z += q.z, a.w += q.w;
+        b.x = fmaf(q.x, q.x, b.x), b.y = fmaf(q.y, q.y, b.y), b.z = fmaf(q.z, q.z, b.z), b.w = fmaf(q.w, q.w, b.w);
+    };
+    int64_t s = 0;
+    for (; s + 4 <= S; s += 4) {
+        const float4 q0 = ldg_stream(reinterpret_cast<const float*>(y + (s + 0) * n4 + i));
+        const float4 q1 = ldg_stream(reinterpret_cast<const float*>(y + (s + 1) * n4 + i));
+        const float4 q2 = ldg_stream(reinterpret_cast<const float*>(y + (s + 2) * n4 + i));
+        const float4 q3 = ldg_stream(reinterpret_cast<const float*>(y + (s + 3) * n4 + i));
+        add(q0), add(q1), add(q2), add(q3);
+    }
+    for (; s < S; ++s) add(ldg_stream(reinterpret_cast<const float*>(y + s * n4 + i)));
+    sum_y[i] = a;
+    if (sum_y2) sum_y2[i] = b;
+}
+
+int launch_mc_moments(const float* y, float* sum_y, float* sum_y2, int64_t S, int64_t n, int accumulate, cudaStream_t stream)
+{
+    const int64_t n4 = n / 4;
+    const int64_t blocks = (n4 + 255) / 256;
+    if (blocks > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "mc_moments: n too large");
+    mc_moments_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<const float4*>(y),
+                                                                        reinterpret_cast<float4*>(sum_y),
+                                                                        reinterpret_cast<float4*>(sum_y2), S, n4, accumulate);
+    return check_launch("mc_moments_kernel");
 }
 
 }  // namespace whvi

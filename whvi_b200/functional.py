@@ -22,7 +22,7 @@ LAUNCH_COUNTS: dict[str, int] = {}
 _LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_layer_fwd_f32": 1, "whvi_layer_bwd_f32": 2,
                       "whvi_layer_fwd_fused_f32": 1, "whvi_layer_bwd_fused_f32": 2,
                       "whvi_layer_bwd_scaled_f32": 2, "whvi_layer_loss_f32": 2, "whvi_reparam_f32": 1,
-                      "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1}
+                      "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1, "whvi_mc_moments_f32": 1}
 # When set to a dict {"name": [(start_event, stop_event), ...]}, the named calls are bracketed
 # by CUDA events on the launching stream (bench.py's per-kernel roofline timing).
 EVENT_SINK: dict[str, list] | None = None
@@ -93,9 +93,10 @@ def _layer_dims(x, g, s1, s2):
     return S, B, D, xs
 
 
-def layer_forward_raw(x, g, s1, s2, bias=None, out=None, relu_out=False, target=None):
+def layer_forward_raw(x, g, s1, s2, bias=None, out=None, relu_out=False, target=None, from_t2=False):
     """y = s1 * H(g[s] * H(s2 * x)) (+bias) [-> max(y, 0)], no autograd.
-    With ``target`` (B, D): returns ``(y, sum (y - target)^2)``, the sum as a 0-d tensor."""
+    With ``target`` (B, D): returns ``(y, sum (y - target)^2)``, the sum as a 0-d tensor.
+    ``from_t2``: ``x`` already holds ``H(s2 * x)`` (sample-independent), only the second half runs."""
     x, g, s1, s2 = _f32c(x, "x"), _f32c(g, "g"), _f32c(s1, "s1"), _f32c(s2, "s2")
     S, B, D, xs = _layer_dims(x, g, s1, s2)
     if bias is not None:
@@ -115,12 +116,64 @@ def layer_forward_raw(x, g, s1, s2, bias=None, out=None, relu_out=False, target=
         partials = torch.empty(max(n.value, 1), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device), _Timed("whvi_layer_fwd_fused_f32"):
         rc = L.whvi_layer_fwd_fused_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
-                                        out.data_ptr(), S, B, D, 1 if relu_out else 0, _ptr(target), _ptr(partials),
+                                        out.data_ptr(), S, B, D, (1 if relu_out else 0) | (2 if from_t2 else 0),
+                                        _ptr(target), _ptr(partials),
                                         _stream(x.device))
     _lib.check(rc, "whvi_layer_fwd_fused_f32")
     if target is not None:
         return out, partials.sum() if S * B > 0 else partials.sum() * 0
     return out
+
+
+def mc_moments_(y, sum_y, sum_y2=None, accumulate=True):
+    """sum_y (+)= y.sum(0), sum_y2 (+)= (y*y).sum(0) over the leading MC-sample axis, in one pass
+    over ``y`` (S, ...); samples ascending, bit-reproducible."""
+    y = _f32c(y, "y")
+    S = y.size(0)
+    n = y[0].numel() if S > 0 else sum_y.numel()
+    for t, name in ((sum_y, "sum_y"), (sum_y2, "sum_y2")):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n or t.device != y.device):
+            raise RuntimeError(f"{name} must be a contiguous float32 tensor with {n} elements on {y.device}")
+    with torch.cuda.device(y.device), _Timed("whvi_mc_moments_f32"):
+        rc = _lib.lib().whvi_mc_moments_f32(y.data_ptr(), sum_y.data_ptr(), _ptr(sum_y2), S, n, 1 if accumulate else 0,
+                                            _stream(y.device))
+    _lib.check(rc, "whvi_mc_moments_f32")
+    return sum_y, sum_y2
+
+
+@torch.no_grad()
+def predictive_moments(x, mu, rho, s1, s2, bias=None, n_samples=64, chunk_samples=16, eps=None, generator=None,
+                       sample_range=None):
+    """MC predictive mean and variance of one square WHVI layer (PAPER semantics) for inputs
+    ``x`` (B, D) -- BASELINE config 5, what ``WHVIRegression.eval_model`` reduces
+    ``WHVINetwork.forward``'s (B, out, S) output to (src/networks.py:36-54, :131-132) --
+    without ever holding more than ``chunk_samples`` outputs:
+
+    * t2 = H(s2 * x) once per input row (the first transform does not depend on the sample);
+    * per sample chunk: g = mu + softplus(rho) * eps, y = s1 * H(g * t2) + bias (one transform
+      per (sample, row)), then one pass that accumulates sum y and sum y^2.
+
+    Returns ``(sum_y, sum_y2, S_done)`` as raw sums so that ranks holding different sample
+    shards can all-reduce them (``distributed.reduce_predictive_moments``); ``sample_range``
+    = (lo, hi) restricts this call to samples lo..hi-1 of ``eps`` / of the n_samples draws.
+    """
+    from .fwht import fwht_
+    x = _f32c(x, "x")
+    if x.dim() != 2:
+        raise RuntimeError("x must be (B, D)")
+    B, D = x.shape
+    lo, hi = sample_range if sample_range is not None else (0, n_samples if eps is None else eps.size(0))
+    t2 = fwht_(x * s2.reshape(1, D))
+    sum_y = torch.zeros((B, D), dtype=torch.float32, device=x.device)
+    sum_y2 = torch.zeros((B, D), dtype=torch.float32, device=x.device)
+    ybuf = torch.empty((min(chunk_samples, max(hi - lo, 1)), B, D), dtype=torch.float32, device=x.device)
+    for s0 in range(lo, hi, chunk_samples):
+        s1_ = min(s0 + chunk_samples, hi)
+        e = eps[s0:s1_] if eps is not None else torch.randn((s1_ - s0, D), device=x.device, generator=generator)
+        g = ReparamFunction.apply(mu, rho, e.contiguous())
+        y = layer_forward_raw(t2, g, s1, s2, bias, out=ybuf[: s1_ - s0], from_t2=True)
+        mc_moments_(y, sum_y, sum_y2, accumulate=True)
+    return sum_y, sum_y2, hi - lo
 
 
 def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False, relu_in=False, target=None, coef=None,
