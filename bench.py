@@ -331,7 +331,7 @@ def run_ours(args):
             traffic = json.loads(tp.read_text())["dram_bytes_per_row"] * rows_per_launch
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "layer_bwd_tma_kernel (+ layer_bwd_reduce_kernel)", "achieved": bwd_gbs, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "layer_bwd_tma_kernel (+ layer_bwd_reduce_{slabs,fold}_kernel)", "achieved": bwd_gbs, "peak": peak,
                 "unit": "GB/s", "frac": bwd_gbs / peak, "frac_of_8TBs_nominal": bwd_gbs / 8000.0, "traffic": traffic,
                 "traffic_source": "profiles/r01_bwd_traffic.json (ncu dram__bytes_read+write per row x rows per launch)",
                 "algorithmic_bytes_per_launch": 12.0 * D * rows_per_launch,
@@ -343,7 +343,7 @@ def run_ours(args):
     if loss_ms:  # fused last layer (forward + MNLL residual + backward in one pass: x in, dx out)
         loss_avg = sum(loss_ms) / len(loss_ms)
         loss_gbs = 8.0 * D * rows_per_launch / (loss_avg * 1e-3) / 1e9
-        roofline["loss_kernel"] = {"kernel": "layer_loss_kernel (+ layer_bwd_reduce_kernel)", "achieved": loss_gbs,
+        roofline["loss_kernel"] = {"kernel": "layer_loss_kernel (+ layer_bwd_reduce_{slabs,fold}_kernel)", "achieved": loss_gbs,
                                    "frac": loss_gbs / peak, "avg_launch_ms": loss_avg, "algorithmic_bytes_per_row": 8 * D,
                                    "share_of_step": sum(loss_ms) / ms_total,
                                    "note": "replaces a forward (8 B/elt) + backward (12 B/elt) pair of the last layer"}

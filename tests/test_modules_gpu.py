@@ -250,3 +250,73 @@ def test_fused_relu_and_mnll_match_unfused(D, bias):
         pf, pp = fused(x), plain(x)
     assert pf.shape == (B, D, S)
     assert rel_err(pf.cpu().numpy(), pp.cpu().numpy()) < TOL
+
+
+def _toy_model(seed, sigma_noise_off=True):
+    import whvi_b200 as W
+    torch.manual_seed(seed)
+    model = W.WHVIRegression([W.WHVILinear(3, 16, lambda_=2.0), torch.nn.ReLU(), W.WHVILinear(16, 16, lambda_=2.0),
+                              torch.nn.ReLU(), W.WHVILinear(16, 1)], train_samples=4).cuda()
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith(("s1", "s2")):
+                p.normal_()          # O(1) scales so that every layer actually learns
+            if name.endswith("g_mu"):
+                p.normal_()
+            if sigma_noise_off and name.endswith("g_rho"):
+                p.fill_(-30.0)       # softplus(-30) ~ 1e-13: the MC noise vanishes, runs are comparable
+    return model
+
+
+def test_cuda_graph_step_matches_eager():
+    """a captured step (forward + ELBO + backward + Adam) replays to the same
+    parameters as the eager loop; the capture's warm-up steps leave no trace."""
+    import copy
+    from whvi_b200.graphs import GraphedTrainStep
+    g = torch.Generator(device="cuda").manual_seed(5)
+    xs = [torch.randn(32, 3, device="cuda", generator=g) for _ in range(6)]
+    ys = [x[:, :1] ** 2 - x[:, 1:2] for x in xs]
+    eager = _toy_model(3)
+    graphed = copy.deepcopy(eager)
+    opt_e = torch.optim.Adam(eager.parameters(), lr=torch.tensor(1e-2, device="cuda"), capturable=True)
+    opt_g = torch.optim.Adam(graphed.parameters(), lr=torch.tensor(1e-2, device="cuda"), capturable=True)
+    eager.train(), graphed.train()
+    for m, o in ((eager, opt_e), (graphed, opt_g)):   # an eager step on the default stream first: the
+        m.loss(xs[5], ys[5], n=150).backward()        # capture must cope with its leftover autograd state
+        o.step()
+        o.zero_grad(set_to_none=True)
+    step = GraphedTrainStep(graphed, opt_g, xs[0], ys[0], n=150)
+    for p, q in zip(eager.parameters(), graphed.parameters()):
+        assert torch.equal(p, q), "warm-up steps of the capture must not train the model"
+    losses_e, losses_g = [], []
+    for x, y in zip(xs, ys):
+        loss = eager.loss(x, y, n=150)
+        loss.backward()
+        opt_e.step()
+        opt_e.zero_grad(set_to_none=True)
+        losses_e.append(float(loss))
+        losses_g.append(float(step(x, y)))
+    assert np.allclose(losses_e, losses_g, rtol=1e-4), (losses_e, losses_g)
+    for (name, p), q in zip(eager.named_parameters(), graphed.parameters()):
+        assert rel_err(q.detach().cpu().numpy(), p.detach().cpu().numpy()) < 1e-4, name
+    with pytest.raises(RuntimeError, match="capturable"):
+        GraphedTrainStep(graphed, torch.optim.Adam(graphed.parameters(), lr=1e-3), xs[0], ys[0], n=150)
+
+
+def test_train_model_cuda_graph():
+    """train_model(cuda_graph=True) keeps the reference's loop semantics (two phases, scheduler
+    stepping a tensor lr, ragged last batch) and actually trains."""
+    model = _toy_model(11, sigma_noise_off=False)
+    torch.manual_seed(0)
+    x = torch.randn(150, 3, device="cuda")
+    y = x[:, :1] + x[:, 1:2] ** 2
+    ds = torch.utils.data.TensorDataset(x, y)
+    loader = torch.utils.data.DataLoader(ds, batch_size=64)   # 64, 64, 22
+    opt = torch.optim.Adam(model.parameters(), lr=torch.tensor(2e-2, device="cuda"), capturable=True)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda t: 1.0 / (1.0 + 1e-3 * t))
+    model.eval()
+    before = model.eval_model(x, y)[1]
+    model.train_model(loader, opt, sched, epochs1=20, epochs2=20, cuda_graph=True)
+    after = model.eval_model(x, y)[1]
+    assert np.isfinite(after) and after < before
+    assert float(opt.param_groups[0]["lr"]) < 2e-2   # the scheduler reached the captured step

@@ -54,7 +54,13 @@ def c1():
         opt.zero_grad(set_to_none=True)
 
     ms = timed(step, 5, 50)
-    return {"config": "C1 README toy, batch 64, S=1", "ms_per_step": ms, "steps_per_s": 1e3 / ms}
+    # the same step captured as one CUDA graph (this model is launch-bound)
+    from whvi_b200.graphs import GraphedTrainStep
+    opt_g = torch.optim.Adam(model.parameters(), lr=torch.tensor(1e-3, device=dev), capturable=True)
+    gstep = GraphedTrainStep(model, opt_g, x[:64], y[:64], n=150)
+    ms_g = timed(lambda: gstep(x[:64], y[:64]), 5, 200)
+    return {"config": "C1 README toy, batch 64, S=1", "ms_per_step": ms, "steps_per_s": 1e3 / ms,
+            "cuda_graph_ms_per_step": ms_g, "cuda_graph_steps_per_s": 1e3 / ms_g}
 
 
 def c2():
@@ -91,8 +97,13 @@ def c3():
         opt.zero_grad(set_to_none=True)
 
     ms = timed(step, 5, 20)
+    from whvi_b200.graphs import GraphedTrainStep
+    opt_g = torch.optim.Adam(model.parameters(), lr=torch.tensor(1e-3, device=dev), capturable=True)
+    gstep = GraphedTrainStep(model, opt_g, x, y, n=B)
+    ms_g = timed(lambda: gstep(x, y), 5, 50)
     return {"config": "C3 UCI-shaped MLP 13-128-128-1, B=4096, S=64, full Adam step", "ms_per_step": ms,
-            "mc_rows_per_s": S * B / (ms * 1e-3)}
+            "mc_rows_per_s": S * B / (ms * 1e-3), "cuda_graph_ms_per_step": ms_g,
+            "cuda_graph_mc_rows_per_s": S * B / (ms_g * 1e-3)}
 
 
 def c5(n_inputs: int):

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--dims", default="16,128,1024,2048,4096,8192")
     ap.add_argument("--samples", type=int, default=16)
     ap.add_argument("--out", default="")
-    ap.add_argument("--mode", default="plain", choices=["plain", "shared", "target", "loss"],
+    ap.add_argument("--mode", default="plain", choices=["plain", "shared", "target", "loss", "fromt2"],
                     help="plain: per-sample x; shared: one (B,D) x block for all samples (first layer); "
                          "target: fused MNLL residual (last layer)")
     args = ap.parse_args()
@@ -43,6 +43,11 @@ def main():
             xs = x[0].contiguous()
             f_med, _ = time_op(lambda: F.layer_forward_raw(xs, g, s1, s2, out=y, relu_out=True))
             b_med, _ = time_op(lambda: F.layer_backward_raw(xs, dy, g, s1, s2, want_dx=False), warmup=3, iters=10)
+        elif args.mode == "fromt2":  # shared input with the first transform hoisted; "bwd" column = moments pass
+            xs = x[0].contiguous()
+            f_med, _ = time_op(lambda: F.layer_forward_raw(xs, g, s1, s2, out=y, from_t2=True))
+            sy, sy2 = torch.zeros(B, D, device=dev), torch.zeros(B, D, device=dev)
+            b_med, _ = time_op(lambda: F.mc_moments_(y, sy, sy2), warmup=3, iters=10)
         elif args.mode == "target":
             tgt = torch.randn(B, D, device=dev)
             coef = torch.tensor(0.5, device=dev)

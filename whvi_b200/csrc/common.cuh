@@ -80,7 +80,7 @@ struct LayerLossCall {  // fused last layer: forward + Gaussian-MNLL residual + 
     int64_t* need_sq;     // query mode
 };
 int launch_layer_loss(const LayerLossCall& c, int64_t D, cudaStream_t stream);
-int launch_bwd_reduce(const float* ws, float* dg, float* ds1, float* ds2, float* dbias, int64_t S, int slabs_per_sample,
+int launch_bwd_reduce(float* ws, float* dg, float* ds1, float* ds2, float* dbias, int64_t S, int slabs_per_sample,
                       int64_t tile, int64_t D, cudaStream_t stream);
 int launch_layer_fwd(const LayerFwdCall& c, int64_t D, cudaStream_t stream);
 int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream);

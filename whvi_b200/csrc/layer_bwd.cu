@@ -446,62 +446,95 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     }
 }
 
-// Second stage: fixed-order sums of the per-group slabs.
-//   dg[s, i]  = sum over slabs of sample s, over the N/D row replicas inside a slab
+// Second stage: fixed-order (bit-reproducible, no atomics) sums of the per-group slabs.
+//   dg[s, i]         = sum over the slabs of sample s and over the N/D row replicas inside a slab
 //   ds1/ds2/dbias[i] = the same over ALL slabs
-// One warp per output coordinate: lanes stride over (slab, replica) pairs, then a fixed
-// shuffle tree.  blockIdx.y < S: dg of that sample; blockIdx.y == S: ds1, ds2, dbias.
+// Workspace layout: [slab][quantity 0..3 = dg, ds1, ds2, dbias][tile element], slabs sample-major.
+//
+// Pass A (layer_bwd_reduce_slabs_kernel): one thread per (sample, quantity, float4 of the tile)
+// adds up that sample's slabs -- consecutive threads read consecutive addresses, so the whole
+// workspace streams through once at L2/HBM speed -- and leaves the sum in the sample's first slab
+// (in place: a thread only ever touches its own column).  With one row per tile (D == tile) the
+// dg sums go straight to their destination.
+// Pass B (layer_bwd_reduce_fold_kernel): one warp per output coordinate folds the row replicas
+// (dg) or the replicas and samples (ds1, ds2, dbias) of the S per-sample sums: a few MB, L2-resident.
 __global__ void __launch_bounds__(256)
-layer_bwd_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dg, float* __restrict__ ds1,
-                        float* __restrict__ ds2, float* __restrict__ dbias, int S, int slabs_per_sample, int64_t tile, int D)
+layer_bwd_reduce_slabs_kernel(float* __restrict__ ws, float* __restrict__ dg_direct, int S, int slabs_per_sample, int64_t tile4)
 {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= D) return;
-    const int reps = static_cast<int>(tile / D);
-    const unsigned full = 0xffffffffu;
-    if (static_cast<int>(blockIdx.y) < S) {
-        const int s = blockIdx.y;
-        const int64_t terms = int64_t(slabs_per_sample) * reps;
-        float acc = 0.f;
-        for (int64_t t = lane; t < terms; t += 32) {
-            const int64_t slab = int64_t(s) * slabs_per_sample + t / reps;
-            acc += ws[(slab * 4) * tile + (t % reps) * D + i];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
-        if (lane == 0) dg[int64_t(s) * D + i] = acc;
-    } else {
-        const int64_t terms = int64_t(S) * slabs_per_sample * reps;
-        float a1 = 0.f, a2 = 0.f, ab = 0.f;
-        for (int64_t t = lane; t < terms; t += 32) {
-            const float* base = ws + ((t / reps) * 4) * tile + (t % reps) * D + i;
-            a1 += base[tile];
-            a2 += base[2 * tile];
-            if (dbias) ab += base[3 * tile];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a1 += __shfl_xor_sync(full, a1, o);
-            a2 += __shfl_xor_sync(full, a2, o);
-            ab += __shfl_xor_sync(full, ab, o);
-        }
-        if (lane == 0) {
-            ds1[i] = a1;
-            ds2[i] = a2;
-            if (dbias) dbias[i] = ab;
-        }
+    const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;  // float4 index inside the tile
+    if (e >= tile4) return;
+    const int q = blockIdx.y;
+    const int64_t stride = 4 * tile4;
+    for (int s = blockIdx.z; s < S; s += gridDim.z) {
+    float4* base = reinterpret_cast<float4*>(ws) + (int64_t(s) * slabs_per_sample * 4 + q) * tile4 + e;
+    float4 acc = base[0];
+    int j = 1;
+    for (; j + 4 <= slabs_per_sample; j += 4) {  // four independent loads in flight, added in slab order
+        const float4 a0 = base[(j + 0) * stride], a1 = base[(j + 1) * stride], a2 = base[(j + 2) * stride],
+                     a3 = base[(j + 3) * stride];
+        acc.x = (((acc.x + a0.x) + a1.x) + a2.x) + a3.x;
+        acc.y = (((acc.y + a0.y) + a1.y) + a2.y) + a3.y;
+        acc.z = (((acc.z + a0.z) + a1.z) + a2.z) + a3.z;
+        acc.w = (((acc.w + a0.w) + a1.w) + a2.w) + a3.w;
+    }
+    for (; j < slabs_per_sample; ++j) {
+        const float4 a0 = base[j * stride];
+        acc.x += a0.x, acc.y += a0.y, acc.z += a0.z, acc.w += a0.w;
+    }
+    if (q == 0 && dg_direct)
+        reinterpret_cast<float4*>(dg_direct)[int64_t(s) * tile4 + e] = acc;
+    else
+        base[0] = acc;
     }
 }
 
-int launch_bwd_reduce(const float* ws, float* dg, float* ds1, float* ds2, float* dbias, int64_t S, int slabs_per_sample,
+__global__ void __launch_bounds__(256)
+layer_bwd_reduce_fold_kernel(const float* __restrict__ ws, float* __restrict__ dg, float* __restrict__ ds1,
+                             float* __restrict__ ds2, float* __restrict__ dbias, int S, int slabs_per_sample, int64_t tile, int D,
+                             int fold_dg)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int reps = static_cast<int>(tile / D);
+    const int64_t sample_stride = int64_t(slabs_per_sample) * 4 * tile;  // first slab of sample s
+    const unsigned full = 0xffffffffu;
+    const int64_t n_dg = fold_dg ? int64_t(S) * D : 0;
+    const int nq = dbias ? 3 : 2;
+    if (w < n_dg) {
+        const int s = static_cast<int>(w / D), i = static_cast<int>(w % D);
+        const float* base = ws + s * sample_stride + i;
+        float acc = 0.f;
+        for (int r = lane; r < reps; r += 32) acc += base[int64_t(r) * D];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
+        if (lane == 0) dg[w] = acc;
+    } else if (w < n_dg + int64_t(nq) * D) {
+        const int q = 1 + static_cast<int>((w - n_dg) / D), i = static_cast<int>((w - n_dg) % D);
+        const float* base = ws + int64_t(q) * tile + i;
+        const int terms = S * reps;
+        float acc = 0.f;
+        for (int t = lane; t < terms; t += 32) acc += base[(t / reps) * sample_stride + int64_t(t % reps) * D];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
+        if (lane == 0) (q == 1 ? ds1 : q == 2 ? ds2 : dbias)[i] = acc;
+    }
+}
+
+int launch_bwd_reduce(float* ws, float* dg, float* ds1, float* ds2, float* dbias, int64_t S, int slabs_per_sample,
                       int64_t tile, int64_t D, cudaStream_t stream)
 {
+    const int64_t tile4 = tile / 4;
+    const bool direct = D == tile;  // one row per tile: pass A's dg sums are final
+    if (slabs_per_sample > 1 || direct) {
+        dim3 agrid(static_cast<unsigned>((tile4 + 255) / 256), dbias ? 4u : 3u, static_cast<unsigned>(S > 65535 ? 65535 : S));
+        layer_bwd_reduce_slabs_kernel<<<agrid, 256, 0, stream>>>(ws, direct ? dg : nullptr, static_cast<int>(S), slabs_per_sample, tile4);
+        if (int rc = check_launch("layer_bwd_reduce_slabs_kernel")) return rc;
+    }
     const int warps = 8;
-    dim3 rgrid(static_cast<unsigned>((D + warps - 1) / warps), static_cast<unsigned>(S + 1));
-    layer_bwd_reduce_kernel<<<rgrid, warps * 32, 0, stream>>>(ws, dg, ds1, ds2, dbias, static_cast<int>(S), slabs_per_sample,
-                                                              tile, static_cast<int>(D));
-    return check_launch("layer_bwd_reduce_kernel");
+    const int64_t outputs = (direct ? 0 : S * D) + (dbias ? 3 : 2) * D;
+    layer_bwd_reduce_fold_kernel<<<static_cast<unsigned>((outputs + warps - 1) / warps), warps * 32, 0, stream>>>(
+        ws, dg, ds1, ds2, dbias, static_cast<int>(S), slabs_per_sample, tile, static_cast<int>(D), direct ? 0 : 1);
+    return check_launch("layer_bwd_reduce_fold_kernel");
 }
 
 template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS = false, int PREG = 0, int ROUNDS = 3>

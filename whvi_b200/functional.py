@@ -19,9 +19,9 @@ _WORKSPACES: dict[tuple[int, int], torch.Tensor] = {}
 
 # Kernel-launch accounting (bench.py reads it): launches issued by each C-ABI call.
 LAUNCH_COUNTS: dict[str, int] = {}
-_LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_layer_fwd_f32": 1, "whvi_layer_bwd_f32": 2,
-                      "whvi_layer_fwd_fused_f32": 1, "whvi_layer_bwd_fused_f32": 2,
-                      "whvi_layer_bwd_scaled_f32": 2, "whvi_layer_loss_f32": 2, "whvi_reparam_f32": 1,
+_LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_layer_fwd_f32": 1, "whvi_layer_bwd_f32": 3,
+                      "whvi_layer_fwd_fused_f32": 1, "whvi_layer_bwd_fused_f32": 3,
+                      "whvi_layer_bwd_scaled_f32": 3, "whvi_layer_loss_f32": 3, "whvi_reparam_f32": 1,
                       "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1, "whvi_mc_moments_f32": 1}
 # When set to a dict {"name": [(start_event, stop_event), ...]}, the named calls are bracketed
 # by CUDA events on the launching stream (bench.py's per-kernel roofline timing).

@@ -151,9 +151,18 @@ class WHVINetwork(nn.Module, WHVI):
         return self.current_mnll + self.current_kl if not ignore_kl else self.current_mnll
 
     def train_model(self, data_loader, optimizer, scheduler, epochs1: int = 500, epochs2: int = 5000,
-                    pbar_update_period=20, ignore_kl=False, checkpoint_dir=None):
-        """Two-phase training loop of the reference (``src/networks.py:71-99``)."""
+                    pbar_update_period=20, ignore_kl=False, checkpoint_dir=None, *, cuda_graph=False):
+        """Two-phase training loop of the reference (``src/networks.py:71-99``).
+
+        ``cuda_graph=True`` replays each step -- forward, ELBO, backward, optimizer
+        -- as one captured CUDA graph per minibatch shape (``whvi_b200.graphs``); the optimizer
+        must be capturable and the minibatches on the GPU.  The small models the reference trains
+        are launch-bound, so this is where their time goes."""
         self.train()
+        graphed = None
+        if cuda_graph:
+            from .graphs import GraphedStepCache
+            graphed = GraphedStepCache(self, optimizer, n=len(data_loader.dataset), ignore_kl=ignore_kl)
         self.likelihood.requires_grad = False
         for phase, epochs, label in ((1, epochs1, 'Fixed LH'), (2, epochs2, 'Optimized LH')):
             if phase == 2:
@@ -162,6 +171,10 @@ class WHVINetwork(nn.Module, WHVI):
                                             f'MNLL = {float(self.current_mnll):.2f}')
             for epoch in pbar:
                 for data_x, data_y in data_loader:
+                    if graphed is not None:
+                        graphed(data_x, data_y)
+                        scheduler.step()
+                        continue
                     loss = self.loss(data_x, data_y, n=len(data_loader.dataset), ignore_kl=ignore_kl)
                     loss.backward()
                     optimizer.step()
