@@ -491,16 +491,17 @@ layer_bwd_reduce_slabs_kernel(float* __restrict__ ws, float* __restrict__ dg_dir
 __global__ void __launch_bounds__(256)
 layer_bwd_reduce_fold_kernel(const float* __restrict__ ws, float* __restrict__ dg, float* __restrict__ ds1,
                              float* __restrict__ ds2, float* __restrict__ dbias, int S, int slabs_per_sample, int64_t tile, int D,
-                             int fold_dg)
+                             int dg_blocks, int cta_per_output)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ float red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int reps = static_cast<int>(tile / D);
     const int64_t sample_stride = int64_t(slabs_per_sample) * 4 * tile;  // first slab of sample s
     const unsigned full = 0xffffffffu;
-    const int64_t n_dg = fold_dg ? int64_t(S) * D : 0;
     const int nq = dbias ? 3 : 2;
-    if (w < n_dg) {
+    if (static_cast<int>(blockIdx.x) < dg_blocks) {  // dg: one warp per (sample, coordinate), `reps` terms
+        const int64_t w = int64_t(blockIdx.x) * 8 + warp;
+        if (w >= int64_t(S) * D) return;
         const int s = static_cast<int>(w / D), i = static_cast<int>(w % D);
         const float* base = ws + s * sample_stride + i;
         float acc = 0.f;
@@ -508,16 +509,31 @@ layer_bwd_reduce_fold_kernel(const float* __restrict__ ws, float* __restrict__ d
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
         if (lane == 0) dg[w] = acc;
-    } else if (w < n_dg + int64_t(nq) * D) {
-        const int q = 1 + static_cast<int>((w - n_dg) / D), i = static_cast<int>((w - n_dg) % D);
-        const float* base = ws + int64_t(q) * tile + i;
-        const int terms = S * reps;
-        float acc = 0.f;
-        for (int t = lane; t < terms; t += 32) acc += base[(t / reps) * sample_stride + int64_t(t % reps) * D];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
-        if (lane == 0) (q == 1 ? ds1 : q == 2 ? ds2 : dbias)[i] = acc;
+        return;
     }
+    // ds1, ds2, dbias: S * reps terms per coordinate; a whole CTA per output when that is many
+    const int64_t o = cta_per_output ? int64_t(blockIdx.x) - dg_blocks : (int64_t(blockIdx.x) - dg_blocks) * 8 + warp;
+    if (o >= int64_t(nq) * D) return;
+    const int q = 1 + static_cast<int>(o / D), i = static_cast<int>(o % D);
+    const float* base = ws + int64_t(q) * tile + i;
+    const int terms = S * reps;
+    const int first = cta_per_output ? threadIdx.x : lane, step = cta_per_output ? 256 : 32;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int t = first; t < terms; t += step) acc += base[(t / reps) * sample_stride + int64_t(t % reps) * D];
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(full, acc, sh);
+    if (cta_per_output) {
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x != 0) return;
+        acc = red[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) acc += red[j];
+    } else if (lane != 0) {
+        return;
+    }
+    (q == 1 ? ds1 : q == 2 ? ds2 : dbias)[i] = acc;
 }
 
 int launch_bwd_reduce(float* ws, float* dg, float* ds1, float* ds2, float* dbias, int64_t S, int slabs_per_sample,
@@ -530,10 +546,13 @@ int launch_bwd_reduce(float* ws, float* dg, float* ds1, float* ds2, float* dbias
         layer_bwd_reduce_slabs_kernel<<<agrid, 256, 0, stream>>>(ws, direct ? dg : nullptr, static_cast<int>(S), slabs_per_sample, tile4);
         if (int rc = check_launch("layer_bwd_reduce_slabs_kernel")) return rc;
     }
-    const int warps = 8;
-    const int64_t outputs = (direct ? 0 : S * D) + (dbias ? 3 : 2) * D;
-    layer_bwd_reduce_fold_kernel<<<static_cast<unsigned>((outputs + warps - 1) / warps), warps * 32, 0, stream>>>(
-        ws, dg, ds1, ds2, dbias, static_cast<int>(S), slabs_per_sample, tile, static_cast<int>(D), direct ? 0 : 1);
+    const int64_t dg_blocks = direct ? 0 : (S * D + 7) / 8;
+    const int64_t ds_outputs = (dbias ? 3 : 2) * D;
+    const int cta_per_output = S * (tile / D) >= 1024;
+    const int64_t ds_blocks = cta_per_output ? ds_outputs : (ds_outputs + 7) / 8;
+    layer_bwd_reduce_fold_kernel<<<static_cast<unsigned>(dg_blocks + ds_blocks), 256, 0, stream>>>(
+        ws, dg, ds1, ds2, dbias, static_cast<int>(S), slabs_per_sample, tile, static_cast<int>(D), static_cast<int>(dg_blocks),
+        cta_per_output);
     return check_launch("layer_bwd_reduce_fold_kernel");
 }
 

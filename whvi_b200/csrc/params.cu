@@ -25,25 +25,40 @@ __global__ void reparam_diag_kernel(const float* __restrict__ mu, const float* _
 }
 
 // dmu[i] (+)= sum_s dg[s,i];  drho[i] (+)= (sum_s dg[s,i] eps[s,i]) * sigmoid(rho[i])
-__global__ void reparam_diag_bwd_kernel(const float* __restrict__ rho, const float* __restrict__ eps,
-                                        const float* __restrict__ dg, float* __restrict__ dmu, float* __restrict__ drho,
-                                        int64_t S, int64_t D, int accumulate)
+// 32 columns x 8 sample slices per CTA; slice sums are combined in a fixed order (bit-reproducible).
+__global__ void __launch_bounds__(256)
+reparam_diag_bwd_kernel(const float* __restrict__ rho, const float* __restrict__ eps, const float* __restrict__ dg,
+                        float* __restrict__ dmu, float* __restrict__ drho, int64_t S, int64_t D, int accumulate)
 {
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= D) return;
+    __shared__ float red[2][8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t i = int64_t(blockIdx.x) * 32 + tx;
     float a = 0.f, b = 0.f;
-    for (int64_t s = 0; s < S; ++s) {
-        const float d = dg[s * D + i];
-        a += d;
-        b = fmaf(d, eps[s * D + i], b);
+    if (i < D) {
+#pragma unroll 4
+        for (int64_t s = ty; s < S; s += 8) {
+            const float d = dg[s * D + i];
+            a += d;
+            b = fmaf(d, eps[s * D + i], b);
+        }
     }
-    b *= sigmoid_f(rho[i]);
-    if (accumulate) {
-        dmu[i] += a;
-        drho[i] += b;
-    } else {
-        dmu[i] = a;
-        drho[i] = b;
+    red[0][ty][tx] = a;
+    red[1][ty][tx] = b;
+    __syncthreads();
+    if (ty == 0 && i < D) {
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+            a += red[0][j][tx];
+            b += red[1][j][tx];
+        }
+        b *= sigmoid_f(rho[i]);
+        if (accumulate) {
+            dmu[i] += a;
+            drho[i] += b;
+        } else {
+            dmu[i] = a;
+            drho[i] = b;
+        }
     }
 }
 
@@ -119,9 +134,7 @@ int launch_reparam_diag(const float* mu, const float* rho, const float* eps, flo
 int launch_reparam_diag_bwd(const float* rho, const float* eps, const float* dg, float* dmu, float* drho, int64_t S,
                             int64_t D, int accumulate, cudaStream_t stream)
 {
-    const int threads = 128;
-    reparam_diag_bwd_kernel<<<static_cast<unsigned>((D + threads - 1) / threads), threads, 0, stream>>>(rho, eps, dg, dmu,
-                                                                                                       drho, S, D, accumulate);
+    reparam_diag_bwd_kernel<<<static_cast<unsigned>((D + 31) / 32), 256, 0, stream>>>(rho, eps, dg, dmu, drho, S, D, accumulate);
     return check_launch("reparam_diag_bwd_kernel");
 }
 
