@@ -290,23 +290,13 @@ def run_ours(args):
     # computes (whvi_b200.utils.DevicePrefetcher), as a data loader would do it.
     from whvi_b200.utils import DevicePrefetcher
 
-    # N > 1: rank 0 alone reads the minibatch from host memory (one PCIe copy per step for the
-    # whole job, overlapped as above) and NCCL broadcasts it over NVLink; every rank needs the
-    # full minibatch because the ranks shard MC samples, not rows.
+    # N > 1: every rank needs the full minibatch (the ranks shard MC samples, not rows).  Each rank
+    # copies 1/N of the rows from pinned host memory over its own PCIe link and the slices are
+    # all-gathered over NVLink, all on the prefetch stream while the previous step computes: the
+    # whole job reads the minibatch from host memory once per step.
     def e2e_run(steps):
         losses = []
-        if world == 1:
-            for x, y in DevicePrefetcher(((x_host, y_host) for _ in range(steps)), dev):
-                losses.append(float(step(x, y).item()))
-            return losses
-        feed = DevicePrefetcher(((x_host, y_host) for _ in range(steps)), dev) if rank == 0 else None
-        for _ in range(steps):
-            if rank == 0:
-                x, y = next(feed)
-            else:
-                x, y = torch.empty_like(x_dev), torch.empty_like(y_dev)
-            dist.broadcast(x, src=0)
-            dist.broadcast(y, src=0)
+        for x, y in DevicePrefetcher(((x_host, y_host) for _ in range(steps)), dev, shard_over_ranks=True):
             losses.append(float(step(x, y).item()))
         return losses
 

@@ -143,7 +143,7 @@ def mc_moments_(y, sum_y, sum_y2=None, accumulate=True):
 
 @torch.no_grad()
 def predictive_moments(x, mu, rho, s1, s2, bias=None, n_samples=64, chunk_samples=16, eps=None, generator=None,
-                       sample_range=None):
+                       sample_range=None, out=None):
     """MC predictive mean and variance of one square WHVI layer (PAPER semantics) for inputs
     ``x`` (B, D) -- BASELINE config 5, what ``WHVIRegression.eval_model`` reduces
     ``WHVINetwork.forward``'s (B, out, S) output to (src/networks.py:36-54, :131-132) --
@@ -156,6 +156,7 @@ def predictive_moments(x, mu, rho, s1, s2, bias=None, n_samples=64, chunk_sample
     Returns ``(sum_y, sum_y2, S_done)`` as raw sums so that ranks holding different sample
     shards can all-reduce them (``distributed.reduce_predictive_moments``); ``sample_range``
     = (lo, hi) restricts this call to samples lo..hi-1 of ``eps`` / of the n_samples draws.
+    ``out`` = (sum_y, sum_y2) buffers to overwrite (e.g. two halves of one all-reduce bucket).
     """
     from .fwht import fwht_
     x = _f32c(x, "x")
@@ -164,8 +165,12 @@ def predictive_moments(x, mu, rho, s1, s2, bias=None, n_samples=64, chunk_sample
     B, D = x.shape
     lo, hi = sample_range if sample_range is not None else (0, n_samples if eps is None else eps.size(0))
     t2 = fwht_(x * s2.reshape(1, D))
-    sum_y = torch.zeros((B, D), dtype=torch.float32, device=x.device)
-    sum_y2 = torch.zeros((B, D), dtype=torch.float32, device=x.device)
+    if out is not None:
+        sum_y, sum_y2 = out
+        sum_y.zero_(), sum_y2.zero_()
+    else:
+        sum_y = torch.zeros((B, D), dtype=torch.float32, device=x.device)
+        sum_y2 = torch.zeros((B, D), dtype=torch.float32, device=x.device)
     ybuf = torch.empty((min(chunk_samples, max(hi - lo, 1)), B, D), dtype=torch.float32, device=x.device)
     for s0 in range(lo, hi, chunk_samples):
         s1_ = min(s0 + chunk_samples, hi)

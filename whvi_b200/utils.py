@@ -44,9 +44,17 @@ class DevicePrefetcher:
     device buffers are reused (no allocator traffic); a batch handed out stays valid until the
     next one is requested."""
 
-    def __init__(self, batches, device):
+    def __init__(self, batches, device, group=None, shard_over_ranks=False):
+        """``shard_over_ranks`` (MC-sample-sharded jobs, where every rank needs the WHOLE minibatch):
+        each rank copies only its 1/world slice of the rows over its own PCIe link and the slices
+        are all-gathered over NVLink on the side stream, so the job reads the minibatch from host
+        memory once per step instead of once per rank."""
+        import torch.distributed as dist
         self.batches = iter(batches)
         self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group) if (shard_over_ranks and dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.stream = torch.cuda.Stream(device=self.device)
         self.bufs = [None, None]
         self.ready = [None, None]   # copy finished (recorded on the side stream)
@@ -67,7 +75,14 @@ class DevicePrefetcher:
             if self.done[k] is not None:
                 self.stream.wait_event(self.done[k])
             for d, h in zip(self.bufs[k], host):
-                d.copy_(h, non_blocking=True)
+                if self.world > 1 and h.size(0) % self.world == 0:
+                    import torch.distributed as dist
+                    n = h.size(0) // self.world
+                    mine = d[self.rank * n:(self.rank + 1) * n]
+                    mine.copy_(h[self.rank * n:(self.rank + 1) * n], non_blocking=True)
+                    dist.all_gather_into_tensor(d, mine, group=self.group)  # in place, on the side stream
+                else:
+                    d.copy_(h, non_blocking=True)
             self.ready[k] = torch.cuda.Event()
             self.ready[k].record(self.stream)
         self.loaded += 1
