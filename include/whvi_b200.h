@@ -191,6 +191,17 @@ WHVI_API int whvi_reparam_bwd_f32(const float* rho, const float* eps, const floa
  */
 WHVI_API int whvi_mc_moments_f32(const float* y, float* sum_y, float* sum_y2, int64_t S, int64_t n, int accumulate,
                                  whvi_stream_t stream);
+/*
+ * The same reduction with separate inputs and outputs and a sample stride (so `y` may be a block of
+ * rows of a larger (S, B, D) tensor):  out_sum_y[i] = in_sum_y[i] + sum_s y[s*y_sample_stride + i]
+ * (likewise y^2); in_* may be NULL (zero), out_sum_y2 may be NULL.  The outputs may point into a PEER
+ * GPU's memory mapped over NVLink (one process per GPU, MC samples sharded over the ranks,
+ * SURVEY 8e): the kernel then reduces this rank's samples and delivers the partial sums to the rank
+ * that owns those rows in one pass -- the evaluation path's reduce-scatter fused into its producer.
+ */
+WHVI_API int whvi_mc_moments_strided_f32(const float* y, int64_t y_sample_stride, const float* in_sum_y,
+                                         const float* in_sum_y2, float* out_sum_y, float* out_sum_y2, int64_t S,
+                                         int64_t n, whvi_stream_t stream);
 
 #define WHVI_KL_REFERENCE 0
 #define WHVI_KL_CONSISTENT 1

@@ -221,7 +221,21 @@ int whvi_mc_moments_f32(const float* y, float* sum_y, float* sum_y2, int64_t S, 
     if (n == 0) return WHVI_OK;
     if (!sum_y || (S > 0 && !y)) return fail(WHVI_E_NULL, "mc_moments: null pointer");
     if (!aligned16(y) || !aligned16(sum_y) || !aligned16(sum_y2)) return fail(WHVI_E_ALIGN, "mc_moments: pointers must be 16-byte aligned");
-    return launch_mc_moments(y, sum_y, sum_y2, S, n, accumulate, static_cast<cudaStream_t>(stream));
+    return launch_mc_moments(y, n, accumulate ? sum_y : nullptr, accumulate ? sum_y2 : nullptr, sum_y, sum_y2, S, n,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int whvi_mc_moments_strided_f32(const float* y, int64_t y_sample_stride, const float* in_sum_y, const float* in_sum_y2,
+                                float* out_sum_y, float* out_sum_y2, int64_t S, int64_t n, whvi_stream_t stream)
+{
+    if (S < 0 || n < 0 || (n & 3) || (y_sample_stride & 3) || y_sample_stride < n)
+        return fail(WHVI_E_SHAPE, "mc_moments_strided: S=%lld n=%lld stride=%lld (n, stride multiples of 4, stride >= n)",
+                    (long long)S, (long long)n, (long long)y_sample_stride);
+    if (n == 0) return WHVI_OK;
+    if (!out_sum_y || (S > 0 && !y)) return fail(WHVI_E_NULL, "mc_moments_strided: null pointer");
+    if (!aligned16(y) || !aligned16(in_sum_y) || !aligned16(in_sum_y2) || !aligned16(out_sum_y) || !aligned16(out_sum_y2))
+        return fail(WHVI_E_ALIGN, "mc_moments_strided: pointers must be 16-byte aligned");
+    return launch_mc_moments(y, y_sample_stride, in_sum_y, in_sum_y2, out_sum_y, out_sum_y2, S, n, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -149,42 +149,44 @@ int launch_kl(const float* mu, const float* rho, float lambda_, int64_t D, int m
 
 // ---- MC predictive moments: sum over the sample axis of y and y^2 ----------------
 // One float4 column per thread, samples ascending (bit-reproducible), 4 independent loads in
-// flight per thread; HBM-bound: reads 4*S*n bytes, touches 2 (or 4 when accumulating) * 4*n more.
-__global__ void __launch_bounds__(256) mc_moments_kernel(const float4* __restrict__ y, float4* __restrict__ sum_y,
-                                                         float4* __restrict__ sum_y2, int64_t S, int64_t n4, int accumulate)
+// flight per thread; HBM-bound: reads 4*S*n bytes.  out = in + sum_s (in == NULL: 0).  `out` may
+// live in a PEER GPU's memory (NVLink-mapped): the reduction and the scatter to the rank that owns
+// these rows are then one kernel -- the stores ride over NVLink while the loads stream from HBM.
+__global__ void __launch_bounds__(256)
+mc_moments_kernel(const float4* __restrict__ y, int64_t stride4, const float4* __restrict__ in_y, const float4* __restrict__ in_y2,
+                  float4* __restrict__ out_y, float4* __restrict__ out_y2, int64_t S, int64_t n4)
 {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (accumulate) {
-        a = sum_y[i];
-        if (sum_y2) b = sum_y2[i];
-    }
+    if (in_y) a = in_y[i];
+    if (in_y2) b = in_y2[i];
     auto add = [&](const float4 q) {
         a.x += q.x, a.y += q.y, a.z += q.z, a.w += q.w;
         b.x = fmaf(q.x, q.x, b.x), b.y = fmaf(q.y, q.y, b.y), b.z = fmaf(q.z, q.z, b.z), b.w = fmaf(q.w, q.w, b.w);
     };
     int64_t s = 0;
     for (; s + 4 <= S; s += 4) {
-        const float4 q0 = ldg_stream(reinterpret_cast<const float*>(y + (s + 0) * n4 + i));
-        const float4 q1 = ldg_stream(reinterpret_cast<const float*>(y + (s + 1) * n4 + i));
-        const float4 q2 = ldg_stream(reinterpret_cast<const float*>(y + (s + 2) * n4 + i));
-        const float4 q3 = ldg_stream(reinterpret_cast<const float*>(y + (s + 3) * n4 + i));
+        const float4 q0 = ldg_stream(reinterpret_cast<const float*>(y + (s + 0) * stride4 + i));
+        const float4 q1 = ldg_stream(reinterpret_cast<const float*>(y + (s + 1) * stride4 + i));
+        const float4 q2 = ldg_stream(reinterpret_cast<const float*>(y + (s + 2) * stride4 + i));
+        const float4 q3 = ldg_stream(reinterpret_cast<const float*>(y + (s + 3) * stride4 + i));
         add(q0), add(q1), add(q2), add(q3);
     }
-    for (; s < S; ++s) add(ldg_stream(reinterpret_cast<const float*>(y + s * n4 + i)));
-    sum_y[i] = a;
-    if (sum_y2) sum_y2[i] = b;
+    for (; s < S; ++s) add(ldg_stream(reinterpret_cast<const float*>(y + s * stride4 + i)));
+    out_y[i] = a;
+    if (out_y2) out_y2[i] = b;
 }
 
-int launch_mc_moments(const float* y, float* sum_y, float* sum_y2, int64_t S, int64_t n, int accumulate, cudaStream_t stream)
+int launch_mc_moments(const float* y, int64_t y_sample_stride, const float* in_y, const float* in_y2, float* out_y,
+                      float* out_y2, int64_t S, int64_t n, cudaStream_t stream)
 {
     const int64_t n4 = n / 4;
     const int64_t blocks = (n4 + 255) / 256;
     if (blocks > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "mc_moments: n too large");
-    mc_moments_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<const float4*>(y),
-                                                                        reinterpret_cast<float4*>(sum_y),
-                                                                        reinterpret_cast<float4*>(sum_y2), S, n4, accumulate);
+    mc_moments_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(y), y_sample_stride / 4, reinterpret_cast<const float4*>(in_y),
+        reinterpret_cast<const float4*>(in_y2), reinterpret_cast<float4*>(out_y), reinterpret_cast<float4*>(out_y2), S, n4);
     return check_launch("mc_moments_kernel");
 }
 

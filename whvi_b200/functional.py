@@ -22,7 +22,8 @@ LAUNCH_COUNTS: dict[str, int] = {}
 _LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_layer_fwd_f32": 1, "whvi_layer_bwd_f32": 3,
                       "whvi_layer_fwd_fused_f32": 1, "whvi_layer_bwd_fused_f32": 3,
                       "whvi_layer_bwd_scaled_f32": 3, "whvi_layer_loss_f32": 3, "whvi_reparam_f32": 1,
-                      "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1, "whvi_mc_moments_f32": 1}
+                      "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1, "whvi_mc_moments_f32": 1,
+                      "whvi_mc_moments_strided_f32": 1}
 # When set to a dict {"name": [(start_event, stop_event), ...]}, the named calls are bracketed
 # by CUDA events on the launching stream (bench.py's per-kernel roofline timing).
 EVENT_SINK: dict[str, list] | None = None
@@ -141,9 +142,27 @@ def mc_moments_(y, sum_y, sum_y2=None, accumulate=True):
     return sum_y, sum_y2
 
 
+def mc_moments_into(y, in_y, in_y2, out_y, out_y2):
+    """out = in + sum over the leading sample axis of ``y`` (and y^2).  ``y`` is (S, rows, D), possibly a
+    block of rows of a larger contiguous (S, B, D) tensor; ``in_*`` may be None; ``out_*`` may be
+    tensors that live on a peer GPU (symmetric memory): the scatter over NVLink is then part of
+    the reduction kernel."""
+    if y.dtype != torch.float32 or y.dim() != 3 or y.stride(2) != 1 or y.stride(1) != y.size(2):
+        raise RuntimeError("y must be a float32 (S, rows, D) block with contiguous rows")
+    S, n = y.size(0), y.size(1) * y.size(2)
+    stride = y.stride(0) if S > 1 else n
+    for t, name in ((in_y, "in_y"), (in_y2, "in_y2"), (out_y, "out_y"), (out_y2, "out_y2")):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n):
+            raise RuntimeError(f"{name} must be a contiguous float32 tensor with {n} elements")
+    with torch.cuda.device(y.device), _Timed("whvi_mc_moments_strided_f32"):
+        rc = _lib.lib().whvi_mc_moments_strided_f32(y.data_ptr(), stride, _ptr(in_y), _ptr(in_y2), out_y.data_ptr(),
+                                                    _ptr(out_y2), S, n, _stream(y.device))
+    _lib.check(rc, "whvi_mc_moments_strided_f32")
+
+
 @torch.no_grad()
 def predictive_moments(x, mu, rho, s1, s2, bias=None, n_samples=64, chunk_samples=16, eps=None, generator=None,
-                       sample_range=None, out=None):
+                       sample_range=None, out=None, t2=None, scatter_to=None):
     """MC predictive mean and variance of one square WHVI layer (PAPER semantics) for inputs
     ``x`` (B, D) -- BASELINE config 5, what ``WHVIRegression.eval_model`` reduces
     ``WHVINetwork.forward``'s (B, out, S) output to (src/networks.py:36-54, :131-132) --
@@ -157,27 +176,37 @@ def predictive_moments(x, mu, rho, s1, s2, bias=None, n_samples=64, chunk_sample
     shards can all-reduce them (``distributed.reduce_predictive_moments``); ``sample_range``
     = (lo, hi) restricts this call to samples lo..hi-1 of ``eps`` / of the n_samples draws.
     ``out`` = (sum_y, sum_y2) buffers to overwrite (e.g. two halves of one all-reduce bucket).
+    ``t2``: the hoisted transform ``fwht_(x * s2)`` if the caller already has it (``x`` may then be
+    None) -- e.g. computed on row slices by different ranks and all-gathered.
+    ``scatter_to``: [(row_lo, row_hi, out_y, out_y2), ...] covering all rows -- the LAST sample
+    chunk's reduction writes its totals there instead of into the local sums (peer-GPU buffers of
+    the ranks that own those rows: ``distributed.PeerMomentExchange``).
     """
     from .fwht import fwht_
-    x = _f32c(x, "x")
+    x = _f32c(x if t2 is None else t2, "x")
     if x.dim() != 2:
         raise RuntimeError("x must be (B, D)")
     B, D = x.shape
     lo, hi = sample_range if sample_range is not None else (0, n_samples if eps is None else eps.size(0))
-    t2 = fwht_(x * s2.reshape(1, D))
+    t2 = fwht_(x * s2.reshape(1, D)) if t2 is None else x
     if out is not None:
         sum_y, sum_y2 = out
-        sum_y.zero_(), sum_y2.zero_()
     else:
-        sum_y = torch.zeros((B, D), dtype=torch.float32, device=x.device)
-        sum_y2 = torch.zeros((B, D), dtype=torch.float32, device=x.device)
+        sum_y = torch.empty((B, D), dtype=torch.float32, device=x.device)
+        sum_y2 = torch.empty((B, D), dtype=torch.float32, device=x.device)
+    if hi <= lo:
+        sum_y.zero_(), sum_y2.zero_()
     ybuf = torch.empty((min(chunk_samples, max(hi - lo, 1)), B, D), dtype=torch.float32, device=x.device)
     for s0 in range(lo, hi, chunk_samples):
         s1_ = min(s0 + chunk_samples, hi)
         e = eps[s0:s1_] if eps is not None else torch.randn((s1_ - s0, D), device=x.device, generator=generator)
         g = ReparamFunction.apply(mu, rho, e.contiguous())
         y = layer_forward_raw(t2, g, s1, s2, bias, out=ybuf[: s1_ - s0], from_t2=True)
-        mc_moments_(y, sum_y, sum_y2, accumulate=True)
+        if scatter_to is not None and s1_ == hi:
+            for r0, r1, oy, oy2 in scatter_to:
+                mc_moments_into(y[:, r0:r1], sum_y[r0:r1] if s0 > lo else None, sum_y2[r0:r1] if s0 > lo else None, oy, oy2)
+        else:
+            mc_moments_(y, sum_y, sum_y2, accumulate=s0 > lo)   # the first chunk overwrites: no zero-fill pass
     return sum_y, sum_y2, hi - lo
 
 

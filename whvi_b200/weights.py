@@ -161,7 +161,8 @@ class WHVISquarePow2Matrix(nn.Module):
         bias = None if self.bias is None else self.bias.reshape(-1)
         return WF.whvi_layer_loss(h, g, self.s1, self.s2, bias, target, relu_in, defer_dx_scale)
 
-    def predictive_moments(self, x, n_samples=64, *, chunk_samples=16, sample_range=None, out=None, generator=None):
+    def predictive_moments(self, x, n_samples=64, *, chunk_samples=16, sample_range=None, out=None, generator=None, t2=None,
+                           scatter_to=None):
         """MC predictive sums (sum_s y, sum_s y^2, samples done) for inputs x (B, D) without the
         (S, B, D) tensor: see functional.predictive_moments (BASELINE config 5)."""
         if self.semantics != "paper":
@@ -170,7 +171,7 @@ class WHVISquarePow2Matrix(nn.Module):
         bias = None if self.bias is None else self.bias.reshape(-1)
         return WF.predictive_moments(x, self.g_mu, self.g_rho, self.s1, self.s2, bias, n_samples=n_samples,
                                      chunk_samples=chunk_samples, eps=eps, sample_range=sample_range, out=out,
-                                     generator=generator)
+                                     generator=generator, t2=t2, scatter_to=scatter_to)
 
     @property
     def loss_fusable(self):
