@@ -66,6 +66,11 @@ WHVI_API int64_t whvi_max_dim(void);
  * (H is symmetric: src/fwht/cuda/fwht.py:14-16).
  */
 WHVI_API int whvi_fwht_f32(const float* in, float* out, int64_t rows, int64_t D, whvi_stream_t stream);
+/* The same transform in double precision (the reference dispatches double too,
+ * src/fwht/cuda/fwht_cuda_kernel.cu:170, and its gradient check runs in double,
+ * src/fwht/grad_check.py:26).  Parity tooling: correct for every D the fp32 entry accepts, not
+ * tuned for bandwidth.  in == out allowed. */
+WHVI_API int whvi_fwht_f64(const double* in, double* out, int64_t rows, int64_t D, whvi_stream_t stream);
 
 /*
  * Fused WHVILinear forward, PAPER semantics (docstring src/weights.py:77):

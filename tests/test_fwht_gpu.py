@@ -167,3 +167,27 @@ def test_against_reference_cuda_kernel(k, rows):
     torch.cuda.synchronize()
     got = fwht_(x)
     assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("k,rows", [(0, 5), (1, 7), (3, 100), (7, 33), (8, 9), (11, 5), (12, 3), (14, 3), (16, 2)])
+def test_fp64_matches_oracle(k, rows):
+    """whvi_fwht_f64 (the reference dispatches double, fwht_cuda_kernel.cu:170)."""
+    from whvi_b200 import fwht_
+    D = 1 << k
+    rng = np.random.default_rng(k * 31 + rows)
+    a = rng.standard_normal((rows, D))
+    x = torch.from_numpy(a).cuda()
+    y = fwht_(x)
+    assert y.dtype == torch.float64
+    assert rel_err(y.cpu().numpy(), O.fwht(a)) < 1e-13
+    assert torch.equal(fwht_(x, out=x), y)          # in place
+    with pytest.raises(RuntimeError, match="float32 and float64"):
+        fwht_(x.half())
+
+
+def test_fp64_gradcheck():
+    """What src/fwht/grad_check.py:26 intends (it asserts on 1-D input in the reference):
+    torch.autograd.gradcheck of the 2-D double FWHTFunction."""
+    from whvi_b200 import FWHTFunction
+    x = torch.randn(3, 16, dtype=torch.float64, device="cuda", requires_grad=True)
+    assert torch.autograd.gradcheck(FWHTFunction.apply, (x,), eps=1e-6, atol=1e-6)

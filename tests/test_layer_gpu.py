@@ -130,6 +130,27 @@ def test_mc_moments(S, n):
         F.mc_moments_(t(y).reshape(S, n), a[:-1].clone(), None)
 
 
+def test_mc_moments_strided_row_blocks():
+    """whvi_mc_moments_strided_f32: out = in + sum_s y on a block of rows of a larger (S, B, D) tensor
+    (the form the sample-sharded evaluation uses to deliver partial sums to the rows' owner)."""
+    from whvi_b200 import functional as F
+    rng = np.random.default_rng(11)
+    S, B, D = 5, 12, 64
+    y = rng.standard_normal((S, B, D)).astype(np.float32)
+    a0, b0 = rng.standard_normal((B, D)).astype(np.float32), rng.standard_normal((B, D)).astype(np.float32)
+    yt, a, b = t(y), t(a0), t(b0)
+    oa, ob = torch.full((B, D), 7.0, device=dev()), torch.full((B, D), 7.0, device=dev())
+    for r0, r1 in ((0, 4), (4, 8), (8, 12)):
+        F.mc_moments_into(yt[:, r0:r1], a[r0:r1], b[r0:r1], oa[r0:r1], ob[r0:r1])
+    y64 = y.astype(np.float64)
+    assert rel_err(oa.cpu().numpy(), a0 + y64.sum(0)) < 1e-6
+    assert rel_err(ob.cpu().numpy(), b0 + (y64 * y64).sum(0)) < 1e-6
+    F.mc_moments_into(yt[:, 2:5], None, None, oa[2:5], None)
+    assert rel_err(oa[2:5].cpu().numpy(), y64[:, 2:5].sum(0)) < 1e-6
+    with pytest.raises(RuntimeError):
+        F.mc_moments_into(yt[:, :, :32], None, None, oa[:, :32].contiguous(), None)   # rows not contiguous
+
+
 @pytest.mark.parametrize("S,B,D,chunk", [(8, 5, 64, 3), (6, 3, 4096, 4), (5, 2, 32768, 2)])
 def test_predictive_moments_vs_oracle(S, B, D, chunk):
     """BASELINE config 5 path: predictive mean/variance over MC samples without the (S,B,D) tensor."""
@@ -156,6 +177,13 @@ def test_predictive_moments_vs_oracle(S, B, D, chunk):
     a2, b2, n2 = layer.predictive_moments(t(x), chunk_samples=chunk, sample_range=(S // 2, S))
     assert n1 + n2 == S
     assert rel_err((a1 + a2).cpu().numpy(), y.sum(0)) < TOL
+    # scatter_to: the last sample chunk's totals land in caller-provided row blocks
+    layer.inject_eps(t(eps))
+    oy, oy2 = torch.zeros(B, D, device=dev()), torch.zeros(B, D, device=dev())
+    h = max(B // 2, 1)
+    blocks = [(0, h, oy[:h], oy2[:h])] + ([(h, B, oy[h:], oy2[h:])] if B > h else [])
+    layer.predictive_moments(t(x), chunk_samples=chunk, scatter_to=blocks)
+    assert rel_err(oy.cpu().numpy(), y.sum(0)) < TOL and rel_err(oy2.cpu().numpy(), (y * y).sum(0)) < TOL
 
 
 def test_backward_without_dx_and_bias_and_determinism():

@@ -30,6 +30,17 @@ int whvi_fwht_f32(const float* in, float* out, int64_t rows, int64_t D, whvi_str
     return launch_fwht(in, out, rows, D, static_cast<cudaStream_t>(stream));
 }
 
+int whvi_fwht_f64(const double* in, double* out, int64_t rows, int64_t D, whvi_stream_t stream)
+{
+    if (rows < 0 || D < 1) return fail(WHVI_E_SHAPE, "fwht_f64: rows=%lld D=%lld", (long long)rows, (long long)D);
+    if (!is_pow2(D)) return fail(WHVI_E_SHAPE, "fwht_f64: n must be a power of 2 (got %lld)", (long long)D);
+    if (rows == 0) return WHVI_OK;
+    if (!in || !out) return fail(WHVI_E_NULL, "fwht_f64: null pointer");
+    if (!aligned16(in) || !aligned16(out)) return fail(WHVI_E_ALIGN, "fwht_f64: pointers must be 16-byte aligned");
+    if (rows > (int64_t(1) << 40) / D) return fail(WHVI_E_SHAPE, "fwht_f64: too many elements");
+    return launch_fwht_f64(in, out, rows, D, static_cast<cudaStream_t>(stream));
+}
+
 static int check_layer_shape(const char* who, int64_t S, int64_t B, int64_t D, int64_t xs, int64_t max_d = 8192)
 {
     if (S < 0 || B < 0 || D < 1) return fail(WHVI_E_SHAPE, "%s: S=%lld B=%lld D=%lld", who, (long long)S, (long long)B, (long long)D);

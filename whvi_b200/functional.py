@@ -19,7 +19,7 @@ _WORKSPACES: dict[tuple[int, int], torch.Tensor] = {}
 
 # Kernel-launch accounting (bench.py reads it): launches issued by each C-ABI call.
 LAUNCH_COUNTS: dict[str, int] = {}
-_LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_layer_fwd_f32": 1, "whvi_layer_bwd_f32": 3,
+_LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_fwht_f64": 1, "whvi_layer_fwd_f32": 1, "whvi_layer_bwd_f32": 3,
                       "whvi_layer_fwd_fused_f32": 1, "whvi_layer_bwd_fused_f32": 3,
                       "whvi_layer_bwd_scaled_f32": 3, "whvi_layer_loss_f32": 3, "whvi_reparam_f32": 1,
                       "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1, "whvi_mc_moments_f32": 1,

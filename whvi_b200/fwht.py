@@ -30,19 +30,20 @@ def fwht_(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     n = x.size(-1)
     if n < 1 or (n & (n - 1)) != 0:
         raise RuntimeError("n must be a power of 2")
-    if x.dtype != torch.float32:
-        raise RuntimeError(f"whvi_b200 FWHT supports float32 only (got {x.dtype})")
+    if x.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError(f"whvi_b200 FWHT supports float32 and float64 (got {x.dtype})")
     x = x.contiguous()
     if out is None:
         out = torch.empty_like(x)
     elif out.shape != x.shape or out.dtype != x.dtype or not out.is_contiguous() or out.device != x.device:
-        raise RuntimeError("out must be a contiguous float32 tensor shaped like x on the same device")
+        raise RuntimeError("out must be a contiguous tensor of x's dtype and shape on the same device")
     if x.numel() == 0:
         return out
     from . import functional as _F
-    with torch.cuda.device(x.device), _F._Timed("whvi_fwht_f32"):
-        rc = _lib.lib().whvi_fwht_f32(x.data_ptr(), out.data_ptr(), x.size(0), n, _stream_ptr(x.device))
-    _lib.check(rc, "whvi_fwht_f32")
+    name = "whvi_fwht_f32" if x.dtype == torch.float32 else "whvi_fwht_f64"   # same dispatch as fwht_cuda_kernel.cu:170
+    with torch.cuda.device(x.device), _F._Timed(name):
+        rc = getattr(_lib.lib(), name)(x.data_ptr(), out.data_ptr(), x.size(0), n, _stream_ptr(x.device))
+    _lib.check(rc, name)
     return out
 
 
