@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--log2d", type=int, default=15)
     ap.add_argument("--samples", type=int, default=256)
     ap.add_argument("--chunk-inputs", type=int, default=512)
-    ap.add_argument("--chunk-samples", type=int, default=16)
+    ap.add_argument("--chunk-samples", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=2, help="untimed input chunks")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
                     help="nccl: local sums + ncclReduceScatter on a side stream (default: measured faster at 8 GPUs); "
