@@ -109,7 +109,7 @@ def c3():
 def c5(n_inputs: int):
     """MC predictive mean/variance, D = 2^15, S = 256: per input chunk t2 = H(s2 x) once, then per
     sample chunk one FROM_T2 forward (one transform per (s, b) pair) and one moments pass."""
-    D, S, chunk_b, chunk_s = 1 << 15, 256, 256, 16
+    D, S, chunk_b, chunk_s = 1 << 15, 256, 256, 32
     torch.manual_seed(0)
     layer = W.WHVISquarePow2Matrix(D, lambda_=1.0).to(dev)
     mean_abs = torch.zeros((), device=dev)
