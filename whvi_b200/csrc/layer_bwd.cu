@@ -58,7 +58,11 @@ struct BwdArgs {
 //     profiles/r01_bwd_notes.md);
 //   * the dg accumulator is split between the roles (X: float4 slots 0..E/8-1, Y: the rest;
 //     each sends the other the half-stream it needs through a shared half-stash), which
-//     balances the register budgets at <= 112 so two CTAs (2 x 288 threads) fit per SM.
+//     balances the register budgets of the two roles.
+// One CTA per SM (shared memory is the limit), so the spare registers hold this thread's s1/s2/g
+// values across tiles (PREG).  A two-CTA/SM variant with shared-memory accumulators, a two-view
+// 64-float variant and a single-barrier stash exchange were measured and dropped
+// (profiles/r01_bwd_notes.md, items 5, 8, 10).
 // Shared memory per pair: NS x (x tile + dy tile) + X scratch + Y scratch + stash (1 tile).
 template <int N, int C, int KT, int PAIRS, int MINB, int NS, bool SINGLE, bool ALIAS, int PREG, int ROUNDS, bool WANT_DBIAS, bool RESID>
 __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_kernel(const BwdArgs p)
@@ -69,7 +73,6 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     constexpr int64_t TILE = int64_t(1) << N;
     constexpr int SCR = SINGLE ? 1 : 2;      // scratch tiles per role
     // RESID: the target tile rides in the stage too (third tile) when shared memory allows
-    constexpr bool LEAN = false;  // (a 2-CTA/SM variant with smem accumulators measured slower; profiles/r01_bwd_notes.md)
     // ALIAS (needs ping-pong scratch): the half-stashes live in each role's idle first scratch
     // buffer instead of a tile of their own (every read of it precedes the barrier that followed
     // the second buffer's write), which makes room for two CTAs per SM.
@@ -135,9 +138,8 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     float* scratch = pair_smem + (SPT * NS + SCR * role) * TILE;  // this role's transposition buffer(s)
     float* scratch2 = scratch + (SINGLE ? 0 : TILE);
     // half-stashes: X -> Y upper half of t2, Y -> X lower half of dt3
-    float* stash_t2 = (LEAN || ALIAS) ? pair_smem + (SPT * NS) * TILE : pair_smem + (SPT * NS + 2 * SCR) * TILE;
-    float* stash_d3 = (LEAN || ALIAS) ? pair_smem + (SPT * NS + SCR) * TILE : stash_t2 + TILE / 2;
-    float* acc2_smem = pair_smem + (SPT * NS + 2 * SCR) * TILE + (tid << 2);  // LEAN: slot m at + m * 4 * T
+    float* stash_t2 = ALIAS ? pair_smem + (SPT * NS) * TILE : pair_smem + (SPT * NS + 2 * SCR) * TILE;
+    float* stash_d3 = ALIAS ? pair_smem + (SPT * NS + SCR) * TILE : stash_t2 + TILE / 2;
     const int bar_role = 1 + 3 * pair + role;
     const int bar_pair = 3 + 3 * pair;
     const float* __restrict__ gs = p.g + (int64_t(s) << k);
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
                 mul4(a + 4 * m, q, w);
             });
             to_mid(a);  // a = t2 (middle layout)
-            if constexpr (LEAN || (ALIAS && SINGLE)) role_sync<T>(bar_role);  // scratch (now the stash) is no longer being read
+            if constexpr (ALIAS && SINGLE) role_sync<T>(bar_role);  // scratch (now the stash) is no longer being read
 #pragma unroll
             for (int jj = 0; jj < H / 4; ++jj)   // publish the upper half of t2
                 *reinterpret_cast<float4*>(stash_t2 + hs_base + ((jj ^ hs_swz) << 2)) =
@@ -374,14 +376,9 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
             });
             load_g_regs(gr);
         }
-        float acc_2[LEAN ? 1 : E];
-        if constexpr (LEAN) {
+        float acc_2[E];
 #pragma unroll
-            for (int m = 0; m < E / 4; ++m) *reinterpret_cast<float4*>(acc2_smem + m * 4 * T) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-#pragma unroll
-            for (int i = 0; i < E; ++i) acc_2[i] = 0.f;
-        }
+        for (int i = 0; i < E; ++i) acc_2[i] = 0.f;
 #pragma unroll 1
         for (int it = 0; it < p.iters_per_group; ++it) {
             const int64_t e0 = tile_of(it, pair);
@@ -401,7 +398,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
                 mul4(b + 4 * m, q, w);
             });
             to_mid(b);  // b = dt3 (middle layout)
-            if constexpr (LEAN || (ALIAS && SINGLE)) role_sync<T>(bar_role);
+            if constexpr (ALIAS && SINGLE) role_sync<T>(bar_role);
 #pragma unroll
             for (int jj = 0; jj < H / 4; ++jj)   // publish the lower half of dt3
                 *reinterpret_cast<float4*>(stash_d3 + hs_base + ((jj ^ hs_swz) << 2)) =
@@ -421,14 +418,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
                 constexpr int m = decltype(m_)::value;
                 const float4 q = raw4(stage_x, off);
                 const float4 w = PREG == 2 ? make_float4(s2r[4 * m], s2r[4 * m + 1], s2r[4 * m + 2], s2r[4 * m + 3]) : ldg4(p.s2 + coord);
-                if constexpr (LEAN) {
-                    float4 t = *reinterpret_cast<float4*>(acc2_smem + m * 4 * T);
-                    float tv[4] = {t.x, t.y, t.z, t.w};
-                    fma4(tv, q, b + 4 * m);
-                    *reinterpret_cast<float4*>(acc2_smem + m * 4 * T) = make_float4(tv[0], tv[1], tv[2], tv[3]);
-                } else {
-                    fma4(acc_2 + 4 * m, q, b + 4 * m);
-                }
+                fma4(acc_2 + 4 * m, q, b + 4 * m);
                 const float4 o = make_float4(q.x > relu_thr ? b[4 * m] * w.x : 0.f, q.y > relu_thr ? b[4 * m + 1] * w.y : 0.f,
                                              q.z > relu_thr ? b[4 * m + 2] * w.z : 0.f, q.w > relu_thr ? b[4 * m + 3] * w.w : 0.f);
                 if (want_dx && (left >= TILE || off < left)) stg_stream(dxs + off, o);
@@ -437,10 +427,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
         }
         for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t) {
             constexpr int m = decltype(m_)::value;
-            if constexpr (LEAN)
-                *reinterpret_cast<float4*>(slab + 2 * TILE + off) = *reinterpret_cast<float4*>(acc2_smem + m * 4 * T);
-            else
-                *reinterpret_cast<float4*>(slab + 2 * TILE + off) = make_float4(acc_2[4 * m], acc_2[4 * m + 1], acc_2[4 * m + 2], acc_2[4 * m + 3]);
+            *reinterpret_cast<float4*>(slab + 2 * TILE + off) = make_float4(acc_2[4 * m], acc_2[4 * m + 1], acc_2[4 * m + 2], acc_2[4 * m + 3]);
         });
         store_dg_half(acc_g, 1, slab);
     }
