@@ -343,3 +343,17 @@ def test_loss_layer_vs_oracle(S, B, D, bias, shared):
     assert rel_err(ds2.cpu().numpy(), rds2) < TOL
     if bias:
         assert rel_err(db.cpu().numpy(), rdb) < TOL
+
+
+def test_deferred_scale_must_be_consumed():
+    """The fused loss layer may hand out dx for a unit coefficient only to a WHVI layer backward;
+    if nobody takes the pending scale the next network pass raises instead of training on wrong grads."""
+    from whvi_b200 import functional as F
+    S, B, D = 2, 4, 128
+    x, g, s1, s2, _, _ = make_case(S, B, D, 5)
+    xt = t(x).requires_grad_()
+    sq = F.whvi_layer_loss(xt, t(g), t(s1), t(s2), None, t(np.zeros((B, D))), relu_in=False, defer_dx_scale=True)
+    (0.5 * sq).backward()          # xt is a leaf: the unit-coefficient dx lands in .grad, scale still pending
+    with pytest.raises(RuntimeError, match="never consumed"):
+        F.check_no_pending_scale()
+    F.check_no_pending_scale()     # cleared by the failure

@@ -259,6 +259,17 @@ LOSS_LAYER_MIN_D, LOSS_LAYER_MAX_D = 128, 4096
 _PENDING_DY_SCALE: dict[int, torch.Tensor] = {}
 
 
+def check_no_pending_scale() -> None:
+    """A deferred scale that nobody consumed means a backward pass handed an unscaled gradient to
+    something other than WHVILayerFunction.backward (e.g. a hook copied the tensor): fail loudly
+    instead of training on wrong gradients."""
+    if _PENDING_DY_SCALE:
+        _PENDING_DY_SCALE.clear()
+        raise RuntimeError("whvi_b200: a deferred gradient scale of the fused loss layer was never consumed; the "
+                           "previous backward pass produced wrongly scaled gradients (construct the network with "
+                           "fuse=False if the activations between the last two layers are hooked or shared)")
+
+
 def layer_loss_raw(x, g, s1, s2, bias, target, want_dx=True, relu_in=False):
     """Fused last layer (forward + squared-error residual + backward for a unit coefficient).
     Returns (sum r^2 as a 0-d tensor, dx | None, dg, ds1, ds2, dbias | None)."""

@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import functional as WF
 from .layers import WHVI, WHVILinear
 from .likelihoods import GaussianLikelihood, Likelihood
 
@@ -84,6 +85,7 @@ class WHVINetwork(nn.Module, WHVI):
         with the ReLU folded into the two kernels (``self.fuse``)."""
         modules = list(self.sequential.children())
         layers = self._whvi_layers()
+        WF.check_no_pending_scale()
         if self.rng_mode == "reference":
             self._predraw_reference_order(n_samples)
         for layer in layers:
