@@ -338,6 +338,14 @@ def run_ours(args):
                                    "share_of_step": sum(loss_ms) / ms_total,
                                    "note": "replaces a forward (8 B/elt) + backward (12 B/elt) pair of the last layer"}
 
+    # whole step against the same roofline: SURVEY 8d's 20*D bytes per (sample, row, layer) over all ranks
+    step_bytes = 20.0 * D * S_TOTAL * B * N_LAYERS
+    step_gbs = step_bytes / (ms_step * 1e-3) / 1e9
+    roofline["whole_step"] = {"algorithmic_bytes_per_step": step_bytes, "achieved": step_gbs, "unit": "GB/s",
+                              "frac": step_gbs / (peak * world), "n_gpus": world,
+                              "note": "fwd 8*D + bwd 12*D bytes per (sample, row, layer); the fused last layer and the "
+                                      "shared first-layer input move fewer bytes than this yardstick"}
+
     out = None
     if rank == 0:
         # ---- FWHT GB/s sweep (second half of BASELINE.json's metric), 2^28 elements = 1 GiB in + out
