@@ -20,6 +20,7 @@ fwht_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total
     constexpr int E = 1 << C;
     constexpr int64_t TILE = int64_t(1) << N;
     constexpr int SEQ = seq_pack(V_FIRST, V_MID, V_LAST);
+    static_assert(rounds_needed(N, C, K) <= 3, "FIRST+MID+LAST must cover every transform bit");
     // only bits 0,1 to transform: FIRST alone covers them and is already store-friendly
     constexpr bool kOneRound = (K <= 2);
 

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     // LAST view.  ROUNDS == 2 (configurations where FIRST + MID cover every bit): the middle is
     // the MID view -- half the transpositions, hence half of the dominant L1/shared wavefronts.
     static_assert(ROUNDS == 3 || rounds_needed(N, C, N) <= 2, "2-view kernel needs FIRST+MID to cover all bits");
+    static_assert(rounds_needed(N, C, N) <= 3, "FIRST+MID+LAST must cover every tile bit (e.g. 5+5+3 = 13 bits at C = 5)");
     constexpr bool GTAB = ROUNDS == 2 && !PREG;  // g in shared memory in MID order (one table per CTA)
     constexpr int STASH = ALIAS ? 0 : 1;
     constexpr bool STAGE_TGT = RESID && bwd_stage_target(N, PAIRS, NS, SINGLE, ALIAS, ROUNDS == 2 && !PREG, MINB);

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, 1) layer_loss_kernel(c
     constexpr int SCR = SINGLE ? 1 : 2;
     constexpr int PAIR_FLOATS = (2 * NS + 2 * SCR + NS) * int(TILE);  // stages, scratch, one full t2 stash per stage
     static_assert(ROUNDS == 3 || rounds_needed(N, C, N) <= 2, "2-view kernel needs FIRST+MID to cover all bits");
+    static_assert(rounds_needed(N, C, N) <= 3, "FIRST+MID+LAST must cover every tile bit");
     static_assert(ROUNDS == 3 || PREG > 0, "the 2-view loss kernel keeps g in registers");
     extern __shared__ float4 smem4[];
     __shared__ uint64_t full_bar[PAIRS][NS], empty_bar[PAIRS][NS], ready_bar[PAIRS][NS];
