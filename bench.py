@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunk", type=int, default=16, help="MC samples per kernel launch")
+    ap.add_argument("--chunk", type=int, default=32, help="MC samples per kernel launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

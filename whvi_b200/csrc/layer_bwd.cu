@@ -556,7 +556,7 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     const size_t smem = (c.target != nullptr && bwd_stage_target(N, PAIRS, NS, SINGLE, ALIAS, gtab, MINB)) ? smem_tgt : smem_plain;
     const int64_t D = int64_t(1) << k;
     const int64_t tiles_per_sample = (c.B * D + int64_t(tile) - 1) / int64_t(tile);
-    const Plan plan = make_plan(c.S, tiles_per_sample, PAIRS, 148 * 4, 8);
+    const Plan plan = make_plan_waves(c.S, tiles_per_sample, PAIRS, 148, 8, 8);
     const size_t need = sizeof(float) * size_t(c.S) * plan.ctas_per_sample * PAIRS * 4 * tile;
     if (c.need_only) {
         *c.need_only = need;

@@ -143,5 +143,24 @@ inline Plan make_plan(int64_t S, int64_t tiles_per_sample, int groups, int64_t t
     return Plan{static_cast<int>(ctas), static_cast<int>(iters)};
 }
 
+// Persistent kernels that run ONE CTA per SM (the backward and the loss layer: shared memory is the
+// limit): the grid executes in waves of `slots` CTAs, so the time is ~ waves x iterations per CTA.
+// Pick the CTAs-per-sample count that minimises that product (a grid of 608 CTAs on 148 SMs costs a
+// fifth wave for 16 CTAs); ties go to the smaller grid (smaller workspace).  At least `min_iters`
+// tiles per group unless the sample is smaller than that.
+inline Plan make_plan_waves(int64_t S, int64_t tiles_per_sample, int groups, int64_t slots, int min_iters, int max_waves)
+{
+    const int64_t max_cps = (tiles_per_sample + groups - 1) / groups;
+    int64_t best_cps = 1, best_iters = (tiles_per_sample + groups - 1) / groups, best_cost = -1;
+    for (int64_t cps = 1; cps <= max_cps && cps * S <= slots * max_waves; ++cps) {
+        int64_t iters = (tiles_per_sample + cps * groups - 1) / (cps * groups);
+        if (iters < min_iters && cps > 1) break;
+        const int64_t eff = (tiles_per_sample + iters * groups - 1) / (iters * groups);  // CTAs actually needed
+        const int64_t waves = (eff * S + slots - 1) / slots;
+        const int64_t cost = waves * iters;
+        if (best_cost < 0 || cost < best_cost) best_cost = cost, best_cps = eff, best_iters = iters;
+    }
+    return Plan{static_cast<int>(best_cps), static_cast<int>(best_iters)};
+}
 
 }  // namespace whvi

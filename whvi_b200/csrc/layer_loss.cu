@@ -341,7 +341,7 @@ static int launch_loss_cfg(const LayerLossCall& c, int k, cudaStream_t stream)
     static_assert(smem <= 227 * 1024, "loss kernel shared memory");
     const int64_t D = int64_t(1) << k;
     const int64_t tiles_per_sample = (c.B * D + int64_t(tile) - 1) / int64_t(tile);
-    const Plan plan = make_plan(c.S, tiles_per_sample, PAIRS, 148 * 4, 8);
+    const Plan plan = make_plan_waves(c.S, tiles_per_sample, PAIRS, 148, 8, 8);
     const int64_t slabs = int64_t(c.S) * plan.ctas_per_sample * PAIRS;
     const size_t need = sizeof(float) * size_t(slabs) * 4 * tile;
     if (c.need_ws) {
