@@ -18,6 +18,7 @@
 #include <set>
 #include <vector>
 #include "layout.cuh"
+#include "plan.cuh"
 
 using namespace whvi;
 
@@ -158,8 +159,37 @@ static void check_engine(int n, int c, int k, const int* seq, int len)
     CHECK(err == 0.0, "engine mismatch n=%d c=%d k=%d len=%d err=%g", n, c, k, len, err);
 }
 
+// Work-split plans: every tile covered, at least one iteration, grids bounded, and the wave-aware
+// plan never costs more waves x iterations than the plain one on a 148-SM chip.
+static void check_plans()
+{
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+    for (int t = 0; t < 20000; ++t) {
+        const int64_t S = 1 + next() % (t % 3 == 0 ? 4096 : 160);
+        const int64_t tiles = 1 + next() % (t % 2 == 0 ? 70000 : 300);
+        const int groups = 1 << (next() % 4);
+        const Plan a = make_plan(S, tiles, groups, 148 * 4, 8);
+        const Plan b = make_plan_waves(S, tiles, groups, 148, 8, 8);
+        auto cost = [&](const Plan& p) { return ((int64_t(p.ctas_per_sample) * S + 147) / 148) * p.iters_per_group; };
+        for (const Plan& p : {a, b}) {
+            CHECK(p.ctas_per_sample >= 1 && p.iters_per_group >= 1, "plan S=%ld tiles=%ld g=%d: empty", (long)S, (long)tiles, groups);
+            CHECK(int64_t(p.ctas_per_sample) * p.iters_per_group * groups >= tiles, "plan S=%ld tiles=%ld g=%d: tiles not covered",
+                  (long)S, (long)tiles, groups);
+            // no CTA without work: the last CTA's first tile exists
+            CHECK((int64_t(p.ctas_per_sample) - 1) * p.iters_per_group * groups < tiles, "plan S=%ld tiles=%ld g=%d: idle CTA",
+                  (long)S, (long)tiles, groups);
+        }
+        // a = make_plan pads to min_iters even when the sample has fewer tiles; compare on real work only
+        if (a.iters_per_group * int64_t(groups) <= tiles)
+            CHECK(cost(b) <= cost(a), "plan S=%ld tiles=%ld g=%d: waves plan costs %ld > %ld", (long)S, (long)tiles, groups,
+                  (long)cost(b), (long)cost(a));
+    }
+}
+
 int main()
 {
+    check_plans();
     const int cfgs[][2] = {{10, 5}, {11, 5}, {12, 5}, {13, 5}, {12, 6}, {13, 6}, {14, 6}, {15, 6}, {16, 6}};
     for (auto& cfg : cfgs) {
         const int n = cfg[0], c = cfg[1];
