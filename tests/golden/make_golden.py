@@ -208,6 +208,14 @@ def gen_toy():
     out["eval_n_eps"] = np.int64(len(cap.draws))
     for i, e in enumerate(cap.draws):
         out[f"eval_eps{i}"] = npy(e)
+    # WHVIRegression.eval_model (src/networks.py:101-116, :130-132): RMSE of the MC mean and test MNLL
+    with CaptureRandn() as cap:
+        rmse, mnll = model.eval_model(x[160:200], y[160:200])
+    out["evalm_x"], out["evalm_y"] = npy(x[160:200]), npy(y[160:200])
+    out["evalm_rmse"], out["evalm_mnll"] = np.float64(rmse), np.float64(mnll)
+    out["evalm_n_eps"] = np.int64(len(cap.draws))
+    for i, e in enumerate(cap.draws):
+        out[f"evalm_eps{i}"] = npy(e)
     np.savez_compressed(HERE / "toy.npz", **out)
 
 
@@ -252,6 +260,10 @@ def gen_init():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:      # e.g. `make_golden.py toy`: regenerate only the named fixtures
+        for name in sys.argv[1:]:
+            globals()[f"gen_{name}"]()
+        sys.exit(0)
     gen_init()
     gen_fwht()
     gen_kl()

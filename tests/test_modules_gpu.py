@@ -92,6 +92,14 @@ def test_reference_semantics_toy_model(golden):
         pred = model(t(g["eval_x"]))
     assert pred.shape == g["eval_pred"].shape
     assert rel_err(pred.cpu().numpy(), g["eval_pred"]) < TOL
+    # WHVIRegression.eval_model: RMSE of the MC mean and test MNLL as the reference returns them
+    assert int(g["evalm_n_eps"]) == S * n_blocks
+    for i, b in enumerate(blocks):
+        b.inject_eps(torch.stack([t(g[f"evalm_eps{s * n_blocks + i}"]) for s in range(S)]))
+    rmse, mnll = model.eval_model(t(g["evalm_x"]), t(g["evalm_y"]))
+    assert isinstance(rmse, float) and isinstance(mnll, float)
+    assert abs(rmse - float(g["evalm_rmse"])) < TOL * float(g["evalm_rmse"])
+    assert abs(mnll - float(g["evalm_mnll"])) < TOL * abs(float(g["evalm_mnll"]))
 
 
 def oracle_layer(layer, x, eps_per_block):
