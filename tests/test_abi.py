@@ -44,3 +44,44 @@ def test_no_oracle_import_in_product():
         src = py.read_text()
         assert "oracle" not in src.replace("# oracle", ""), f"{py} mentions the oracle"
         assert "/root/reference" not in src
+
+
+def test_argument_validation_without_a_gpu():
+    """Every entry point validates its arguments before it touches CUDA: bad calls return a negative
+    WHVI_E_* code and leave a message in whvi_last_error() (what the Python side turns into the
+    RuntimeError the reference's TORCH_CHECKs raise, src/fwht/cuda/fwht_cuda.cpp:6-10).  No kernel runs."""
+    from whvi_b200 import _lib
+    L = _lib.lib()
+    a = 1 << 20        # a 16-byte aligned fake "device pointer" that is never dereferenced
+    E_NULL, E_SHAPE, E_ALIGN, E_MODE = -1, -2, -3, -4
+
+    def err():
+        return L.whvi_last_error().decode()
+
+    assert L.whvi_fwht_f32(a, a, 4, 12, None) == E_SHAPE and "power of 2" in err()         # fwht_cuda.cpp:10
+    assert L.whvi_fwht_f32(a, a, -1, 16, None) == E_SHAPE
+    assert L.whvi_fwht_f32(None, a, 4, 16, None) == E_NULL
+    assert L.whvi_fwht_f32(a + 4, a, 4, 16, None) == E_ALIGN
+    assert L.whvi_fwht_f32(a, a, 0, 16, None) == 0                                         # empty batch: no-op
+    assert L.whvi_fwht_f64(a, a, 4, 24, None) == E_SHAPE
+    # fused layer: D range, power of two, sample stride, flags, pointers
+    assert L.whvi_layer_fwd_f32(a, 0, a, a, a, None, a, 2, 3, 48, None) == E_SHAPE
+    assert L.whvi_layer_fwd_f32(a, 0, a, a, a, None, a, 2, 3, 2, None) == E_SHAPE and "outside" in err()
+    assert L.whvi_layer_fwd_f32(a, 7, a, a, a, None, a, 2, 3, 64, None) == E_SHAPE and "x_sample_stride" in err()
+    assert L.whvi_layer_fwd_f32(None, 0, a, a, a, None, a, 2, 3, 64, None) == E_NULL
+    assert L.whvi_layer_fwd_fused_f32(a, 0, a, a, a, None, a, 2, 3, 64, 8, None, None, None) == E_MODE
+    assert L.whvi_layer_fwd_fused_f32(a, 0, a, a, a, None, a, 2, 3, 64, 0, a, None, None) == E_NULL  # target without partials
+    assert L.whvi_layer_fwd_f32(a, 0, a, a, a, None, a, 0, 3, 64, None) == 0                # S = 0: nothing to do
+    ws = ctypes.c_size_t(0)
+    assert L.whvi_layer_bwd_workspace_bytes(2, 3, 1 << 14, ctypes.byref(ws)) == E_SHAPE     # backward stops at 8192
+    assert L.whvi_layer_bwd_workspace_bytes(16, 4096, 4096, ctypes.byref(ws)) == 0 and ws.value > 0
+    assert L.whvi_layer_bwd_f32(a, 0, a, a, a, a, a, None, a, a, None, a, 0, 2, 3, 64, None) == E_NULL   # dg missing
+    assert L.whvi_layer_bwd_f32(a, 0, a, a, a, a, a, a, a, a, None, a, 16, 2, 3, 64, None) == -5          # workspace too small
+    n_sq = ctypes.c_int64(0)
+    assert L.whvi_layer_loss_sizes(2, 3, 64, ctypes.byref(ws), ctypes.byref(n_sq)) in (0, E_SHAPE)
+    assert L.whvi_reparam_f32(a, a, a, a, 2, 64, 7, None) == E_MODE
+    assert L.whvi_kl_f32(a, a, ctypes.c_float(-1.0), 64, 0, a, None, None, ctypes.c_float(1.0), 0, None) == E_SHAPE
+    assert L.whvi_kl_f32(a, a, ctypes.c_float(1.0), 64, 5, a, None, None, ctypes.c_float(1.0), 0, None) == E_MODE
+    assert L.whvi_mc_moments_f32(a, a, a, 2, 6, 0, None) == E_SHAPE                          # n % 4
+    assert L.whvi_mc_moments_strided_f32(a, 8, None, None, a, None, 2, 16, None) == E_SHAPE  # stride < n
+    assert L.whvi_mc_moments_f32(a, None, a, 2, 8, 0, None) == E_NULL
