@@ -142,3 +142,59 @@ def test_stacked_dims_match_reference_probe():
     assert O.stacked_dims(13, 128) == (16, 128, 3, 8)
     assert O.stacked_dims(13, 32) == (16, 32, 3, 2)
     assert O.stacked_dims(8, 20) == (8, 24, 0, 3)
+
+
+def test_oracle_backward_is_the_derivative_of_its_forward():
+    """Independent of the reference's autograd goldens: central finite differences (fp64) of the
+    oracle's own forward reproduce every gradient its backward returns (layer, reparameterisation, KL)."""
+    rng = np.random.default_rng(42)
+    S, B, D = 3, 4, 16
+    x, g = rng.standard_normal((S, B, D)), rng.standard_normal((S, D))
+    s1, s2, bias = rng.standard_normal(D), rng.standard_normal(D), rng.standard_normal(D)
+    dy = rng.standard_normal((S, B, D))
+    f = lambda x_, g_, s1_, s2_, b_: float((O.layer_fwd(x_, g_, s1_, s2_, b_) * dy).sum())
+    dx, dg, ds1, ds2, db = O.layer_bwd(x, dy, g, s1, s2, want_dbias=True)
+    h = 1e-6
+
+    def fd(arr, idx, which):
+        p, m = arr.copy(), arr.copy()
+        p[idx] += h
+        m[idx] -= h
+        args_p = {"x": x, "g": g, "s1": s1, "s2": s2, "b": bias}
+        args_m = dict(args_p)
+        args_p[which], args_m[which] = p, m
+        return (f(args_p["x"], args_p["g"], args_p["s1"], args_p["s2"], args_p["b"]) -
+                f(args_m["x"], args_m["g"], args_m["s1"], args_m["s2"], args_m["b"])) / (2 * h)
+
+    for arr, grad, which in ((x, dx, "x"), (g, dg, "g"), (s1, ds1, "s1"), (s2, ds2, "s2"), (bias, db, "b")):
+        for _ in range(6):
+            idx = tuple(int(rng.integers(0, n)) for n in arr.shape)
+            num = fd(arr, idx, which)
+            assert abs(num - grad[idx]) < 1e-6 * max(1.0, abs(num)), (which, idx, num, grad[idx])
+    # shared x: dx is summed over the samples
+    xs = x[0]
+    dxs = O.layer_bwd(xs, dy, g, s1, s2)[0]
+    assert rel_err(dxs, O.layer_bwd(np.broadcast_to(xs, (S, B, D)).copy(), dy, g, s1, s2)[0].sum(0)) < 1e-12
+    # reparameterisation: g = mu + softplus(rho) * eps
+    mu, rho, eps = rng.standard_normal(D), rng.standard_normal(D), rng.standard_normal((S, D))
+    w = rng.standard_normal((S, D))
+    dmu, drho = O.reparam_bwd(rho, eps, w)
+    for j in (0, 5, D - 1):
+        rp, rm = rho.copy(), rho.copy()
+        rp[j] += h
+        rm[j] -= h
+        num = float(((O.reparam(mu, rp, eps) - O.reparam(mu, rm, eps)) * w).sum()) / (2 * h)
+        assert abs(num - drho[j]) < 1e-6 * max(1.0, abs(num))
+        assert abs(dmu[j] - w[:, j].sum()) < 1e-12
+    # KL value and gradients, both modes
+    for mode in (0, 1):
+        val, kmu, krho = O.kl(mu, rho, 1.7, mode, grads=True)
+        for j in (1, D - 2):
+            for arr, grad, pos in ((mu, kmu, 0), (rho, krho, 1)):
+                p, m = arr.copy(), arr.copy()
+                p[j] += h
+                m[j] -= h
+                a = O.kl(p, rho, 1.7, mode) if pos == 0 else O.kl(mu, p, 1.7, mode)
+                b = O.kl(m, rho, 1.7, mode) if pos == 0 else O.kl(mu, m, 1.7, mode)
+                num = (float(a) - float(b)) / (2 * h)
+                assert abs(num - grad[j]) < 1e-6 * max(1.0, abs(num)), (mode, pos, j)
