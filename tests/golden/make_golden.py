@@ -19,6 +19,8 @@ What is recorded (all from reference code paths, nothing from this repo):
   init.npz      state_dict of a freshly constructed model under torch.manual_seed(0)
   toy.npz       README toy model (README.md:25-44): loss, KL, MNLL and every grad for one
                 batch with captured eps; state_dict key names
+  train.npz     three Adam steps of the toy model as written: per-step losses, captured eps,
+                parameters before and after
   paper.npz     PAPER-semantics layer (docstring src/weights.py:77) from a dense fp64
                 H-matrix formula using the reference's own build_H, with autograd grads
 """
@@ -219,6 +221,45 @@ def gen_toy():
     np.savez_compressed(HERE / "toy.npz", **out)
 
 
+def gen_train():
+    """Three optimisation steps of the README toy model with the reference as written: losses per
+    step and every parameter afterwards (fixed minibatch), eps captured per step.  Plain SGD with a
+    step size scaled to the first gradient: Adam would turn the reference's rounding-noise gradients
+    (exactly zero in exact arithmetic) into full-size steps and make the comparison
+    ill-conditioned."""
+    out = {}
+    torch.manual_seed(0)
+    x = torch.randn(200, 3)
+    y = torch.reshape(x[:, 0] + x[:, 1] ** 2 - 0.3 * x[:, 2] ** 3, (-1, 1))
+    model = WHVIRegression([WHVILinear(3, 16, lambda_=2.0), torch.nn.ReLU(), WHVILinear(16, 1)], train_samples=2)
+    randomise(model.sequential, 23)
+    model.train()
+    for name, p in model.named_parameters():
+        out[f"init.{name}"] = npy(p).copy()       # npy() aliases the parameter, which SGD updates in place
+    xb, yb = x[:64], y[:64]
+    model.loss(xb, yb, n=150).backward()          # probe gradient scale (its eps draws are not recorded)
+    gmax = max(float(p.grad.abs().max()) for p in model.parameters())
+    model.zero_grad()
+    lr = 0.02 / gmax
+    out["lr"] = np.float64(lr)
+    opt = torch.optim.SGD(model.parameters(), lr=lr)
+    losses = []
+    for step in range(3):
+        with CaptureRandn() as cap:
+            loss = model.loss(xb, yb, n=150)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        losses.append(float(loss))
+        out[f"n_eps_{step}"] = np.int64(len(cap.draws))
+        for i, e in enumerate(cap.draws):
+            out[f"eps_{step}_{i}"] = npy(e)
+    out["x"], out["y"], out["losses"] = npy(xb), npy(yb), np.array(losses)
+    for name, p in model.named_parameters():
+        out[f"final.{name}"] = npy(p)
+    np.savez_compressed(HERE / "train.npz", **out)
+
+
 def gen_paper():
     """PAPER semantics y = x @ (S1 H diag(g) H S2)^T in dense fp64 with the reference's
     own build_H (src/utils.py:74-101); grads from torch autograd."""
@@ -270,6 +311,7 @@ if __name__ == "__main__":
     gen_mnll()
     gen_layers()
     gen_toy()
+    gen_train()
     gen_paper()
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size, "bytes")

@@ -328,3 +328,30 @@ def test_train_model_cuda_graph():
     after = model.eval_model(x, y)[1]
     assert np.isfinite(after) and after < before
     assert float(opt.param_groups[0]["lr"]) < 2e-2   # the scheduler reached the captured step
+
+
+def test_three_training_steps_match_the_reference(golden):
+    """loss -> backward -> optimizer step, three times, against the reference run as written on CPU
+    (tests/golden/make_golden.py gen_train): per-step losses and every parameter afterwards."""
+    g = golden("train")
+    model = W.WHVIRegression([W.WHVILinear(3, 16, lambda_=2.0, semantics="reference"), torch.nn.ReLU(),
+                              W.WHVILinear(16, 1, semantics="reference")], train_samples=2)
+    model.load_state_dict({k: torch.from_numpy(g[f"init.{k}"]) for k in model.state_dict().keys()})
+    model = model.to(dev()).train()
+    opt = torch.optim.SGD(model.parameters(), lr=float(g["lr"]))
+    blocks = [b for layer in model._whvi_layers() for b in layer.square_blocks()]
+    S, n_blocks = 2, len(blocks)
+    x, y = t(g["x"]), t(g["y"])
+    for step in range(3):
+        assert int(g[f"n_eps_{step}"]) == S * n_blocks
+        for i, b in enumerate(blocks):
+            b.inject_eps(torch.stack([t(g[f"eps_{step}_{s * n_blocks + i}"]) for s in range(S)]))
+        loss = model.loss(x, y, n=150)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        assert abs(loss.item() - float(g["losses"][step])) < TOL * abs(float(g["losses"][step])), step
+    change = max(float(np.abs(g[f"final.{k}"] - g[f"init.{k}"]).max()) for k, _ in model.named_parameters())
+    for name, p in model.named_parameters():
+        diff = float(np.max(np.abs(p.detach().cpu().numpy().astype(np.float64) - g[f"final.{name}"])))
+        assert diff < 1e-3 * change, (name, diff, change)   # 1e-4 per gradient, three accumulated steps
