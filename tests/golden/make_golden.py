@@ -21,6 +21,8 @@ What is recorded (all from reference code paths, nothing from this repo):
                 batch with captured eps; state_dict key names
   train.npz     three Adam steps of the toy model as written: per-step losses, captured eps,
                 parameters before and after
+  dims.npz      setup_dimensions on a 199 x 200 grid; WHVILinear's weight class and parameter
+                count for every (n_in, n_out) <= 40
   paper.npz     PAPER-semantics layer (docstring src/weights.py:77) from a dense fp64
                 H-matrix formula using the reference's own build_H, with autograd grads
 """
@@ -260,6 +262,30 @@ def gen_train():
     np.savez_compressed(HERE / "train.npz", **out)
 
 
+def gen_dims():
+    """WHVIStackedMatrix.setup_dimensions (src/weights.py:135-160) on a grid, and which weight class /
+    how many parameters WHVILinear builds for every (n_in, n_out) <= 40 (src/layers.py:31-38)."""
+    from src.weights import WHVIStackedMatrix
+    ins, outs = np.arange(2, 201), np.arange(1, 201)
+    table = np.zeros((len(ins), len(outs), 4), dtype=np.int64)
+    for i, a in enumerate(ins):
+        for j, b in enumerate(outs):
+            table[i, j] = WHVIStackedMatrix.setup_dimensions(int(a), int(b))
+    kinds = np.zeros((40, 40), dtype=np.int64)      # 0 column, 1 column transposed, 2 square, 3 stacked
+    counts = np.zeros((40, 40), dtype=np.int64)
+    names = {"WHVIColumnMatrix": 0, "WHVISquarePow2Matrix": 2, "WHVIStackedMatrix": 3}
+    for a in range(1, 41):
+        for b in range(1, 41):
+            layer = WHVILinear(a, b)
+            sub = layer.weight_submodule
+            k = names[type(sub).__name__]
+            if k == 0 and getattr(sub, "transposed", False):
+                k = 1
+            kinds[a - 1, b - 1] = k
+            counts[a - 1, b - 1] = sum(p.numel() for p in layer.parameters())
+    np.savez_compressed(HERE / "dims.npz", ins=ins, outs=outs, table=table, kinds=kinds, counts=counts)
+
+
 def gen_paper():
     """PAPER semantics y = x @ (S1 H diag(g) H S2)^T in dense fp64 with the reference's
     own build_H (src/utils.py:74-101); grads from torch autograd."""
@@ -312,6 +338,7 @@ if __name__ == "__main__":
     gen_layers()
     gen_toy()
     gen_train()
+    gen_dims()
     gen_paper()
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size, "bytes")

@@ -56,3 +56,23 @@ def test_kl_diag_normal_helper(golden):
     g = golden("kl")
     v = kl_diag_normal(*(torch.from_numpy(g[f"gen_{k}"]) for k in ("mu1", "sd1", "mu2", "sd2")))
     assert abs(float(v) - float(g["gen_kl"])) < 1e-4
+
+
+def test_dimensions_and_dispatch_match_reference_grid(golden):
+    """setup_dimensions (integer arithmetic here, float log + fix-up branch in the reference,
+    src/weights.py:150-152) and WHVILinear's shape dispatch / parameter counts on a grid generated
+    by the reference itself."""
+    g = golden("dims")
+    for i, a in enumerate(g["ins"]):
+        for j, b in enumerate(g["outs"]):
+            assert W.WHVIStackedMatrix.setup_dimensions(int(a), int(b)) == tuple(int(v) for v in g["table"][i, j]), (a, b)
+    probe = (1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 40)   # a subset keeps the CPU suite short
+    for a in probe:
+        for b in probe:
+            layer = W.WHVILinear(a, b)
+            sub = layer.weight_submodule
+            kind = {W.WHVIColumnMatrix: 0, W.WHVISquarePow2Matrix: 2, W.WHVIStackedMatrix: 3}[type(sub)]
+            if kind == 0 and sub.transposed:
+                kind = 1
+            assert kind == int(g["kinds"][a - 1, b - 1]), (a, b)
+            assert sum(p.numel() for p in layer.parameters()) == int(g["counts"][a - 1, b - 1]), (a, b)
