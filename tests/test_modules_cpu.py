@@ -63,16 +63,16 @@ def test_dimensions_and_dispatch_match_reference_grid(golden):
     src/weights.py:150-152) and WHVILinear's shape dispatch / parameter counts on a grid generated
     by the reference itself."""
     g = golden("dims")
-    for i, a in enumerate(g["ins"]):
-        for j, b in enumerate(g["outs"]):
-            assert W.WHVIStackedMatrix.setup_dimensions(int(a), int(b)) == tuple(int(v) for v in g["table"][i, j]), (a, b)
-    probe = (1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 40)   # a subset keeps the CPU suite short
-    for a in probe:
-        for b in probe:
+    ins, outs, table, kinds, counts = (np.asarray(g[k]) for k in ("ins", "outs", "table", "kinds", "counts"))  # decompress once
+    for i, a in enumerate(ins):
+        for j, b in enumerate(outs):
+            assert W.WHVIStackedMatrix.setup_dimensions(int(a), int(b)) == tuple(int(v) for v in table[i, j]), (a, b)
+    for a in range(1, 41):
+        for b in range(1, 41):
             layer = W.WHVILinear(a, b)
             sub = layer.weight_submodule
             kind = {W.WHVIColumnMatrix: 0, W.WHVISquarePow2Matrix: 2, W.WHVIStackedMatrix: 3}[type(sub)]
             if kind == 0 and sub.transposed:
                 kind = 1
-            assert kind == int(g["kinds"][a - 1, b - 1]), (a, b)
-            assert sum(p.numel() for p in layer.parameters()) == int(g["counts"][a - 1, b - 1]), (a, b)
+            assert kind == int(kinds[a - 1, b - 1]), (a, b)
+            assert sum(p.numel() for p in layer.parameters()) == int(counts[a - 1, b - 1]), (a, b)
