@@ -99,6 +99,53 @@ static void check_transposition(int n, int c, int ida, int idb)
     }
 }
 
+// STUDY (not used by the kernels yet): the same transpositions with a
+// PADDED reader layout instead of the XOR swizzle -- thread tid' owns E + 4 words at tid' * (E + 4),
+// register r at word r.  Every address is then (thread base) + (compile-time constant): no LOP3 per
+// STS/LDS.  Checks: bijection into T * (E + 4) words, scalar writes of a warp hit 32 distinct
+// banks, float4 reads of a quarter-warp hit 8 distinct 16-byte bank groups, and the writer's
+// address splits into a thread part plus a register part additively.
+static uint32_t phys_padded(const View& v, uint32_t idx)
+{
+    uint32_t reg = 0, tid = 0;
+    for (int p = 0; p < v.n; ++p) {
+        const uint32_t b = (idx >> v.bit[p]) & 1u;
+        if (p < v.c) reg |= b << p; else tid |= b << (p - v.c);
+    }
+    return tid * ((1u << v.c) + 4u) + reg;
+}
+static int g_padded_fail = 0;
+static void study_padded(int n, int c, int ida, int idb)
+{
+    const View a = get_view_rt(n, c, ida), b = get_view_rt(n, c, idb);
+    const int E = 1 << c, T = 1 << (n - c), N = 1 << n;
+    std::set<uint32_t> seen;
+    for (uint32_t i = 0; i < (uint32_t)N; ++i) seen.insert(phys_padded(b, i));
+    bool ok = (int)seen.size() == N && *seen.rbegin() < (uint32_t)(T * (E + 4));
+    for (int tid0 = 0; tid0 < T && ok; tid0 += 32)
+        for (int r = 0; r < E && ok; ++r) {
+            std::set<uint32_t> banks;
+            for (int lane = 0; lane < 32; ++lane) {
+                const uint32_t tid = tid0 + lane;
+                const uint32_t want = phys_padded(b, logical_of(a, tid, r));
+                // additive split: thread part (r = 0) + register part (tid = 0)
+                ok = ok && want == phys_padded(b, logical_of(a, tid, 0)) + phys_padded(b, view_reg_logical(a, r));
+                banks.insert(want & 31u);
+            }
+            ok = ok && banks.size() == 32;
+        }
+    for (int tid0 = 0; tid0 < T && ok; tid0 += 8)
+        for (int j = 0; j < E / 4 && ok; ++j) {
+            std::set<uint32_t> groups;
+            for (int l = 0; l < 8; ++l) groups.insert(((uint32_t(tid0 + l) * (E + 4) + 4 * j) >> 2) & 7u);
+            ok = ok && groups.size() == 8;
+        }
+    if (!ok) {
+        ++g_padded_fail;
+        std::printf("padded-layout study: n=%d c=%d %d->%d NOT conflict-free / additive\n", n, c, ida, idb);
+    }
+}
+
 static void fwht_bits(std::vector<double>& x, int k)
 {
     const size_t N = x.size();
@@ -202,6 +249,11 @@ int main()
         check_transposition(n, c, 2, 3);
         check_transposition(n, c, 3, 0);
         if (rounds_needed(n, c, n) == 2) check_transposition(n, c, 1, 0);
+        study_padded(n, c, 0, 1);
+        study_padded(n, c, 1, 2);
+        study_padded(n, c, 2, 3);
+        study_padded(n, c, 3, 0);
+        if (rounds_needed(n, c, n) == 2) study_padded(n, c, 1, 0);
         const int fwd3[3] = {0, 1, 2}, rev3[3] = {2, 3, 0}, fwd2[2] = {0, 1}, rev2[2] = {1, 0};
         for (int k = 0; k <= n; ++k) {
             check_engine(n, c, k, fwd3, 3);
@@ -221,6 +273,8 @@ int main()
         for (int p = 0; p < c; ++p) std::printf("%d ", l.bit[p]);
         std::printf("]\n");
     }
+    std::printf("padded-layout study: %s\n", g_padded_fail ? "some transpositions need more than padding" :
+                                                            "every transposition is conflict-free and additive with E + 4 padding");
     std::printf(g_fail ? "FAILED: %d checks\n" : "all layout checks passed\n", g_fail);
     return g_fail ? 1 : 0;
 }
