@@ -1,6 +1,8 @@
 """Build libwhvi_b200.so (the C-ABI CUDA library) in-tree with plain nvcc for sm_100a.
 
     python -m whvi_b200.build [--force] [--verbose]
+    python -m whvi_b200.build --variant NAME -DFOO=1 ...   # A/B builds: tools/lab/libwhvi_b200_NAME.so, own object
+                                                           # directory, extra -D flags; time it with tools/lab_bwd.py
 
 No torch headers are involved, so the whole library builds in seconds.  The .so lands
 next to this file (git-ignored, but shipped to the GPU box by gpurun).
@@ -39,14 +41,19 @@ def _stale(target: Path, deps: list[Path]) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    OBJ.mkdir(exist_ok=True)
+def build(force: bool = False, verbose: bool = False, variant: str | None = None, defines: tuple[str, ...] = ()) -> Path:
+    obj_dir, lib_path = OBJ, LIB
+    if variant:  # experiment build: never touches the product library
+        lab = PKG.parent / "tools" / "lab"
+        lab.mkdir(parents=True, exist_ok=True)
+        obj_dir, lib_path = lab / f"_obj_{variant}", lab / f"libwhvi_b200_{variant}.so"
+    obj_dir.mkdir(exist_ok=True)
     hdrs = _deps()
     jobs = []
     for src in sources():
-        obj = OBJ / (src.stem + ".o")
+        obj = obj_dir / (src.stem + ".o")
         if force or _stale(obj, [src] + hdrs):
-            cmd = [NVCC, *ARCH, *CFLAGS, "-c", str(src), "-o", str(obj)]
+            cmd = [NVCC, *ARCH, *CFLAGS, *defines, "-c", str(src), "-o", str(obj)]
             if verbose:
                 cmd[1:1] = ["-Xptxas", "-v"]
             jobs.append(cmd)
@@ -61,11 +68,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(run, jobs))
-    objs = [OBJ / (s.stem + ".o") for s in sources()]
-    if force or jobs or _stale(LIB, objs):
-        run([NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
-    return LIB
+    objs = [obj_dir / (s.stem + ".o") for s in sources()]
+    if force or jobs or _stale(lib_path, objs):
+        run([NVCC, *ARCH, "-shared", "-o", str(lib_path), *map(str, objs), "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    _defines = tuple(a for a in sys.argv[1:] if a.startswith("-D"))
+    if _defines and not _variant:
+        sys.exit("extra -D flags need --variant NAME (the product library is always built from the plain sources)")
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=_variant, defines=_defines))
