@@ -57,11 +57,12 @@ static void check_transposition(int n, int c, int ida, int idb)
     const View a = get_view_rt(n, c, ida), b = get_view_rt(n, c, idb);
     const int E = 1 << c, T = 1 << (n - c), N = 1 << n;
     // bijection
-    std::vector<char> hit(N, 0);
+    const uint32_t words = scratch_words(n, c);
+    std::vector<char> hit(words, 0);
     for (uint32_t i = 0; i < (uint32_t)N; ++i) {
         uint32_t p = view_phys(b, i);
-        CHECK(p < (uint32_t)N && !hit[p], "phys not bijective n=%d c=%d", n, c);
-        if (p < (uint32_t)N) hit[p] = 1;
+        CHECK(p < words && !hit[p], "phys not bijective n=%d c=%d", n, c);
+        if (p < words) hit[p] = 1;
     }
     // writer: address split + bank conflicts per warp instruction
     for (int tid0 = 0; tid0 < T; tid0 += 32) {
@@ -74,7 +75,14 @@ static void check_transposition(int n, int c, int ida, int idb)
                 for (int j = 0; j < n - c; ++j)
                     if ((tid >> j) & 1u) wbase ^= view_phys(b, 1u << a.bit[c + j]);
                 uint32_t pr = view_phys(b, view_reg_logical(a, r));
+#if WHVI_PADDED
+                wbase = 0;
+                for (int j = 0; j < n - c; ++j)
+                    if ((tid >> j) & 1u) wbase += view_phys(b, 1u << a.bit[c + j]);
+                uint32_t got = wbase + pr;
+#else
                 uint32_t got = (wbase ^ (pr & 0x1Cu)) + (pr & ~0x1Cu);
+#endif
                 CHECK(got == want, "writer split n=%d c=%d %d->%d tid=%u r=%d got=%u want=%u", n, c, ida, idb, tid, r, got,
                       want);
                 banks.insert(want & 31u);
@@ -89,7 +97,11 @@ static void check_transposition(int n, int c, int ida, int idb)
             std::set<uint32_t> groups;
             for (int l = 0; l < 8; ++l) {
                 uint32_t tid = tid0 + l;
+#if WHVI_PADDED
+                uint32_t addr = tid * (E + 4) + 4 * j;
+#else
                 uint32_t addr = (tid << c) + ((j ^ swz_of_tid(c, tid)) << 2);
+#endif
                 CHECK(addr == view_phys(b, logical_of(b, tid, 4 * j)), "reader addr n=%d c=%d", n, c);
                 groups.insert((addr >> 2) & 7u);
             }
@@ -167,7 +179,7 @@ static void check_engine(int n, int c, int k, const int* seq, int len)
     ref = x;
     fwht_bits(ref, k);
     std::vector<std::vector<double>> regs(T, std::vector<double>(E));
-    std::vector<double> smem(N);
+    std::vector<double> smem(scratch_words(n, c));
     std::set<int> done;
     for (int round = 0; round < len; ++round) {
         const View v = get_view_rt(n, c, seq[round]);
@@ -181,7 +193,11 @@ static void check_engine(int n, int c, int k, const int* seq, int len)
             for (int tid = 0; tid < T; ++tid)
                 for (int j = 0; j < E / 4; ++j)
                     for (int q = 0; q < 4; ++q)
+#if WHVI_PADDED
+                        regs[tid][4 * j + q] = smem[tid * (E + 4) + 4 * j + q];
+#else
                         regs[tid][4 * j + q] = smem[(tid << c) + ((j ^ swz_of_tid(c, tid)) << 2) + q];
+#endif
         }
         for (int p = 0; p < c; ++p) {
             int b = v.bit[p];

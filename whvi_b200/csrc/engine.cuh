@@ -217,7 +217,11 @@ __device__ __forceinline__ uint32_t transpose_writer_base(uint32_t tid)
         constexpr View a = get_view(N, C, VA);
         constexpr View b = get_view(N, C, VB);
         constexpr uint32_t col = view_phys(b, 1u << a.bit[C + j]);
+#if WHVI_PADDED
+        base += ((tid >> j) & 1u) ? col : 0u;   // the padded map is additive over disjoint index bits
+#else
         base ^= ((tid >> j) & 1u) ? col : 0u;
+#endif
     });
     return base;
 }
@@ -230,9 +234,13 @@ __device__ __forceinline__ void transpose_write(const float (&v)[1 << C], float*
         constexpr View a = get_view(N, C, VA);
         constexpr View b = get_view(N, C, VB);
         constexpr uint32_t pr = view_phys(b, view_reg_logical(a, r));
+#if WHVI_PADDED
+        buf[wbase + pr] = v[r];
+#else
         constexpr uint32_t lo = pr & 0x1Cu;   // may overlap thread bits (swizzle): XOR
         constexpr uint32_t hi = pr & ~0x1Cu;  // disjoint from thread bits: additive
         buf[(wbase ^ lo) + hi] = v[r];
+#endif
     });
 }
 
@@ -241,11 +249,19 @@ template <int C>
 __device__ __forceinline__ void transpose_read(float (&v)[1 << C], const float* buf, uint32_t tid)
 {
     constexpr int E = 1 << C;
+#if WHVI_PADDED
+    const float* base = buf + tid * (E + 4);
+#else
     const uint32_t sw = swz_of_tid(C, tid);
     const float* base = buf + (tid << C);
+#endif
 #pragma unroll
     for (int j = 0; j < E / 4; ++j) {
+#if WHVI_PADDED
+        const float4 q = *reinterpret_cast<const float4*>(base + 4 * j);
+#else
         const float4 q = *reinterpret_cast<const float4*>(base + ((j ^ sw) << 2));
+#endif
         v[4 * j + 0] = q.x;
         v[4 * j + 1] = q.y;
         v[4 * j + 2] = q.z;

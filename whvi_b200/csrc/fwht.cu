@@ -29,7 +29,7 @@ fwht_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total
     const uint32_t tid = threadIdx.x % T;
     const int64_t base = (int64_t(blockIdx.x) * GROUPS + group) * TILE;
     if (base >= total) return;  // whole group leaves together; barriers are per group
-    float* buf = reinterpret_cast<float*>(smem4) + size_t(group) * (kOneRound ? 0 : TILE);
+    float* buf = reinterpret_cast<float*>(smem4) + size_t(group) * (kOneRound ? 0 : scratch_words(N, C));
 
     float v[E];
     const uint32_t toff = tile_thread_offset<N, C, V_FIRST>(tid);
@@ -143,7 +143,7 @@ static int launch_cfg(const float* in, float* out, int64_t total, cudaStream_t s
 {
     static unsigned char smem_ok[64] = {};
     constexpr int threads = (1 << (N - C)) * GROUPS;
-    constexpr size_t smem = (K <= 2) ? 0 : sizeof(float) * (size_t(1) << N) * GROUPS;
+    constexpr size_t smem = (K <= 2) ? 0 : sizeof(float) * size_t(scratch_words(N, C)) * GROUPS;
     auto kernel = fwht_kernel<N, C, K, GROUPS>;
     if (int rc = ensure_smem(kernel, smem, smem_ok)) return rc;
     const int64_t tiles = (total + (int64_t(1) << N) - 1) >> N;

@@ -6,14 +6,15 @@ namespace whvi {
 // ------------------------------------------------------------------------------ backward
 // Does the MNLL target tile ride in the TMA stage (RESID kernels)?  One definition for the
 // kernel's shared-memory carve-up and the launcher's size computation.
-constexpr size_t bwd_smem_bytes(int n, int pairs, int ns, bool single, bool alias, bool gtab, int spt)
+// sw = words of one transposition buffer (scratch_words(n, c); == 2^n unless WHVI_PADDED)
+constexpr size_t bwd_smem_bytes(int n, int pairs, int ns, bool single, bool alias, bool gtab, int spt, size_t sw)
 {
-    return sizeof(float) * ((size_t(spt) * ns + (single ? 2 : 4) + (alias ? 0 : 1)) * (size_t(1) << n) * pairs +
-                            (gtab ? (size_t(1) << n) : 0));
+    return sizeof(float) * (((size_t(spt) * ns + (alias ? 0 : 1)) * (size_t(1) << n) + (single ? 2 : 4) * sw) * pairs +
+                            (gtab ? sw : 0));
 }
-constexpr bool bwd_stage_target(int n, int pairs, int ns, bool single, bool alias, bool gtab, int minb)
+constexpr bool bwd_stage_target(int n, int pairs, int ns, bool single, bool alias, bool gtab, int minb, size_t sw)
 {
-    return bwd_smem_bytes(n, pairs, ns, single, alias, gtab, 3) <= size_t(minb == 2 ? 112 : 200) * 1024;
+    return bwd_smem_bytes(n, pairs, ns, single, alias, gtab, 3, sw) <= size_t(minb == 2 ? 112 : 200) * 1024;
 }
 
 struct BwdArgs {
@@ -83,13 +84,14 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     static_assert(rounds_needed(N, C, N) <= 3, "FIRST+MID+LAST must cover every tile bit (e.g. 5+5+3 = 13 bits at C = 5)");
     constexpr bool GTAB = ROUNDS == 2 && !PREG;  // g in shared memory in MID order (one table per CTA)
     constexpr int STASH = ALIAS ? 0 : 1;
-    constexpr bool STAGE_TGT = RESID && bwd_stage_target(N, PAIRS, NS, SINGLE, ALIAS, ROUNDS == 2 && !PREG, MINB);
+    constexpr int SW = int(scratch_words(N, C));  // one transposition buffer (== TILE unless WHVI_PADDED)
+    constexpr bool STAGE_TGT = RESID && bwd_stage_target(N, PAIRS, NS, SINGLE, ALIAS, ROUNDS == 2 && !PREG, MINB, SW);
     constexpr int SPT = STAGE_TGT ? 3 : 2;   // tiles per stage
-    constexpr int PAIR_FLOATS = (SPT * NS + 2 * SCR + STASH) * int(TILE);
+    constexpr int PAIR_FLOATS = WHVI_PADDED ? (SPT * NS + STASH) * int(TILE) + 2 * SCR * SW : (SPT * NS + 2 * SCR + STASH) * int(TILE);
     extern __shared__ float4 smem4[];
     __shared__ uint64_t full_bar[PAIRS][NS], empty_bar[PAIRS][NS];
     float* gt = reinterpret_cast<float*>(smem4);                      // GTAB only
-    float* smem = reinterpret_cast<float*>(smem4) + (ROUNDS == 2 && !PREG ? (size_t(1) << N) : 0);
+    float* smem = reinterpret_cast<float*>(smem4) + (ROUNDS == 2 && !PREG ? (WHVI_PADDED ? size_t(SW) : (size_t(1) << N)) : 0);
     const int k = KT >= 0 ? KT : p.k;
     const uint32_t cmask = (1u << k) - 1u;
     // sample-minor CTA order (see layer_fwd.cu): shared x / target tiles are reused out of L2
@@ -136,11 +138,18 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     const int pair = (threadIdx.x % (T * PAIRS)) / T;
     const uint32_t tid = threadIdx.x % T;
     float* pair_smem = smem + size_t(pair) * PAIR_FLOATS;
+#if WHVI_PADDED
+    float* scratch = pair_smem + (SPT * NS) * TILE + (SCR * role) * SW;  // this role's transposition buffer(s)
+    float* scratch2 = scratch + (SINGLE ? 0 : SW);
+    float* stash_t2 = ALIAS ? pair_smem + (SPT * NS) * TILE : pair_smem + (SPT * NS) * TILE + 2 * SCR * SW;
+    float* stash_d3 = ALIAS ? pair_smem + (SPT * NS) * TILE + SCR * SW : stash_t2 + TILE / 2;
+#else
     float* scratch = pair_smem + (SPT * NS + SCR * role) * TILE;  // this role's transposition buffer(s)
     float* scratch2 = scratch + (SINGLE ? 0 : TILE);
     // half-stashes: X -> Y upper half of t2, Y -> X lower half of dt3
     float* stash_t2 = ALIAS ? pair_smem + (SPT * NS) * TILE : pair_smem + (SPT * NS + 2 * SCR) * TILE;
     float* stash_d3 = ALIAS ? pair_smem + (SPT * NS + SCR) * TILE : stash_t2 + TILE / 2;
+#endif
     const int bar_role = 1 + 3 * pair + role;
     const int bar_pair = 3 + 3 * pair;
     const float* __restrict__ gs = p.g + (int64_t(s) << k);
@@ -551,9 +560,11 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     constexpr int threads = (2 << (N - C)) * PAIRS;
     constexpr size_t tile = size_t(1) << N;
     constexpr bool gtab = ROUNDS == 2 && !PREG;
-    constexpr size_t smem_plain = bwd_smem_bytes(N, PAIRS, NS, SINGLE, ALIAS, gtab, 2);
-    constexpr size_t smem_tgt = bwd_smem_bytes(N, PAIRS, NS, SINGLE, ALIAS, gtab, 3);  // RESID with the target staged
-    const size_t smem = (c.target != nullptr && bwd_stage_target(N, PAIRS, NS, SINGLE, ALIAS, gtab, MINB)) ? smem_tgt : smem_plain;
+    constexpr size_t sw = scratch_words(N, C);
+    constexpr size_t smem_plain = bwd_smem_bytes(N, PAIRS, NS, SINGLE, ALIAS, gtab, 2, sw);
+    constexpr size_t smem_tgt = bwd_smem_bytes(N, PAIRS, NS, SINGLE, ALIAS, gtab, 3, sw);  // RESID with the target staged
+    static_assert(smem_plain <= 227 * 1024, "backward kernel shared memory");
+    const size_t smem = (c.target != nullptr && bwd_stage_target(N, PAIRS, NS, SINGLE, ALIAS, gtab, MINB, sw)) ? smem_tgt : smem_plain;
     const int64_t D = int64_t(1) << k;
     const int64_t tiles_per_sample = (c.B * D + int64_t(tile) - 1) / int64_t(tile);
     const Plan plan = make_plan_waves(c.S, tiles_per_sample, PAIRS, 148, 8, 8);
@@ -596,7 +607,11 @@ int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream)
     // 1.16 ms vs 1.08 ms -- too few warps and no room for register-resident parameters)
     if (k == 11) return launch_bwd_tma_cfg<11, 5, 11, 2, 1, 2, false, false, 2, 3>(c, k, stream);
     if (k == 12) return launch_bwd_tma_cfg<12, 5, 12, 1, 1, 2, false, false, 2, 3>(c, k, stream);
+#if WHVI_PADDED  // the padded scratch does not fit next to a stash tile of its own at D = 8192: alias the stash
+    if (k == 13) return launch_bwd_tma_cfg<13, 5, 13, 1, 1, 2, true, true, 0, 3>(c, k, stream);
+#else
     if (k == 13) return launch_bwd_tma_cfg<13, 5, 13, 1, 1, 2, true, false, 0, 3>(c, k, stream);
+#endif
     return fail(WHVI_E_SHAPE, "layer_bwd: D = %lld unsupported (4 <= D <= 8192)", (long long)D);
 }
 

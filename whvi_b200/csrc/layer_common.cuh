@@ -108,7 +108,11 @@ __device__ __forceinline__ uint32_t gtab_base(uint32_t tid, int k)
         constexpr View mid = view_mid(N, C);
         constexpr int b = mid.bit[C + j];
         constexpr uint32_t col = view_phys(mid, 1u << b);
+#if WHVI_PADDED
+        base += (((tid >> j) & 1u) && b < k) ? col : 0u;
+#else
         base ^= (((tid >> j) & 1u) && b < k) ? col : 0u;
+#endif
     });
     return base;
 }
@@ -120,8 +124,12 @@ __device__ __forceinline__ void gtab_for_each(const float* gt, uint32_t base, F&
         constexpr int j = decltype(j_)::value;
         constexpr View mid = view_mid(N, C);
         constexpr uint32_t pr = view_phys(mid, view_reg_logical(mid, 4 * j));
+#if WHVI_PADDED
+        f(j_, *reinterpret_cast<const float4*>(gt + (base + pr)));
+#else
         constexpr uint32_t lo = pr & 0x1Cu, hi = pr & ~0x1Cu;
         f(j_, *reinterpret_cast<const float4*>(gt + ((base ^ lo) + hi)));
+#endif
     });
 }
 

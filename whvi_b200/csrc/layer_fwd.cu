@@ -67,9 +67,10 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
     const int s = blockIdx.x % a.n_samples;
     const int cta_in_sample = blockIdx.x / a.n_samples;
     const float* __restrict__ gs = a.g + (int64_t(s) << k);
+    constexpr size_t SW = scratch_words(N, C);  // one transposition buffer / g table (== TILE unless WHVI_PADDED)
     float* gt = smem;  // ROUNDS == 2 only
-    float* bufA = smem + (ROUNDS == 2 ? TILE : 0) + size_t(group) * BUFS * TILE;
-    float* bufB = bufA + (BUFS == 2 ? TILE : 0);
+    float* bufA = smem + (ROUNDS == 2 ? SW : 0) + size_t(group) * BUFS * SW;
+    float* bufB = bufA + (BUFS == 2 ? SW : 0);
     const float relu_floor = a.relu_out ? 0.f : -INFINITY;
 
     const uint32_t off_f = tile_thread_offset<N, C, V_FIRST>(tid);
@@ -203,7 +204,8 @@ static int launch_fwd_cfg(const LayerFwdCall& c, int k, cudaStream_t stream)
     static unsigned char smem_ok[6][64] = {};
     constexpr int threads = (1 << (N - C)) * GROUPS;
     constexpr size_t tile = size_t(1) << N;
-    constexpr size_t smem = sizeof(float) * (tile * BUFS * GROUPS + (ROUNDS == 2 ? tile : 0));
+    constexpr size_t sw = scratch_words(N, C);
+    constexpr size_t smem = sizeof(float) * (sw * BUFS * GROUPS + (ROUNDS == 2 ? sw : 0));
     const int64_t D = int64_t(1) << k;
     const int64_t tiles_per_sample = (c.B * D + int64_t(tile) - 1) / int64_t(tile);
     // persistent CTAs: 2-view kernels amortise the g-table fill over >= 4 tiles per group, and

@@ -54,7 +54,9 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, 1) layer_loss_kernel(c
     constexpr int E = 1 << C;
     constexpr int64_t TILE = int64_t(1) << N;
     constexpr int SCR = SINGLE ? 1 : 2;
-    constexpr int PAIR_FLOATS = (2 * NS + 2 * SCR + NS) * int(TILE);  // stages, scratch, one full t2 stash per stage
+    constexpr int SW = int(scratch_words(N, C));  // one transposition buffer (== TILE unless WHVI_PADDED)
+    constexpr int PAIR_FLOATS = WHVI_PADDED ? (2 * NS + NS) * int(TILE) + 2 * SCR * SW
+                                            : (2 * NS + 2 * SCR + NS) * int(TILE);  // stages, scratch, one full t2 stash per stage
     static_assert(ROUNDS == 3 || rounds_needed(N, C, N) <= 2, "2-view kernel needs FIRST+MID to cover all bits");
     static_assert(rounds_needed(N, C, N) <= 3, "FIRST+MID+LAST must cover every tile bit");
     static_assert(ROUNDS == 3 || PREG > 0, "the 2-view loss kernel keeps g in registers");
@@ -99,9 +101,15 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, 1) layer_loss_kernel(c
     const int pair = (threadIdx.x % (T * PAIRS)) / T;
     const uint32_t tid = threadIdx.x % T;
     float* pair_smem = smem + size_t(pair) * PAIR_FLOATS;
+#if WHVI_PADDED
+    float* scratch = pair_smem + (2 * NS) * TILE + (SCR * role) * SW;
+    float* scratch2 = scratch + (SINGLE ? 0 : SW);
+    float* stash0 = pair_smem + (2 * NS) * TILE + 2 * SCR * SW;       // + st * TILE
+#else
     float* scratch = pair_smem + (2 * NS + SCR * role) * TILE;
     float* scratch2 = scratch + (SINGLE ? 0 : TILE);
     float* stash0 = pair_smem + (2 * NS + 2 * SCR) * TILE;       // + st * TILE
+#endif
     const int bar_role = 1 + 2 * pair + role;
     const float* __restrict__ gs = p.g + (int64_t(s) << k);
     const float relu_thr = p.relu_in ? 0.f : -INFINITY;
@@ -337,7 +345,7 @@ static int launch_loss_cfg(const LayerLossCall& c, int k, cudaStream_t stream)
     constexpr int T = 1 << (N - C);
     constexpr int threads = 2 * T * PAIRS;
     constexpr size_t tile = size_t(1) << N;
-    constexpr size_t smem = sizeof(float) * (2 * NS + (SINGLE ? 2 : 4) + NS) * tile * PAIRS;
+    constexpr size_t smem = sizeof(float) * ((2 * NS + NS) * tile + (SINGLE ? 2 : 4) * size_t(scratch_words(N, C))) * PAIRS;
     static_assert(smem <= 227 * 1024, "loss kernel shared memory");
     const int64_t D = int64_t(1) << k;
     const int64_t tiles_per_sample = (c.B * D + int64_t(tile) - 1) / int64_t(tile);

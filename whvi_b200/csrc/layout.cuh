@@ -29,9 +29,22 @@
 #define WHVI_HD inline
 #endif
 
+// WHVI_PADDED=1 (variant builds only: python -m whvi_b200.build --variant padded -DWHVI_PADDED=1):
+// the reader-owned transposition layout without the XOR swizzle -- thread tid' owns E + 4 words at
+// tid' * (E + 4), register r at word r.  Conflict-free on both sides like the swizzle
+// (tools/sim_layout.cpp proves it for every transposition in use) and every address is a thread
+// base plus a compile-time constant (no LOP3 per access), at 12.5% more scratch.  Not measured yet
+// (DESIGN.md section 9); the product library is always built with WHVI_PADDED=0.
+#ifndef WHVI_PADDED
+#define WHVI_PADDED 0
+#endif
+
 namespace whvi {
 
 constexpr int kMaxBits = 16;
+
+// words of one transposition buffer (or MID-order g table) of a 2^n tile, 2^c floats per thread
+constexpr uint32_t scratch_words(int n, int c) { return (1u << n) + (WHVI_PADDED ? (4u << (n - c)) : 0u); }
 
 struct View {
     int n;               // log2(tile elements)
@@ -154,8 +167,12 @@ constexpr uint32_t view_phys(const View& v, uint32_t idx)
         const uint32_t b = (idx >> v.bit[p]) & 1u;
         if (p < v.c) reg |= b << p; else tid |= b << (p - v.c);
     }
+#if WHVI_PADDED
+    return tid * ((1u << v.c) + 4u) + reg;
+#else
     const uint32_t slot = (reg >> 2) ^ swz_of_tid(v.c, tid);
     return (tid << v.c) + (slot << 2) + (reg & 3u);
+#endif
 }
 
 // view_phys is GF(2)-linear in idx, so phys(a ^ b) = phys(a) ^ phys(b); the writer uses
