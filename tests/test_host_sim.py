@@ -10,9 +10,13 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def test_layout_and_plan_simulator(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("flags", [[], ["-DWHVI_PADDED=1"]], ids=["xor-swizzle (product)", "padded (variant builds)"])
+def test_layout_and_plan_simulator(tmp_path, flags):
     exe = tmp_path / "sim_layout"
-    subprocess.run(["g++", "-O2", "-std=c++17", "-I", str(ROOT / "whvi_b200" / "csrc"), "-o", str(exe),
+    subprocess.run(["g++", "-O2", "-std=c++17", *flags, "-I", str(ROOT / "whvi_b200" / "csrc"), "-o", str(exe),
                     str(ROOT / "tools" / "sim_layout.cpp")], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     sys.stdout.write(out.stdout[-2000:])
