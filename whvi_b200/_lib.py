@@ -10,7 +10,12 @@ import ctypes
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libwhvi_b200.so"
+import os
+
+# WHVI_B200_LIB=/path/to/libwhvi_b200_NAME.so loads an A/B variant build (python -m whvi_b200.build
+# --variant NAME -D...) in place of the product library, so the whole test-suite and bench.py can be
+# run against it.  Same C ABI, still no fallback of any kind.
+LIB_PATH = Path(os.environ.get("WHVI_B200_LIB") or Path(__file__).resolve().parent / "libwhvi_b200.so")
 
 # name -> (restype, argtypes); kept in one place so tests can check that every symbol
 # the header declares is exported and bound.

@@ -1,4 +1,9 @@
 // Kernel (3): the fused WHVILinear backward (see layer_fwd.cu for the math and layout notes).
+// Variant builds: -DWHVI_PADDED_BWD=1 pads the transposition buffers of THIS translation unit only
+// (measured: the backward gains ~4%, the two-view forward loses; profiles/r01_bwd_notes.md item 14).
+#if defined(WHVI_PADDED_BWD) && WHVI_PADDED_BWD && !defined(WHVI_PADDED)
+#define WHVI_PADDED 1
+#endif
 #include "layer_common.cuh"
 
 namespace whvi {

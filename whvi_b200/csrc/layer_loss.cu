@@ -24,6 +24,11 @@
 // released by Y one tile ago, so it does not stall, and the copy still has a whole tile of lead
 // time.  (With 2 stages and the refill at the start of an iteration X waits for Y and the two
 // roles serialise: measured 2x slower.)
+// Variant builds: -DWHVI_PADDED_BWD=1 pads the transposition buffers of THIS translation unit only
+// (measured: the backward gains ~4%, the two-view forward loses; profiles/r01_bwd_notes.md item 14).
+#if defined(WHVI_PADDED_BWD) && WHVI_PADDED_BWD && !defined(WHVI_PADDED)
+#define WHVI_PADDED 1
+#endif
 #include "layer_common.cuh"
 
 namespace whvi {
