@@ -377,7 +377,7 @@ def run_ours(args):
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": WORKLOAD, "D": D, "B": B, "S": S_TOTAL, "layers": N_LAYERS,
                           "rows_counted": "S*B*layers per step", "parallelism": f"mc-sample-shard x{world}",
-                          "samples_per_launch": chunk, "l2": "inputs larger than L2 (2 GiB activations per launch)",
+                          "samples_per_launch": chunk, "l2": f"inputs larger than L2 ({chunk * B * D * 4 / 2**30:.0f} GiB activations per launch)",
                           "step": "fwd + MNLL + KL + bwd + grad all-reduce (N>1) + Adam",
                           "fusion": "ReLU folded into the layer kernels; last layer fwd+MNLL+bwd in one kernel"},
                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
