@@ -208,6 +208,19 @@ WHVI_API int whvi_mc_moments_strided_f32(const float* y, int64_t y_sample_stride
                                          const float* in_sum_y2, float* out_sum_y, float* out_sum_y2, int64_t S,
                                          int64_t n, whvi_stream_t stream);
 
+/*
+ * One Adam step over a flat fp32 parameter buffer (the optimizer.step() of the reference's training loop,
+ * src/networks.py:80-82, :92-94, which the reference runs as torch.optim.Adam: src/evaluation.py:15-27), in
+ * torch.optim.Adam's arithmetic (weight_decay = 0, amsgrad = False):
+ *   m += (1-beta1)(g-m);  v = beta2 v + (1-beta2) g^2;  p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps)
+ * with g = grad_scale * grad.  step_dev: device float[1] holding t >= 1 (the caller increments it before the
+ * call); lr_dev: device float[1] or NULL (then `lr` is used) -- device-resident so that a captured CUDA graph
+ * follows learning-rate schedules and step counts.  All four buffers have n elements; in place.
+ */
+WHVI_API int whvi_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                           const float* lr_dev, const float* step_dev, float beta1, float beta2, float eps,
+                           float grad_scale, whvi_stream_t stream);
+
 #define WHVI_KL_REFERENCE 0
 #define WHVI_KL_CONSISTENT 1
 WHVI_API int whvi_kl_f32(const float* mu, const float* rho, float lambda_, int64_t D, int mode, float* out_kl,

@@ -20,7 +20,15 @@
   only built on request (``python oracle/build.py --ref-cuda``) or by
   ``__graft_entry__.build()`` when the file is missing.
 
-Run ``python oracle/build.py`` to build the first two.
+* ``build_ref_py()`` byte-compiles the reference's own Python modules on the hot path
+  (``/root/reference/src/{utils,weights,layers,likelihoods,networks}.py`` and
+  ``src/fwht/{python,cuda}/fwht.py``) UNMODIFIED, from where they lie, into sourceless ``.pyc`` files
+  under ``oracle/_ref/refpy/src/`` (compiled output only -- no reference source text enters the repo
+  or ``oracle/_ref``).  ``oracle/ref_torch.reference_package()`` imports them there (with the
+  ``fwht_cuda`` extension stubbed), which is what ``bench.py --impl reference`` and the
+  ``cpu_baseline`` leg time on the GPU box: the reference's own layer code, not a restatement.
+
+Run ``python oracle/build.py`` to build the first three.
 """
 from __future__ import annotations
 
@@ -125,9 +133,37 @@ def build_ref_cuda(force: bool = False) -> Path | None:
     return REF_CUDA_SO
 
 
+REF_PY_DIR = REF_DIR / "refpy"
+REF_PY_SRC = Path("/root/reference/src")
+REF_PY_MODULES = ["utils", "weights", "layers", "likelihoods", "networks", "fwht/python/fwht", "fwht/cuda/fwht",
+                  "fwht/python/__init__", "fwht/cuda/__init__"]
+
+
+def build_ref_py(force: bool = False) -> Path | None:
+    """Byte-compile the unmodified reference modules into oracle/_ref/refpy/src/**.pyc (sourceless import)."""
+    import py_compile
+    marker = REF_PY_DIR / "src" / "weights.pyc"
+    if not REF_PY_SRC.exists():
+        return REF_PY_DIR if marker.exists() else None
+    if not force and _newer(marker, *(REF_PY_SRC / f"{m}.py" for m in REF_PY_MODULES)):
+        return REF_PY_DIR
+    for m in REF_PY_MODULES:
+        src = REF_PY_SRC / f"{m}.py"
+        if not src.exists():
+            continue
+        out = REF_PY_DIR / "src" / f"{m}.pyc"
+        out.parent.mkdir(parents=True, exist_ok=True)
+        # dfile: the path recorded in the code object (tracebacks) -- the reference's own path
+        # unchecked-hash pyc: validity does not depend on a source file (there is none on the GPU box)
+        py_compile.compile(str(src), cfile=str(out), dfile=f"reference/src/{m}.py", doraise=True,
+                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+    return REF_PY_DIR
+
+
 def main() -> int:
     print("oracle:", build_oracle(force="--force" in sys.argv))
     print("reference fwht_cpp:", build_ref(force="--force" in sys.argv))
+    print("reference python modules (bytecode):", build_ref_py(force="--force" in sys.argv))
     if "--ref-cuda" in sys.argv:
         print("reference fwht_cuda:", build_ref_cuda(force="--force" in sys.argv))
     return 0

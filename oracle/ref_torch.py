@@ -107,3 +107,40 @@ def fwht_cuda_module():
         return fwht_cuda
     except Exception:
         return None
+
+
+def reference_package():
+    """The reference's OWN layer code (oracle/_ref/refpy: its modules byte-compiled unmodified by
+    oracle/build.py:build_ref_py, importable without sources) or None when it did not travel.
+    ``fwht_cuda`` -- imported unconditionally by src/weights.py:8 even on CPU -- is stubbed
+    exactly as tests/golden/make_golden.py does.  Returns the imported ``src.layers`` module."""
+    import importlib
+    import types
+    ref_dir = Path(__file__).resolve().parent / "_ref" / "refpy"
+    if not (ref_dir / "src" / "weights.pyc").exists():
+        return None
+    if str(ref_dir) not in sys.path:
+        sys.path.insert(0, str(ref_dir))
+    sys.modules.setdefault("fwht_cuda", types.ModuleType("fwht_cuda"))
+    try:
+        return importlib.import_module("src.layers")
+    except Exception:
+        return None
+
+
+def reference_layer_fwd_bwd_seconds(D: int, B: int, n_samples: int = 1, seed: int = 0):
+    """Wall time of n_samples forward+backward passes of the reference's own ``WHVILinear(D, D)`` on B rows
+    (its CPU path as written: src/weights.py:34-41, :66-93), all host threads; None if the package is absent."""
+    import time
+    layers = reference_package()
+    if layers is None:
+        return None
+    torch.manual_seed(seed)
+    layer = layers.WHVILinear(D, D)
+    h = torch.randn(B, D, requires_grad=True)
+    dy = torch.randn(B, D)
+    t0 = time.perf_counter()
+    for _ in range(n_samples):
+        y = layer(h)          # one eps draw per call = one MC sample (src/weights.py:92)
+        y.backward(dy)
+    return time.perf_counter() - t0

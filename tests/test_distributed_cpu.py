@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from whvi_b200.distributed import FlatGradAllReduce, reduce_predictive_moments, shard_rows, shard_samples
+from whvi_b200.distributed import FlatGradAllReduce, rank_loss, reduce_predictive_moments, shard_rows, shard_samples
+from whvi_b200.optim import FlatParams
 
 
 def test_shard_samples_partition():
@@ -59,6 +60,22 @@ def _worker(rank, world, port, out):
         mean, var = reduce_predictive_moments(ys.sum(0), (ys ** 2).sum(0), n_local)
         ok = ok and torch.allclose(mean, noise.mean(0), atol=1e-6)
         ok = ok and torch.allclose(var, noise.var(0, unbiased=False), atol=1e-5)
+        # uneven shards (S = 7 over 2 ranks) with rank_loss, gradients exchanged through FlatParams (views of one
+        # buffer, a single all-reduce, no copies): still the single-process gradient
+        S7 = 7
+        first7, n7 = shard_samples(S7, rank, world)
+        net.zero_grad(set_to_none=True)
+        flat = FlatParams(net.parameters())
+        kl = sum((p ** 2).sum() for p in net.parameters())
+        mnll7 = ((net(x).unsqueeze(0) + noise[first7:first7 + n7]) ** 2).mean()
+        rank_loss(mnll7, kl, n7, S7, world).backward()
+        ok = ok and flat.attached()
+        flat.all_reduce()
+        got = [p.grad.clone() for p in net.parameters()]
+        flat.zero_grad()
+        ok = ok and flat.attached() and float(flat.grad.abs().sum()) == 0.0
+        (((net(x).unsqueeze(0) + noise[:S7]) ** 2).mean() + sum((p ** 2).sum() for p in net.parameters())).backward()
+        ok = ok and all(torch.allclose(g, p.grad, atol=1e-6) for g, p in zip(got, net.parameters()))
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

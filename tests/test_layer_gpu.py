@@ -345,15 +345,28 @@ def test_loss_layer_vs_oracle(S, B, D, bias, shared):
         assert rel_err(db.cpu().numpy(), rdb) < TOL
 
 
-def test_deferred_scale_must_be_consumed():
-    """The fused loss layer may hand out dx for a unit coefficient only to a WHVI layer backward;
-    if nobody takes the pending scale the next network pass raises instead of training on wrong grads."""
+def test_deferred_scale_rides_on_the_graph():
+    """The fused loss layer hands its producer a dx for a UNIT loss coefficient; the coefficient travels in a
+    DeferredScale shared by the two autograd nodes, so a hook that copies the gradient tensor in between (the
+    failure mode of a data_ptr-keyed side table) changes nothing, and without a holder dx is scaled in place."""
     from whvi_b200 import functional as F
     S, B, D = 2, 4, 128
     x, g, s1, s2, _, _ = make_case(S, B, D, 5)
-    xt = t(x).requires_grad_()
-    sq = F.whvi_layer_loss(xt, t(g), t(s1), t(s2), None, t(np.zeros((B, D))), relu_in=False, defer_dx_scale=True)
-    (0.5 * sq).backward()          # xt is a leaf: the unit-coefficient dx lands in .grad, scale still pending
-    with pytest.raises(RuntimeError, match="never consumed"):
-        F.check_no_pending_scale()
-    F.check_no_pending_scale()     # cleared by the failure
+    x2, g2, s1b, s2b, _, _ = make_case(S, B, D, 6)
+    tgt = t(np.zeros((B, D)))
+
+    def run(shared_holder, hook):
+        xt, s1t = t(x).requires_grad_(), t(s1).requires_grad_()
+        holder = F.DeferredScale() if shared_holder else None
+        h = F.whvi_layer(xt, t(g), s1t, t(s2), None, True, False, holder)
+        if hook:
+            h.register_hook(lambda gr: gr.clone())     # the producer sees a COPY of the loss layer's dx
+        sq = F.whvi_layer_loss(h, t(g2), t(s1b), t(s2b), None, tgt, relu_in=True, dx_scale_to=holder)
+        (0.37 * sq).backward()
+        assert holder is None or holder.value is None  # consumed
+        return xt.grad.cpu().numpy(), s1t.grad.cpu().numpy()
+
+    base = run(False, False)
+    for shared, hook in ((True, False), (True, True), (False, True)):
+        got = run(shared, hook)
+        assert rel_err(got[0], base[0]) < 1e-6 and rel_err(got[1], base[1]) < 1e-6

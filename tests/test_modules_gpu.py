@@ -133,7 +133,8 @@ def oracle_layer(layer, x, eps_per_block):
 
 
 @pytest.mark.parametrize("n_in,n_out,bias", [(16, 16, False), (128, 128, True), (3, 16, False), (13, 128, True),
-                                             (128, 1, False), (1, 8, True), (20, 50, False), (1024, 1024, False)])
+                                             (128, 1, False), (1, 8, True), (20, 50, False), (1024, 1024, False),
+                                             (2, 2, True), (2, 5, False), (1, 1, False), (2, 1, False)])
 @pytest.mark.parametrize("shared", [True, False])
 def test_paper_semantics_vs_oracle(n_in, n_out, bias, shared):
     torch.manual_seed(n_in * 1000 + n_out)
@@ -355,3 +356,41 @@ def test_three_training_steps_match_the_reference(golden):
     for name, p in model.named_parameters():
         diff = float(np.max(np.abs(p.detach().cpu().numpy().astype(np.float64) - g[f"final.{name}"])))
         assert diff < 1e-3 * change, (name, diff, change)   # 1e-4 per gradient, three accumulated steps
+
+
+def test_square_blocks_narrower_than_a_float4():
+    """D = 1, 2 blocks (WHVILinear(2, 2), stacked layers with 2 inputs) run on the width-4 kernels
+    through zero padding; values AND all gradients equal the width-D layer's (fp64 oracle)."""
+    from oracle import oracle as O
+    from whvi_b200 import functional as F
+    for D in (1, 2):
+        rng = np.random.default_rng(40 + D)
+        S, B = 3, 5
+        x, g, dy = rng.standard_normal((S, B, D)), rng.standard_normal((S, D)), rng.standard_normal((S, B, D))
+        s1, s2, bias = rng.standard_normal(D), rng.standard_normal(D), rng.standard_normal(D)
+        xt, gt, s1t, s2t, bt = (t(v).requires_grad_() for v in (x, g, s1, s2, bias))
+        y = F.whvi_layer(xt, gt, s1t, s2t, bt)
+        assert y.shape == (S, B, D)
+        assert rel_err(y.detach().cpu().numpy(), O.layer_fwd(x, g, s1, s2, bias)) < TOL
+        (y * t(dy)).sum().backward()
+        rdx, rdg, rds1, rds2, rdb = O.layer_bwd(x, dy, g, s1, s2, want_dbias=True)
+        for got, ref in ((xt.grad, rdx), (gt.grad, rdg), (s1t.grad, rds1), (s2t.grad, rds2), (bt.grad, rdb)):
+            assert rel_err(got.cpu().numpy(), ref) < TOL
+    net = W.WHVIRegression([W.WHVILinear(2, 2), torch.nn.ReLU(), W.WHVILinear(2, 1)], train_samples=3).to(dev()).train()
+    xb = torch.randn(7, 2, device=dev())
+    net.loss(xb, xb[:, :1], n=7).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+def test_device_prefetcher_short_last_batch():
+    """a DataLoader's shorter last batch must come out with its own length and values (it used to
+    raise, or to broadcast a 1-row batch over the whole buffer)."""
+    from whvi_b200.utils import DevicePrefetcher
+    sizes = [8, 8, 8, 3, 1, 8]
+    host = [(torch.randn(n, 5).pin_memory(), torch.randn(n, 1).pin_memory()) for n in sizes]
+    seen = 0
+    for (hx, hy), (dx, dy) in zip(host, DevicePrefetcher(iter(host), dev())):
+        assert dx.shape == hx.shape and dy.shape == hy.shape
+        assert torch.equal(dx.cpu(), hx) and torch.equal(dy.cpu(), hy)
+        seen += 1
+    assert seen == len(sizes)

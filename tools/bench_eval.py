@@ -58,7 +58,7 @@ def main():
     comm = torch.cuda.Stream(device=dev)
     peer = None
     if world > 1 and args.exchange == "peer":
-        from whvi_b200.distributed import PeerMomentExchange
+        from tools.peer_moments import PeerMomentExchange
         peer = PeerMomentExchange(cb, D, dev)
     checksum = torch.zeros((), device=dev)
 

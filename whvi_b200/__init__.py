@@ -4,7 +4,8 @@ from .fwht import FWHT, FWHTFunction, fwht_  # noqa: F401
 from .layers import WHVI, WHVILinear  # noqa: F401
 from .likelihoods import GaussianLikelihood, Likelihood  # noqa: F401
 from .networks import WHVINetwork, WHVIRegression  # noqa: F401
+from .optim import FlatAdam, FlatParams  # noqa: F401
 from .weights import WHVIColumnMatrix, WHVISquarePow2Matrix, WHVIStackedMatrix  # noqa: F401
 
 __all__ = ["FWHT", "FWHTFunction", "fwht_", "WHVI", "WHVILinear", "GaussianLikelihood", "Likelihood",
-           "WHVINetwork", "WHVIRegression", "WHVIColumnMatrix", "WHVISquarePow2Matrix", "WHVIStackedMatrix"]
+           "WHVINetwork", "WHVIRegression", "FlatAdam", "FlatParams", "WHVIColumnMatrix", "WHVISquarePow2Matrix", "WHVIStackedMatrix"]

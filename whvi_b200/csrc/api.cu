@@ -225,6 +225,19 @@ int whvi_kl_f32(const float* mu, const float* rho, float lambda_, int64_t D, int
     return launch_kl(mu, rho, lambda_, D, mode, out_kl, dmu, drho, grad_scale, accumulate, static_cast<cudaStream_t>(stream));
 }
 
+int whvi_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  const float* lr_dev, const float* step_dev, float beta1, float beta2, float eps, float grad_scale,
+                  whvi_stream_t stream)
+{
+    if (n < 0) return fail(WHVI_E_SHAPE, "adam: n=%lld", (long long)n);
+    if (n == 0) return WHVI_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !step_dev) return fail(WHVI_E_NULL, "adam: null pointer");
+    if (!(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f))
+        return fail(WHVI_E_MODE, "adam: betas must be in [0, 1) and eps >= 0");
+    return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, lr_dev, step_dev, beta1, beta2, eps, grad_scale,
+                       static_cast<cudaStream_t>(stream));
+}
+
 int whvi_mc_moments_f32(const float* y, float* sum_y, float* sum_y2, int64_t S, int64_t n, int accumulate,
                         whvi_stream_t stream)
 {

@@ -92,6 +92,8 @@ int launch_reparam_diag_bwd(const float* rho, const float* eps, const float* dg,
                             int64_t D, int accumulate, cudaStream_t stream);
 int launch_mc_moments(const float* y, int64_t y_sample_stride, const float* in_y, const float* in_y2, float* out_y, float* out_y2,
                       int64_t S, int64_t n, cudaStream_t stream);
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, const float* step,
+                float b1, float b2, float eps, float grad_scale, cudaStream_t stream);
 int launch_kl(const float* mu, const float* rho, float lambda_, int64_t D, int mode, float* out, float* dmu, float* drho,
               float grad_scale, int accumulate, cudaStream_t stream);
 

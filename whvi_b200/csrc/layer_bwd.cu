@@ -1,10 +1,15 @@
 // Kernel (3): the fused WHVILinear backward (see layer_fwd.cu for the math and layout notes).
-// Variant builds: -DWHVI_PADDED_BWD=1 pads the transposition buffers of THIS translation unit only
-// (measured: the backward gains ~4%, the two-view forward loses; profiles/r01_bwd_notes.md item 14).
-#if defined(WHVI_PADDED_BWD) && WHVI_PADDED_BWD && !defined(WHVI_PADDED)
+// The transposition buffers of THIS translation unit use the padded (XOR-free) layout (WHVI_PADDED_BWD, default 1;
+// measured: the backward gains ~4% at D = 1024...8192 with bit-identical outputs, the two-view forward does not,
+// profiles/r01_bwd_notes.md item 14, profiles/r02_ab_padbwd.txt); -DWHVI_PADDED_BWD=0 builds the swizzled variant.
+#ifndef WHVI_PADDED_BWD
+#define WHVI_PADDED_BWD 1   // product default since round 2: bit-identical outputs, -4% (profiles/r02_ab_padbwd.txt)
+#endif
+#if WHVI_PADDED_BWD && !defined(WHVI_PADDED)
 #define WHVI_PADDED 1
 #endif
 #include "layer_common.cuh"
+#include "tmem.cuh"
 
 namespace whvi {
 
@@ -448,6 +453,405 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     }
 }
 
+// ------------------------------------------------------------------ backward, TMEM edition (round 2)
+// D >= 2048.  The three-view kernel above is bound by the L1/shared-memory data pipe (77% of its peak at 48% of
+// the HBM roofline, profiles/r01_bwd_notes.md item 7): ~3260 wavefronts per 4096-element tile pair, and because
+// its single tile pair per SM runs all eight warps in lock-step, shared-memory phases and FP32 phases add up
+// instead of overlapping.  Two views (64 floats per thread, ONE transposition per transform) need 1024 + 512
+// (raw tiles) + 128 (dx) = 1664 wavefronts, but the round-1 attempt at it died of register pressure: 64 floats of
+// stream + three 64-float running sums + three 64-float parameter vectors per thread.  Here everything that only
+// its owner touches lives in TENSOR MEMORY instead (tmem.cuh: tcgen05.ld/st, 4-6x the bandwidth of shared
+// memory and off its data path):
+//   * the running sums ds1, ds2, dg (and dbias): load 32 columns, FFMA, store, once per tile;
+//   * g (middle-layout order) and the Y role's s2;
+//   * the X <-> Y exchange of half-streams (the "stash"): the X thread and the Y thread with the same tid sit in
+//     warps w and w + 4, i.e. in the same TMEM lane, so one writes columns the other reads -- no shared memory.
+// That leaves stream + one parameter vector in registers (no spills at 255), makes room for TWO tile pairs per
+// SM at D <= 4096 (shared memory: 2 stages x (x, dy) + one in-place transposition buffer per role), and the two
+// pairs are independent, so one pair's shared-memory phase overlaps the other's butterflies.
+// TMEM columns per lane (E = 64 floats per thread, H = E / 2), shared by the X/Y thread pair of that lane:
+//   [0,E) g | [E,2E) ds1 (X) | [2E,2E+H) dg lower half (X) | [2E+H,3E) dg upper half (Y) | [3E,4E) ds2 (Y) |
+//   [4E,5E) s2 (Y) | [5E,5E+H) t2 upper half X->Y | [5E+H,6E) dt3 lower half Y->X | [6E,7E) dbias (X)
+// Everything else (bulk-copy staging ring, roles, workspace layout, second-stage reduction) is the kernel above.
+template <int N, int C, int KT, int ROUNDS, bool WANT_DBIAS, bool RESID>
+__global__ void __launch_bounds__(256, 1) layer_bwd_tm_kernel(const BwdArgs p)
+{
+    constexpr int T = 1 << (N - C);
+    constexpr int E = 1 << C;
+    constexpr int H = E / 2;
+    constexpr int PAIRS = 128 / T;
+    constexpr int NS = 2;
+    constexpr int64_t TILE = int64_t(1) << N;
+    constexpr int SW = int(scratch_words(N, C));
+    constexpr int PAIR_FLOATS = 2 * NS * int(TILE) + 2 * SW;
+    static_assert(E == 64 && PAIRS >= 1 && PAIRS * T == 128, "layer_bwd_tm_kernel: 64 floats per thread, 4 warps per role");
+    static_assert(ROUNDS == 3 || rounds_needed(N, C, N) <= 2, "2-view kernel needs FIRST+MID to cover all bits");
+    static_assert(rounds_needed(N, C, N) <= 3, "FIRST+MID+LAST must cover every tile bit");
+    constexpr uint32_t COL_G = 0, COL_A1 = E, COL_AGX = 2 * E, COL_AGY = 2 * E + H, COL_A2 = 3 * E, COL_S2 = 4 * E,
+                       COL_ST2 = 5 * E, COL_SD3 = 5 * E + H, COL_AB = 6 * E;
+    extern __shared__ float4 smem4[];
+    __shared__ uint64_t full_bar[PAIRS][NS], empty_bar[PAIRS][NS];
+    __shared__ uint32_t tmem_base_smem;
+    float* smem = reinterpret_cast<float*>(smem4);
+    const int k = KT >= 0 ? KT : p.k;
+    const uint32_t cmask = (1u << k) - 1u;
+    const int s = blockIdx.x % p.n_samples;   // sample-minor CTA order
+    const int cta_in_sample = blockIdx.x / p.n_samples;
+    const float* __restrict__ xbase = p.x + int64_t(s) * p.x_sample_stride;
+    const float* __restrict__ dybase = p.dy + int64_t(s) * p.sample_elems;
+
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < PAIRS; ++q)
+            for (int st = 0; st < NS; ++st) {
+                mbar_init(&full_bar[q][st], 1);
+                mbar_init(&empty_bar[q][st], 2 * T);
+            }
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 32) tm_alloc(&tmem_base_smem, 512);
+    tm_fence_before();
+    __syncthreads();
+    tm_fence_after();
+    const uint32_t tm = tm_lane_base(tmem_base_smem);
+
+    auto tile_of = [&](int it, int pr) -> int64_t {
+        return ((int64_t(cta_in_sample) * p.iters_per_group + it) * PAIRS + pr) * TILE;
+    };
+    auto issue_tile = [&](int it, int pr) {
+        if (it >= p.iters_per_group) return;
+        const int64_t e0 = tile_of(it, pr);
+        if (e0 >= p.sample_elems) return;
+        const int st = it % NS;
+        if (it >= NS) mbar_wait(&empty_bar[pr][st], ((it / NS) & 1) ^ 1);
+        const int64_t left = p.sample_elems - e0;
+        const uint32_t bytes = static_cast<uint32_t>((left < TILE ? left : TILE) * sizeof(float));
+        float* stage = smem + size_t(pr) * PAIR_FLOATS + size_t(st) * 2 * TILE;
+        mbar_arrive_expect_tx(&full_bar[pr][st], 2 * bytes);
+        bulk_g2s(stage, xbase + e0, bytes, &full_bar[pr][st]);
+        bulk_g2s(stage + TILE, dybase + e0, bytes, &full_bar[pr][st]);
+    };
+
+    const int role = threadIdx.x / 128;               // 0 = X (warps 0..3), 1 = Y (warps 4..7): same TMEM quadrant per tid
+    const int pair = (threadIdx.x % 128) / T;
+    const uint32_t tid = threadIdx.x % T;
+    float* pair_smem = smem + size_t(pair) * PAIR_FLOATS;
+    float* scratch = pair_smem + 2 * NS * TILE + role * SW;   // this role's in-place transposition buffer
+    const int bar_role = 1 + 3 * pair + role;
+    const int bar_pair = 3 + 3 * pair;
+    const float* __restrict__ gs = p.g + (int64_t(s) << k);
+    float coef = 1.f;
+    if constexpr (RESID) coef = __ldg(p.coef);
+    const float dysc = p.dy_scale != nullptr ? __ldg(p.dy_scale) : 1.f;
+    const float relu_thr = p.relu_in ? 0.f : -INFINITY;
+
+    const uint32_t off_f = tile_thread_offset<N, C, V_FIRST>(tid);
+    const uint32_t off_l = tile_thread_offset<N, C, V_LAST>(tid);
+    const uint32_t wb_fm = transpose_writer_base<N, C, V_FIRST, V_MID>(tid);
+    const uint32_t wb_ml = transpose_writer_base<N, C, V_MID, V_LAST>(tid);
+    const uint32_t wb_lm = transpose_writer_base<N, C, V_LAST, V_MID2>(tid);
+    const uint32_t wb_mf = ROUNDS == 3 ? transpose_writer_base<N, C, V_MID2, V_FIRST>(tid)
+                                       : transpose_writer_base<N, C, V_MID, V_FIRST>(tid);
+    const uint32_t mid_logical = view_tid_logical(view_mid(N, C), tid);
+
+    auto to_mid = [&](float (&v)[E]) {
+        if constexpr (ROUNDS == 3) {
+            transform_in<N, C, KT, T, true>(v, scratch, scratch, tid, bar_role, k, wb_fm, wb_ml);
+        } else {
+            bfly_round<N, C, KT, SEQ2_IN, 0>(v, k);
+            role_sync<T>(bar_role);   // earlier reads of the buffer are done
+            transpose_write<N, C, V_FIRST, V_MID>(v, scratch, wb_fm);
+            role_sync<T>(bar_role);
+            transpose_read<C>(v, scratch, tid);
+            bfly_round<N, C, KT, SEQ2_IN, 1>(v, k);
+        }
+    };
+    auto from_mid = [&](float (&v)[E]) {
+        if constexpr (ROUNDS == 3) {
+            transform_out<N, C, KT, T, true>(v, scratch, scratch, tid, bar_role, k, wb_lm, wb_mf);
+        } else {
+            bfly_round<N, C, KT, SEQ2_OUT, 0>(v, k);
+            role_sync<T>(bar_role);
+            transpose_write<N, C, V_MID, V_FIRST>(v, scratch, wb_mf);
+            role_sync<T>(bar_role);
+            transpose_read<C>(v, scratch, tid);
+            bfly_round<N, C, KT, SEQ2_OUT, 1>(v, k);
+        }
+    };
+    // v *= g: g comes from TMEM in the middle layout's register order, 32 columns at a time
+    auto apply_g = [&](float (&v)[E]) {
+#pragma unroll
+        for (int c = 0; c < E; c += 32) {
+            float gq[32];
+            tm_ld32(gq, tm + COL_G + c);
+            tm_wait_ld();
+#pragma unroll
+            for (int m = 0; m < 8; ++m) scale4(v + c + 4 * m, make_float4(gq[4 * m], gq[4 * m + 1], gq[4 * m + 2], gq[4 * m + 3]));
+        }
+    };
+    auto store_dg_half = [&](const float* acc, int half_is_upper, float* dst) {
+        if constexpr (ROUNDS == 3) {
+            for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t off, uint32_t) {
+                constexpr int m = decltype(m_)::value;
+                constexpr int mh = m % (E / 8);
+                if ((m >= E / 8) == (half_is_upper != 0))
+                    *reinterpret_cast<float4*>(dst + off) = make_float4(acc[4 * mh], acc[4 * mh + 1], acc[4 * mh + 2], acc[4 * mh + 3]);
+            });
+        } else {
+            static_for<0, E / 2>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                constexpr uint32_t rl_lo = view_reg_logical(view_mid(N, C), r);
+                constexpr uint32_t rl_hi = view_reg_logical(view_mid(N, C), r + E / 2);
+                dst[mid_logical | (half_is_upper ? rl_hi : rl_lo)] = acc[r];
+            });
+        }
+    };
+    float* __restrict__ slab = p.ws + (((int64_t(s) * p.ctas_per_sample + cta_in_sample) * PAIRS + pair) * 4) * TILE;
+
+    auto zero_tail = [&](float* stage_x, int64_t left) {
+        if (left < TILE) {
+            static_for<0, E / 4>([&](auto m_) {
+                constexpr int m = decltype(m_)::value;
+                const uint32_t off = off_f + tile_reg_offset<N, C, V_FIRST>(m);
+                if (off >= left) {
+                    *reinterpret_cast<float4*>(stage_x + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(stage_x + TILE + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            });
+        }
+    };
+    auto raw4 = [&](const float* stage_tile, uint32_t off) -> float4 {
+        return *reinterpret_cast<const float4*>(stage_tile + off);
+    };
+    // RESID: dy = coef * (saved output - target); the target (shared by all samples, L2-resident) is read from
+    // global memory, zero beyond the valid part of a partial tile
+    auto to_dy = [&](float4 q, const float* tgt, uint32_t off, int64_t left) -> float4 {
+        if constexpr (RESID) {
+            float4 tg = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (left >= TILE || off < left) tg = ldg4(tgt + off);
+            q = make_float4(coef * (q.x - tg.x), coef * (q.y - tg.y), coef * (q.z - tg.z), coef * (q.w - tg.w));
+        } else {
+            q = make_float4(dysc * q.x, dysc * q.y, dysc * q.z, dysc * q.w);
+        }
+        return q;
+    };
+
+    // ---- TMEM initialisation: running sums = 0; g (X writes it, both roles read it); s2 (Y)
+    {
+        float z[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) z[i] = 0.f;
+        if (role == 0) {
+            tm_st32(z, tm + COL_A1), tm_st32(z, tm + COL_A1 + 32), tm_st32(z, tm + COL_AGX);
+            if constexpr (WANT_DBIAS) tm_st32(z, tm + COL_AB), tm_st32(z, tm + COL_AB + 32);
+            float gr[E];
+            if constexpr (ROUNDS == 3) {
+                for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+                    constexpr int m = decltype(m_)::value;
+                    const float4 w = ldg4(gs + coord);
+                    gr[4 * m] = w.x, gr[4 * m + 1] = w.y, gr[4 * m + 2] = w.z, gr[4 * m + 3] = w.w;
+                });
+            } else {
+                static_for<0, E>([&](auto r_) {
+                    constexpr int r = decltype(r_)::value;
+                    constexpr uint32_t rl = view_reg_logical(view_mid(N, C), r);
+                    gr[r] = __ldg(gs + ((mid_logical | rl) & cmask));
+                });
+            }
+            tm_st32(gr, tm + COL_G), tm_st32(gr + 32, tm + COL_G + 32);
+        } else {
+            tm_st32(z, tm + COL_A2), tm_st32(z, tm + COL_A2 + 32), tm_st32(z, tm + COL_AGY);
+            float sr[E];
+            for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+                constexpr int m = decltype(m_)::value;
+                const float4 w = ldg4(p.s2 + coord);
+                sr[4 * m] = w.x, sr[4 * m + 1] = w.y, sr[4 * m + 2] = w.z, sr[4 * m + 3] = w.w;
+            });
+            tm_st32(sr, tm + COL_S2), tm_st32(sr + 32, tm + COL_S2 + 32);
+        }
+        tm_wait_st();
+        tm_fence_before();
+        __syncthreads();
+        tm_fence_after();
+    }
+
+    // ONE instruction stream for both roles (the two transforms, the g multiply, the running-sum updates are the same
+    // code on different data; only the half-stream exchange and the dx store are role-specific): the fully unrolled
+    // 64-float transforms are ~8 KB of SASS each, and with a private copy per role the hot loop (53 KB) thrashed the
+    // 32 KB instruction cache -- "no instruction" was the top stall reason (22% of samples, profiles/r02_bwd_notes.md).
+    //   X: v = s2 * x  -> t2  -> t4,   end product ds1 += dy * t4 (dbias += dy)
+    //   Y: v = s1 * dy -> dt3 -> dt1,  end product ds2 += x * dt1, dx = s2 * dt1
+    float pr[E];   // this role's input-side parameter vector: X s2, Y s1 (FIRST-view order)
+    {
+        const float* __restrict__ pv = role ? p.s1 : p.s2;
+        for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t, uint32_t coord) {
+            constexpr int m = decltype(m_)::value;
+            const float4 w = ldg4(pv + coord);
+            pr[4 * m] = w.x, pr[4 * m + 1] = w.y, pr[4 * m + 2] = w.z, pr[4 * m + 3] = w.w;
+        });
+    }
+    const uint32_t col_acc = role ? COL_A2 : COL_A1;          // this role's end-product running sum
+    // the upstream gradient is dy_scale * dy: folded into Y's s1 once (s1 * dy_scale) and into X's sums at the end
+    // (ds1, dbias are linear in dy), not applied to every element of every tile
+    if constexpr (!RESID) {
+        if (role) {
+#pragma unroll
+            for (int i = 0; i < E; ++i) pr[i] *= dysc;
+        }
+    }
+    if (role == 0 && tid == 0)
+        for (int i = 0; i < NS - 1; ++i) issue_tile(i, pair);
+#pragma unroll 1
+    for (int it = 0; it < p.iters_per_group; ++it) {
+        const int64_t e0 = tile_of(it, pair);
+        if (e0 >= p.sample_elems) break;
+        const int64_t left = p.sample_elems - e0;
+        const int st = it % NS;
+        float* stage_x = pair_smem + size_t(st) * 2 * TILE;
+        const float* stage_dy = stage_x + TILE;
+        const float* tgt = RESID ? p.target + e0 : nullptr;
+        const float* src_in = role ? stage_dy : stage_x;       // the stream this role transforms
+        const float* src_end = role ? stage_x : stage_dy;      // the other raw tile, for the end product
+        if (role == 0 && tid == 0) issue_tile(it + NS - 1, pair);
+        mbar_wait(&full_bar[pair][st], (it / NS) & 1);
+        zero_tail(stage_x, left);
+        float v[E];
+        if constexpr (RESID) {
+            if (role) {
+                for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t) {
+                    constexpr int m = decltype(m_)::value;
+                    mul4(v + 4 * m, to_dy(raw4(stage_dy, off), tgt, off, left), make_float4(pr[4 * m], pr[4 * m + 1], pr[4 * m + 2], pr[4 * m + 3]));
+                });
+            } else {
+                for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t) {
+                    constexpr int m = decltype(m_)::value;
+                    mul4(v + 4 * m, raw4(stage_x, off), make_float4(pr[4 * m], pr[4 * m + 1], pr[4 * m + 2], pr[4 * m + 3]));
+                });
+            }
+        } else {
+            for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t) {
+                constexpr int m = decltype(m_)::value;
+                mul4(v + 4 * m, raw4(src_in, off), make_float4(pr[4 * m], pr[4 * m + 1], pr[4 * m + 2], pr[4 * m + 3]));
+            });
+        }
+        to_mid(v);  // X: t2, Y: dt3 (middle layout)
+        // half-stream exchange through TMEM: X publishes the upper half of t2 and accumulates the lower half of dg,
+        // Y publishes the lower half of dt3 and accumulates the upper half
+        if (role == 0) tm_st32(v + H, tm + COL_ST2); else tm_st32(v, tm + COL_SD3);
+        tm_wait_st();
+        tm_fence_before();
+        bar_wait<2 * T>(bar_pair);
+        tm_fence_after();
+        {
+            float oth[H], ag[H];
+            tm_ld32(oth, tm + (role ? COL_ST2 : COL_SD3));
+            tm_ld32(ag, tm + (role ? COL_AGY : COL_AGX));
+            tm_wait_ld();
+            if (role == 0) {
+#pragma unroll
+                for (int jj = 0; jj < H / 4; ++jj)
+                    fma4(ag + 4 * jj, make_float4(oth[4 * jj], oth[4 * jj + 1], oth[4 * jj + 2], oth[4 * jj + 3]), v + 4 * jj);
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < H / 4; ++jj)
+                    fma4(ag + 4 * jj, make_float4(oth[4 * jj], oth[4 * jj + 1], oth[4 * jj + 2], oth[4 * jj + 3]), v + H + 4 * jj);
+            }
+            tm_st32(ag, tm + (role ? COL_AGY : COL_AGX));
+        }
+        tm_fence_before();
+        bar_wait<2 * T>(bar_pair);  // both half-stashes consumed
+        tm_fence_after();
+        apply_g(v);
+        from_mid(v);  // X: t4, Y: dt1 (FIRST layout)
+        const bool want_dx = p.dx != nullptr;
+        float* __restrict__ dxs = p.dx + int64_t(s) * p.sample_elems + e0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {   // end product, 32 registers at a time
+            float acc[32];
+            tm_ld32(acc, tm + col_acc + 32 * c);
+            float4 q[8];
+            if constexpr (RESID) {
+                if (role == 0) {
+                    static_for<0, 8>([&](auto j_) {
+                        constexpr int j = decltype(j_)::value;
+                        const uint32_t off = off_f + tile_reg_offset<N, C, V_FIRST>(8 * c + j);
+                        q[j] = to_dy(raw4(stage_dy, off), tgt, off, left);
+                    });
+                } else {
+                    static_for<0, 8>([&](auto j_) {
+                        constexpr int j = decltype(j_)::value;
+                        q[j] = raw4(stage_x, off_f + tile_reg_offset<N, C, V_FIRST>(8 * c + j));
+                    });
+                }
+            } else {
+                static_for<0, 8>([&](auto j_) {
+                    constexpr int j = decltype(j_)::value;
+                    q[j] = raw4(src_end, off_f + tile_reg_offset<N, C, V_FIRST>(8 * c + j));
+                });
+            }
+            tm_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fma4(acc + 4 * j, q[j], v + 32 * c + 4 * j);
+            tm_st32(acc, tm + col_acc + 32 * c);
+            if (role) {   // dx = s2 * dt1, masked by the fused ReLU of the producer
+                float w[32];
+                tm_ld32(w, tm + COL_S2 + 32 * c);
+                tm_wait_ld();
+                static_for<0, 8>([&](auto j_) {
+                    constexpr int j = decltype(j_)::value;
+                    const uint32_t off = off_f + tile_reg_offset<N, C, V_FIRST>(8 * c + j);
+                    const float* bb = v + 32 * c + 4 * j;
+                    const float4 o = make_float4(q[j].x > relu_thr ? bb[0] * w[4 * j] : 0.f, q[j].y > relu_thr ? bb[1] * w[4 * j + 1] : 0.f,
+                                                 q[j].z > relu_thr ? bb[2] * w[4 * j + 2] : 0.f, q[j].w > relu_thr ? bb[3] * w[4 * j + 3] : 0.f);
+                    if (want_dx && (left >= TILE || off < left)) stg_stream(dxs + off, o);
+                });
+            } else if constexpr (WANT_DBIAS) {
+                float ab[32];
+                tm_ld32(ab, tm + COL_AB + 32 * c);
+                tm_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ab[4 * j] += q[j].x, ab[4 * j + 1] += q[j].y, ab[4 * j + 2] += q[j].z, ab[4 * j + 3] += q[j].w;
+                tm_st32(ab, tm + COL_AB + 32 * c);
+            }
+        }
+        mbar_arrive(&empty_bar[pair][st]);
+        tm_wait_st();   // this thread's next loads of the running sums come after these stores
+    }
+    // running sums -> workspace: [0] dg, [1] ds1, [2] ds2, [3] dbias
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        float acc[32];
+        tm_ld32(acc, tm + col_acc + 32 * c);
+        tm_wait_ld();
+        float* dst = slab + (role ? 2 : 1) * TILE;
+        const float osc = (RESID || role) ? 1.f : dysc;   // X: ds1 = dy_scale * sum dy * t4
+        static_for<0, 8>([&](auto j_) {
+            constexpr int j = decltype(j_)::value;
+            const uint32_t off = off_f + tile_reg_offset<N, C, V_FIRST>(8 * c + j);
+            *reinterpret_cast<float4*>(dst + off) = make_float4(osc * acc[4 * j], osc * acc[4 * j + 1], osc * acc[4 * j + 2], osc * acc[4 * j + 3]);
+        });
+        if constexpr (WANT_DBIAS) {
+            if (role == 0) {
+                tm_ld32(acc, tm + COL_AB + 32 * c);
+                tm_wait_ld();
+                static_for<0, 8>([&](auto j_) {
+                    constexpr int j = decltype(j_)::value;
+                    const uint32_t off = off_f + tile_reg_offset<N, C, V_FIRST>(8 * c + j);
+                    *reinterpret_cast<float4*>(slab + 3 * TILE + off) = make_float4(osc * acc[4 * j], osc * acc[4 * j + 1], osc * acc[4 * j + 2], osc * acc[4 * j + 3]);
+                });
+            }
+        }
+    }
+    {
+        float ag[H];
+        tm_ld32(ag, tm + (role ? COL_AGY : COL_AGX));
+        tm_wait_ld();
+        store_dg_half(ag, role, slab);
+    }
+    tm_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tm_dealloc(tmem_base_smem, 512);
+}
+
 // Second stage: fixed-order (bit-reproducible, no atomics) sums of the per-group slabs.
 //   dg[s, i]         = sum over the slabs of sample s and over the N/D row replicas inside a slab
 //   ds1/ds2/dbias[i] = the same over ALL slabs
@@ -599,6 +1003,44 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     return launch_bwd_reduce(c.ws, c.dg, c.ds1, c.ds2, c.dbias, c.S, plan.ctas_per_sample * PAIRS, int64_t(tile), D, stream);
 }
 
+template <int N, int C, int KT, int ROUNDS>
+static int launch_bwd_tm_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
+{
+    static unsigned char smem_ok[4][64] = {};
+    constexpr int T = 1 << (N - C);
+    constexpr int PAIRS = 128 / T;
+    constexpr size_t tile = size_t(1) << N;
+    constexpr size_t smem = sizeof(float) * PAIRS * (2 * 2 * tile + 2 * size_t(scratch_words(N, C)));
+    static_assert(smem <= 227 * 1024, "TMEM backward kernel shared memory");
+    const int64_t D = int64_t(1) << k;
+    const int64_t tiles_per_sample = (c.B * D + int64_t(tile) - 1) / int64_t(tile);
+    const Plan plan = make_plan_waves(c.S, tiles_per_sample, PAIRS, 148, 8, 8);
+    const size_t need = sizeof(float) * size_t(c.S) * plan.ctas_per_sample * PAIRS * 4 * tile;
+    if (c.need_only) {
+        *c.need_only = need;
+        return WHVI_OK;
+    }
+    if (c.ws == nullptr || c.ws_bytes < need)
+        return fail(WHVI_E_WORKSPACE, "layer_bwd: workspace of %zu bytes needed, %zu given", need, c.ws_bytes);
+    const int64_t ctas = int64_t(plan.ctas_per_sample) * c.S;
+    if (ctas > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "layer_bwd: grid too large");
+    BwdArgs a{c.x, c.xs, c.dy, c.g, c.s1, c.s2, c.dx, c.ws, c.B * D, static_cast<int>(c.S), plan.ctas_per_sample, plan.iters_per_group, k,
+              c.relu_in, c.target, c.coef, c.dy_scale};
+    auto go = [&](auto kernel, int slot) -> int {
+        if (int rc = ensure_smem(kernel, smem, smem_ok[slot])) return rc;
+        kernel<<<static_cast<unsigned>(ctas), 256, smem, stream>>>(a);
+        return check_launch("layer_bwd_tm_kernel");
+    };
+    const bool db = c.dbias != nullptr, rs = c.target != nullptr;
+    int rc;
+    if (db && rs) rc = go(layer_bwd_tm_kernel<N, C, KT, ROUNDS, true, true>, 0);
+    else if (db) rc = go(layer_bwd_tm_kernel<N, C, KT, ROUNDS, true, false>, 1);
+    else if (rs) rc = go(layer_bwd_tm_kernel<N, C, KT, ROUNDS, false, true>, 2);
+    else rc = go(layer_bwd_tm_kernel<N, C, KT, ROUNDS, false, false>, 3);
+    if (rc) return rc;
+    return launch_bwd_reduce(c.ws, c.dg, c.ds1, c.ds2, c.dbias, c.S, plan.ctas_per_sample * PAIRS, int64_t(tile), D, stream);
+}
+
 int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream)
 {
     const int k = ilog2(D);
@@ -610,6 +1052,11 @@ int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream)
     if (k == 10) return launch_bwd_tma_cfg<10, 5, 10, 4, 1, 2, false, false, 1, 2>(c, k, stream);
     // D >= 2048: three views (a 64-float-per-thread two-view variant measured slower at D = 4096:
     // 1.16 ms vs 1.08 ms -- too few warps and no room for register-resident parameters)
+#ifndef WHVI_BWD_LEGACY   // -DWHVI_BWD_LEGACY=1: round 1's three-view register-only kernels (A/B builds)
+    // D = 2048, 4096: two views, 64 floats per thread, running sums / g / role exchange in tensor memory
+    if (k == 11) return launch_bwd_tm_cfg<12, 6, 11, 2>(c, k, stream);
+    if (k == 12) return launch_bwd_tm_cfg<12, 6, 12, 2>(c, k, stream);
+#endif
     if (k == 11) return launch_bwd_tma_cfg<11, 5, 11, 2, 1, 2, false, false, 2, 3>(c, k, stream);
     if (k == 12) return launch_bwd_tma_cfg<12, 5, 12, 1, 1, 2, false, false, 2, 3>(c, k, stream);
 #if WHVI_PADDED  // the padded scratch does not fit next to a stash tile of its own at D = 8192: alias the stash

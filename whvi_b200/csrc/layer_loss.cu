@@ -24,9 +24,13 @@
 // released by Y one tile ago, so it does not stall, and the copy still has a whole tile of lead
 // time.  (With 2 stages and the refill at the start of an iteration X waits for Y and the two
 // roles serialise: measured 2x slower.)
-// Variant builds: -DWHVI_PADDED_BWD=1 pads the transposition buffers of THIS translation unit only
-// (measured: the backward gains ~4%, the two-view forward loses; profiles/r01_bwd_notes.md item 14).
-#if defined(WHVI_PADDED_BWD) && WHVI_PADDED_BWD && !defined(WHVI_PADDED)
+// The transposition buffers of THIS translation unit use the padded (XOR-free) layout (WHVI_PADDED_BWD, default 1;
+// measured: the backward gains ~4% at D = 1024...8192 with bit-identical outputs, the two-view forward does not,
+// profiles/r01_bwd_notes.md item 14, profiles/r02_ab_padbwd.txt); -DWHVI_PADDED_BWD=0 builds the swizzled variant.
+#ifndef WHVI_PADDED_BWD
+#define WHVI_PADDED_BWD 1   // product default since round 2: bit-identical outputs, -4% (profiles/r02_ab_padbwd.txt)
+#endif
+#if WHVI_PADDED_BWD && !defined(WHVI_PADDED)
 #define WHVI_PADDED 1
 #endif
 #include "layer_common.cuh"

@@ -190,4 +190,40 @@ int launch_mc_moments(const float* y, int64_t y_sample_stride, const float* in_y
     return check_launch("mc_moments_kernel");
 }
 
+// ---- fused Adam over one flat parameter buffer (the optimizer.step() of the reference's step loop,
+// src/networks.py:80-82 / :92-94, with torch.optim.Adam's arithmetic: no weight decay, no amsgrad) ---------------
+//   m = m + (1 - b1) (g - m);  v = b2 v + (1 - b2) g^2;  p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// `step` is the device-resident step count t >= 1 (already incremented by the caller) and `lr_dev`, when given, a
+// device scalar, so that a captured CUDA graph sees learning-rate schedules and step counts without re-capture.
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+            float lr_host, const float* __restrict__ lr_dev, const float* __restrict__ step, float b1, float b2, float eps,
+            float grad_scale)
+{
+    const float t = __ldg(step);
+    const float lr = lr_dev ? __ldg(lr_dev) : lr_host;
+    const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(b1), static_cast<double>(t)));
+    const float bc2_sqrt = sqrtf(static_cast<float>(1.0 - pow(static_cast<double>(b2), static_cast<double>(t))));
+    const float step_size = lr / bc1;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i] * grad_scale;
+        const float mi = m[i] + (1.f - b1) * (gi - m[i]);           // exp_avg.lerp_(grad, 1 - beta1)
+        const float vi = fmaf(1.f - b2, gi * gi, b2 * v[i]);        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] -= step_size * (mi / denom);
+    }
+}
+
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, const float* step,
+                float b1, float b2, float eps, float grad_scale, cudaStream_t stream)
+{
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    adam_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p, g, m, v, n, lr, lr_dev, step, b1, b2, eps, grad_scale);
+    return check_launch("adam_kernel");
+}
+
 }  // namespace whvi

@@ -6,9 +6,14 @@ path needs no collective; the only exchange is the sum of the small parameter gr
 ({d mu, d rho, d s1, d s2, d bias} of every layer plus the likelihood's sigma): 4.D floats per
 square block, ~49 K floats (196 KB) for the 3 x 4096 network -- latency-bound, one NCCL call.
 
-Scaling convention: each rank computes ``loss_r = (mnll_r + kl) / world`` on its own sample
-shard (``mnll_r`` already divides by its local sample count), so the SUM over ranks of the
-gradients equals the single-process gradient of ``mean_s mnll + kl``.
+Scaling convention (``rank_loss``): each rank computes ``loss_r = mnll_r * n_local / S + kl / world``
+on its own sample shard (``mnll_r`` already divides by its LOCAL sample count ``n_local``), so the SUM
+over ranks of the gradients equals the single-process gradient of ``mean_s mnll + kl`` for even and
+uneven shards alike; with ``S % world == 0`` this is the familiar ``(mnll_r + kl) / world``.
+
+The exchange itself is ``whvi_b200.optim.FlatParams.all_reduce`` (gradients live as views of one buffer:
+one NCCL call, no pack / unpack kernels); ``FlatGradAllReduce`` is the copying variant for models whose
+``.grad`` tensors are managed by someone else.
 """
 from __future__ import annotations
 
@@ -31,6 +36,15 @@ def shard_samples(total_samples: int, rank: int, world_size: int) -> Tuple[int, 
 def shard_rows(total_rows: int, rank: int, world_size: int) -> Tuple[int, int]:
     """(first_row, n_local): evaluation can shard minibatch rows instead of samples."""
     return shard_samples(total_rows, rank, world_size)
+
+
+def rank_loss(mnll_local, kl, n_local: int, total_samples: int, world_size: int):
+    """This rank's share of the ELBO loss such that the SUM over ranks has the gradient of
+    ``mean over all S samples of mnll + kl`` (KL is replicated: every rank adds 1/world of it).
+    ``mnll_local`` is the MNLL estimate over this rank's ``n_local`` samples."""
+    if total_samples <= 0 or world_size < 1:
+        raise ValueError("bad rank_loss arguments")
+    return mnll_local * (float(n_local) / float(total_samples)) + kl * (1.0 / world_size)
 
 
 class FlatGradAllReduce:
@@ -78,50 +92,3 @@ def reduce_predictive_moments(sum_y: torch.Tensor, sum_y2: torch.Tensor, n_local
     mean = sum_y / count
     var = sum_y2 / count - mean * mean
     return mean, var
-
-
-class PeerMomentExchange:
-    """Reduce-scatter of the evaluation path's (sum y, sum y^2) over NVLink peer memory, without a
-    collective kernel: every rank's reduction kernel (``functional.mc_moments_into``) stores the
-    partial sums of the rows owned by rank q straight into q's staging buffer (symmetric memory,
-    NVLink-mapped), a signal-pad barrier on a side stream publishes them, and q adds up the
-    ``world`` slots for its rows.  No SMs are taken from the transforms by a communication kernel
-    and the partial sums never make a second trip through local HBM.
-
-    ``rows`` per input chunk must divide by the world size; ``slots`` chunks may be in flight.
-    """
-
-    def __init__(self, rows: int, D: int, device, group=None, slots: int = 2):
-        import torch.distributed._symmetric_memory as symm_mem
-        self.group = group if group is not None else dist.group.WORLD
-        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        if rows % self.world:
-            raise RuntimeError("rows per chunk must be a multiple of the world size")
-        self.rows, self.D, self.n_mine, self.slots = rows, D, rows // self.world, slots
-        self.shape = (slots, self.world, 2, self.n_mine, D)   # [slot][source rank][sum y | sum y^2][row][col]
-        self.local = symm_mem.empty(self.shape, dtype=torch.float32, device=device)
-        self.handle = symm_mem.rendezvous(self.local, self.group)
-        self.peers = [self.handle.get_buffer(q, self.shape, torch.float32) for q in range(self.world)]
-        self.stream = torch.cuda.Stream(device=device)
-        self.handle.barrier()
-
-    def destinations(self, slot: int):
-        """``scatter_to`` argument of ``predictive_moments``: rows of owner q -> q's slot for this rank."""
-        return [(q * self.n_mine, (q + 1) * self.n_mine, self.peers[q][slot, self.rank, 0], self.peers[q][slot, self.rank, 1])
-                for q in range(self.world)]
-
-    def publish(self) -> torch.cuda.Event:
-        """Call after the scattering kernels have been enqueued on the current stream: a barrier on
-        the side stream (so the current stream can go on with the next chunk); returns the event to
-        wait for before reading ``totals``."""
-        self.stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.stream):
-            self.handle.barrier()
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        return ev
-
-    def totals(self, slot: int):
-        """(sum y, sum y^2) over all ranks' samples for the rows this rank owns: (n_mine, D) each."""
-        t = self.local[slot].sum(dim=0)
-        return t[0], t[1]

@@ -23,7 +23,7 @@ _LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_fwht_f64": 1, "whvi_layer_fwd_f3
                       "whvi_layer_fwd_fused_f32": 1, "whvi_layer_bwd_fused_f32": 3,
                       "whvi_layer_bwd_scaled_f32": 3, "whvi_layer_loss_f32": 3, "whvi_reparam_f32": 1,
                       "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1, "whvi_mc_moments_f32": 1,
-                      "whvi_mc_moments_strided_f32": 1}
+                      "whvi_mc_moments_strided_f32": 1, "whvi_adam_f32": 1}
 # When set to a dict {"name": [(start_event, stop_event), ...]}, the named calls are bracketed
 # by CUDA events on the launching stream (bench.py's per-kernel roofline timing).
 EVENT_SINK: dict[str, list] | None = None
@@ -180,7 +180,7 @@ def predictive_moments(x, mu, rho, s1, s2, bias=None, n_samples=64, chunk_sample
     None) -- e.g. computed on row slices by different ranks and all-gathered.
     ``scatter_to``: [(row_lo, row_hi, out_y, out_y2), ...] covering all rows -- the LAST sample
     chunk's reduction writes its totals there instead of into the local sums (peer-GPU buffers of
-    the ranks that own those rows: ``distributed.PeerMomentExchange``).
+    the ranks that own those rows; the experiment in ``tools/peer_moments.py`` uses it).
     """
     from .fwht import fwht_
     x = _f32c(x if t2 is None else t2, "x")
@@ -254,20 +254,27 @@ def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False, relu_in
 
 LOSS_LAYER_MIN_D, LOSS_LAYER_MAX_D = 128, 4096
 
-# dx tensors handed out by WHVILayerLossFunction for a UNIT loss coefficient, keyed by data_ptr,
-# with the scalar they still have to be multiplied by; consumed by WHVILayerFunction.backward.
-_PENDING_DY_SCALE: dict[int, torch.Tensor] = {}
+class DeferredScale:
+    """Scalar hand-over between two autograd nodes of ONE graph: the fused loss layer computes its
+    dx for a unit loss coefficient and leaves the true coefficient here; the producer of its input
+    (a fused ``WHVILayerFunction``) picks it up in its own backward and applies it while loading dy
+    (``whvi_layer_bwd_scaled_f32``), which saves a pass over dx.  ``WHVINetwork._run`` creates one
+    holder per (producer, loss layer) pair and passes it to both ``forward`` calls, so the scale is
+    carried by the graph itself: copies of the gradient tensor (hooks, accumulation) cannot lose
+    it, and nothing outlives the graph.  If the consumer's backward has not run when the producer's
+    does (``torch.autograd.grad`` on a subset), the holder is empty and dy is used as it is."""
 
+    __slots__ = ("value",)
 
-def check_no_pending_scale() -> None:
-    """A deferred scale that nobody consumed means a backward pass handed an unscaled gradient to
-    something other than WHVILayerFunction.backward (e.g. a hook copied the tensor): fail loudly
-    instead of training on wrong gradients."""
-    if _PENDING_DY_SCALE:
-        _PENDING_DY_SCALE.clear()
-        raise RuntimeError("whvi_b200: a deferred gradient scale of the fused loss layer was never consumed; the "
-                           "previous backward pass produced wrongly scaled gradients (construct the network with "
-                           "fuse=False if the activations between the last two layers are hooked or shared)")
+    def __init__(self):
+        self.value = None
+
+    def put(self, c: torch.Tensor) -> None:
+        self.value = c
+
+    def take(self):
+        c, self.value = self.value, None
+        return c
 
 
 def layer_loss_raw(x, g, s1, s2, bias, target, want_dx=True, relu_in=False):
@@ -311,11 +318,12 @@ class WHVILayerFunction(Function):
     touching HBM."""
 
     @staticmethod
-    def forward(ctx, x, g, s1, s2, bias, relu_out=False, relu_in=False):
+    def forward(ctx, x, g, s1, s2, bias, relu_out=False, relu_in=False, dy_scale_from=None):
         y = layer_forward_raw(x, g, s1, s2, bias, relu_out=relu_out)
         ctx.save_for_backward(x, g, s1, s2)
         ctx.has_bias = bias is not None
         ctx.relu_in = relu_in
+        ctx.dy_scale_from = dy_scale_from  # DeferredScale shared with the fused loss layer that consumes y
         return y
 
     @staticmethod
@@ -323,16 +331,28 @@ class WHVILayerFunction(Function):
         x, g, s1, s2 = ctx.saved_tensors
         want_dx = ctx.needs_input_grad[0]
         want_db = ctx.has_bias and ctx.needs_input_grad[4]
-        scale = _PENDING_DY_SCALE.pop(dy.data_ptr(), None)  # dy came from a fused loss layer, still unscaled
+        # dy came from a fused loss layer that left its loss coefficient in the shared holder
+        scale = ctx.dy_scale_from.take() if ctx.dy_scale_from is not None else None
         dx, dg, ds1, ds2, dbias = layer_backward_raw(x, dy, g, s1, s2, want_dx=want_dx, want_dbias=want_db,
                                                      relu_in=ctx.relu_in, dy_scale=scale)
         if dx is not None and x.dim() == 2:
             dx = dx.sum(dim=0)
-        return dx, dg, ds1, ds2, dbias, None, None
+        return dx, dg, ds1, ds2, dbias, None, None, None
 
 
-def whvi_layer(x, g, s1, s2, bias=None, relu_out=False, relu_in=False):
-    return WHVILayerFunction.apply(x, g, s1, s2, bias, relu_out, relu_in)
+MIN_LAYER_D = 4  # narrowest row the layer kernels take (one float4)
+
+
+def whvi_layer(x, g, s1, s2, bias=None, relu_out=False, relu_in=False, dy_scale_from=None):
+    D = g.size(-1)
+    if D < MIN_LAYER_D:
+        # D = 1, 2 (the reference takes them, e.g. WHVILinear(2, 2) on 2-D toy inputs): zero-pad x, g, s1, s2 to
+        # width 4.  H_4 = H_2 (x) H_2 and the padded s2 / g / s1 zero the other block at every stage, so the first D
+        # outputs -- and, through autograd of the pad, all gradients -- are exactly the width-D layer's.
+        pad = lambda v: None if v is None else torch.nn.functional.pad(v, (0, MIN_LAYER_D - D))
+        y = WHVILayerFunction.apply(pad(x), pad(g), pad(s1), pad(s2), pad(bias), relu_out, relu_in, dy_scale_from)
+        return y[..., :D]
+    return WHVILayerFunction.apply(x, g, s1, s2, bias, relu_out, relu_in, dy_scale_from)
 
 
 class WHVILayerSqErrFunction(Function):
@@ -380,16 +400,17 @@ class WHVILayerLossFunction(Function):
     ``sum (y_hat - target)^2``; the predictions never exist in HBM and the layer's whole backward
     is computed in the same pass (for a unit loss coefficient) and kept for ``backward``.
 
-    ``defer_dx_scale``: the producer of ``x`` is a fused ``WHVILayerFunction`` (set by
-    ``WHVINetwork`` in matching pairs, like relu_out/relu_in); ``dx`` is then handed on unscaled
-    and the consumer's backward kernel applies the scalar on load, saving a pass over dx."""
+    ``dx_scale_to``: a ``DeferredScale`` shared with the fused ``WHVILayerFunction`` that produced
+    ``x`` and is its ONLY consumer (set by ``WHVINetwork._run`` in matching pairs, like
+    relu_out/relu_in); ``dx`` is then handed on unscaled, the coefficient goes into the holder and
+    the producer's backward kernel applies it on load, saving a pass over dx."""
 
     @staticmethod
-    def forward(ctx, x, g, s1, s2, bias, target, relu_in=False, defer_dx_scale=False):
+    def forward(ctx, x, g, s1, s2, bias, target, relu_in=False, dx_scale_to=None):
         want_dx = ctx.needs_input_grad[0]
         sq, dx, dg, ds1, ds2, dbias = layer_loss_raw(x, g, s1, s2, bias, target, want_dx=want_dx, relu_in=relu_in)
         ctx.shared_x = x.dim() == 2
-        ctx.defer = bool(defer_dx_scale) and want_dx and not ctx.shared_x
+        ctx.dx_scale_to = dx_scale_to if (want_dx and not ctx.shared_x) else None
         ctx.has_dx, ctx.has_db = dx is not None, dbias is not None
         ctx.save_for_backward(*[t for t in (dx, dg, ds1, ds2, dbias) if t is not None])
         return sq
@@ -404,15 +425,15 @@ class WHVILayerLossFunction(Function):
         if dx is not None:
             if ctx.shared_x:
                 dx = dx.sum(dim=0) * c
-            elif ctx.defer:
-                _PENDING_DY_SCALE[dx.data_ptr()] = c.reshape(1)
+            elif ctx.dx_scale_to is not None:
+                ctx.dx_scale_to.put(c.reshape(1))
             else:
                 dx = dx.mul_(c)
         return dx, dg * c, ds1 * c, ds2 * c, None if dbias is None else dbias * c, None, None, None
 
 
-def whvi_layer_loss(x, g, s1, s2, bias, target, relu_in=False, defer_dx_scale=False):
-    return WHVILayerLossFunction.apply(x, g, s1, s2, bias, target, relu_in, defer_dx_scale)
+def whvi_layer_loss(x, g, s1, s2, bias, target, relu_in=False, dx_scale_to=None):
+    return WHVILayerLossFunction.apply(x, g, s1, s2, bias, target, relu_in, dx_scale_to)
 
 
 class ReparamFunction(Function):

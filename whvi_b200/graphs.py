@@ -7,20 +7,28 @@ backward + optimizer step once into a ``torch.cuda.CUDAGraph`` (all of this repo
 plain stream-ordered launches with caller-owned buffers, so they capture as they are) and
 replays it per minibatch: one launch per step.
 
-Requirements (checked): the optimizer must be graph-capturable (``capturable=True``); if a
-learning-rate scheduler is to act on a captured step, the optimizer's ``lr`` must be a CUDA
-tensor (PyTorch schedulers then update it in place).
+Requirements (both checked by ``_check_optimizer``): the optimizer must be graph-capturable
+(``capturable=True``, or ``whvi_b200.optim.FlatAdam``); if a learning-rate scheduler is to act on
+a captured step (``train_model(cuda_graph=True)`` always steps one), the optimizer's ``lr`` must be
+a CUDA tensor (PyTorch schedulers then update it in place) -- a float ``lr`` raises.
 """
 from __future__ import annotations
 
 import torch
 
 
-def _check_optimizer(optimizer) -> None:
+def _check_optimizer(optimizer, scheduled: bool = False) -> None:
+    """``scheduled``: a learning-rate scheduler will step between replays.  A Python-float ``lr`` is
+    baked into the captured kernels' arguments, so the schedule would be silently ignored: the
+    ``lr`` of every group must then be a CUDA tensor (schedulers update it in place)."""
     for group in optimizer.param_groups:
-        if not group.get("capturable", False):
+        if not group.get("capturable", False) and not getattr(optimizer, "whvi_graph_safe", False):
             raise RuntimeError("CUDA-graph training needs a capturable optimizer, e.g. "
                                "torch.optim.Adam(params, lr=torch.tensor(1e-3, device='cuda'), capturable=True)")
+        if scheduled and not (torch.is_tensor(group["lr"]) and group["lr"].is_cuda):
+            raise RuntimeError("CUDA-graph training with a learning-rate scheduler needs lr to be a CUDA tensor "
+                               "(lr=torch.tensor(1e-3, device='cuda')): a float lr is frozen into the captured graph "
+                               "and scheduler.step() would have no effect")
 
 
 class GraphedTrainStep:
@@ -33,10 +41,10 @@ class GraphedTrainStep:
     graph's private pool and are recomputed (not accumulated) by every replay.
     """
 
-    def __init__(self, model, optimizer, x, y, n: int, ignore_kl: bool = False, warmup: int = 3):
+    def __init__(self, model, optimizer, x, y, n: int, ignore_kl: bool = False, warmup: int = 3, scheduled: bool = False):
         if not (x.is_cuda and y.is_cuda):
             raise RuntimeError("GraphedTrainStep needs CUDA minibatches")
-        _check_optimizer(optimizer)
+        _check_optimizer(optimizer, scheduled)
         self.model, self.optimizer = model, optimizer
         self.x, self.y = x.detach().clone(), y.detach().clone()
         # the warm-up steps below must not count as training: remember parameters and optimizer
@@ -72,6 +80,8 @@ class GraphedTrainStep:
             self.loss = model.loss(self.x, self.y, n=n, ignore_kl=ignore_kl)
             self.loss.backward()
             optimizer.step()
+            if getattr(optimizer, "whvi_graph_safe", False):
+                optimizer.zero_grad()  # FlatAdam: gradients persist as views of one buffer; the memset is part of the step
         self.kl, self.mnll = model.current_kl, model.current_mnll
 
     def __call__(self, x, y):
@@ -85,13 +95,15 @@ class GraphedTrainStep:
 class GraphedStepCache:
     """One captured step per minibatch shape (a data loader's last batch is usually shorter)."""
 
-    def __init__(self, model, optimizer, n: int, ignore_kl: bool = False):
-        self.model, self.optimizer, self.n, self.ignore_kl = model, optimizer, n, ignore_kl
+    def __init__(self, model, optimizer, n: int, ignore_kl: bool = False, scheduled: bool = False):
+        _check_optimizer(optimizer, scheduled)  # fail before the first minibatch, not inside the loop
+        self.model, self.optimizer, self.n, self.ignore_kl, self.scheduled = model, optimizer, n, ignore_kl, scheduled
         self.steps: dict[tuple, GraphedTrainStep] = {}
 
     def __call__(self, x, y):
         key = (tuple(x.shape), tuple(y.shape), x.dtype, y.dtype)
         step = self.steps.get(key)
         if step is None:
-            step = self.steps[key] = GraphedTrainStep(self.model, self.optimizer, x, y, self.n, self.ignore_kl)
+            step = self.steps[key] = GraphedTrainStep(self.model, self.optimizer, x, y, self.n, self.ignore_kl,
+                                                      scheduled=self.scheduled)
         return step(x, y)

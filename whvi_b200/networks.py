@@ -85,14 +85,13 @@ class WHVINetwork(nn.Module, WHVI):
         with the ReLU folded into the two kernels (``self.fuse``)."""
         modules = list(self.sequential.children())
         layers = self._whvi_layers()
-        WF.check_no_pending_scale()
         if self.rng_mode == "reference":
             self._predraw_reference_order(n_samples)
         for layer in layers:
             layer.mc_samples = n_samples
         sq = None
         try:
-            h, i, relu_in = x, 0, False
+            h, i, relu_in, scale_holder = x, 0, False, None
             while i < len(modules):
                 module = modules[i]
                 last = i == len(modules) - 1
@@ -101,13 +100,18 @@ class WHVINetwork(nn.Module, WHVI):
                     relu_out = (i + 2 < len(modules) and type(modules[i + 1]) is nn.ReLU
                                 and self._fusable_square(modules[i + 2]))
                     if last and sqerr_target is not None and w.loss_fusable and torch.is_grad_enabled():
-                        # training: forward + residual + backward of the last layer in one pass
-                        sq = w.forward_loss(h, sqerr_target, relu_in=relu_in, defer_dx_scale=relu_in)
+                        # training: forward + residual + backward of the last layer in one pass; its dx is
+                        # for a unit loss coefficient, which the producer of h applies (scale_holder)
+                        sq = w.forward_loss(h, sqerr_target, relu_in=relu_in, dx_scale_to=scale_holder)
                         h = None
                     elif last and sqerr_target is not None:
                         h, sq = w.forward_sqerr(h, sqerr_target, relu_in=relu_in)
                     else:
-                        h = w.forward(h, relu_out=relu_out, relu_in=relu_in)
+                        # h's only consumer will be the fused loss layer: share a DeferredScale with it
+                        nxt = modules[i + 2].weight_submodule if relu_out else None
+                        scale_holder = (WF.DeferredScale() if (relu_out and i + 2 == len(modules) - 1 and sqerr_target is not None
+                                                               and nxt.loss_fusable and torch.is_grad_enabled()) else None)
+                        h = w.forward(h, relu_out=relu_out, relu_in=relu_in, dy_scale_from=scale_holder)
                     relu_in = relu_out
                     i += 2 if relu_out else 1
                     continue
@@ -164,7 +168,7 @@ class WHVINetwork(nn.Module, WHVI):
         graphed = None
         if cuda_graph:
             from .graphs import GraphedStepCache
-            graphed = GraphedStepCache(self, optimizer, n=len(data_loader.dataset), ignore_kl=ignore_kl)
+            graphed = GraphedStepCache(self, optimizer, n=len(data_loader.dataset), ignore_kl=ignore_kl, scheduled=True)
         self.likelihood.requires_grad = False
         for phase, epochs, label in ((1, epochs1, 'Fixed LH'), (2, epochs2, 'Optimized LH')):
             if phase == 2:

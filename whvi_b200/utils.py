@@ -57,6 +57,7 @@ class DevicePrefetcher:
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.stream = torch.cuda.Stream(device=self.device)
         self.bufs = [None, None]
+        self.views = [None, None]   # what is handed out: the leading rows of bufs that the batch fills
         self.ready = [None, None]   # copy finished (recorded on the side stream)
         self.done = [None, None]    # consumer finished with the slot (recorded on its stream)
         self.i = 0                  # index of the next batch to hand out
@@ -69,13 +70,18 @@ class DevicePrefetcher:
         except StopIteration:
             return
         k = self.loaded % 2
-        if self.bufs[k] is None:
+        # the slot's buffers are sized by the largest batch seen; a shorter batch (a DataLoader's last one
+        # with drop_last=False) is copied into -- and handed out as -- the leading rows of the buffers
+        fits = self.bufs[k] is not None and len(self.bufs[k]) == len(host) and all(
+            d.shape[1:] == h.shape[1:] and d.dtype == h.dtype and d.size(0) >= h.size(0) for d, h in zip(self.bufs[k], host))
+        if not fits:
             self.bufs[k] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host)
+        views = tuple(d[:h.size(0)] for d, h in zip(self.bufs[k], host))
         with torch.cuda.stream(self.stream):
             if self.done[k] is not None:
                 self.stream.wait_event(self.done[k])
-            for d, h in zip(self.bufs[k], host):
-                if self.world > 1 and h.size(0) % self.world == 0:
+            for d, h in zip(views, host):
+                if self.world > 1 and h.size(0) % self.world == 0 and h.size(0) > 0:
                     import torch.distributed as dist
                     n = h.size(0) // self.world
                     mine = d[self.rank * n:(self.rank + 1) * n]
@@ -83,6 +89,7 @@ class DevicePrefetcher:
                     dist.all_gather_into_tensor(d, mine, group=self.group)  # in place, on the side stream
                 else:
                     d.copy_(h, non_blocking=True)
+            self.views[k] = views
             self.ready[k] = torch.cuda.Event()
             self.ready[k].record(self.stream)
         self.loaded += 1
@@ -101,5 +108,6 @@ class DevicePrefetcher:
         k = self.i % 2
         cur.wait_event(self.ready[k])
         self.i += 1
+        out = self.views[k]
         self._preload()
-        return self.bufs[k]
+        return out

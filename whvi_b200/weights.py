@@ -1,7 +1,12 @@
 """WHVI weight parameterisations behind the reference's class names and signatures
 (reference ``src/weights.py``): ``WHVISquarePow2Matrix``, ``WHVIStackedMatrix``,
 ``WHVIColumnMatrix``.  Parameter names, shapes, initialisation and registration order are
-the reference's (``src/weights.py:28-32``), so ``state_dict``s are interchangeable.
+the reference's (``src/weights.py:28-32``), so ``state_dict`` KEYS AND SHAPES are interchangeable.
+The FUNCTION those parameters define is not, under the default ``semantics="paper"``: weights
+trained by the reference were trained for the map the reference actually executes
+(``D.diag(s1 g s2)``) and must be loaded into modules built with
+``semantics="reference"`` to reproduce the reference's predictions and loss;
+``load_state_dict`` on a ``"paper"`` module says so once (``WARN_ON_LOAD``).
 
 What changed underneath: the reference materialises a D x D matrix per MC sample through
 four FWHTs of D x D matrices and multiplies by it (``src/weights.py:73``, ``:93``); here a
@@ -15,7 +20,8 @@ called with ``(S, B, n_in)`` it maps sample to sample.  Called standalone on a 2
 
 ``semantics``:
   * ``"paper"`` (default) -- W = S1 H diag(g) H S2, the docstring formula at
-    ``src/weights.py:77`` and the north-star definition of the hot path.
+    ``src/weights.py:77`` and the north-star definition of the hot path.  NOT numerically
+    compatible with reference-trained weights (a different function of the same parameters).
   * ``"reference"`` -- the op chain as the reference actually executes it
     (``src/weights.py:73``: both FWHTs act on rows, so W collapses to D.diag(s1 g s2),
     SURVEY F1), run literally with this repo's FWHT kernel in place of ``fwht_cuda``; for
@@ -31,6 +37,22 @@ from . import functional as WF
 from .fwht import FWHTFunction
 
 _SEMANTICS = ("paper", "reference")
+
+# load_state_dict into a semantics="paper" block warns once per process that reference-trained weights
+# need semantics="reference"; set to False to silence it (e.g. when resuming this package's own checkpoints).
+WARN_ON_LOAD = True
+_warned_on_load = False
+
+
+def _warn_paper_load(module, *args):
+    global _warned_on_load
+    if WARN_ON_LOAD and not _warned_on_load and module.semantics == "paper":
+        _warned_on_load = True
+        import warnings
+        warnings.warn('whvi_b200: loading a state_dict into WHVI blocks built with semantics="paper" (W = S1 H diag(g) H S2). '
+                      'Checkpoints trained by the reference implementation were trained for the map it actually executes '
+                      '(D.diag(s1 g s2), SURVEY F1): construct the model with semantics="reference" to reproduce their '
+                      'predictions and loss.  (whvi_b200.weights.WARN_ON_LOAD = False silences this.)', stacklevel=3)
 
 
 def _next_pow2(n: int) -> int:
@@ -72,6 +94,7 @@ class WHVISquarePow2Matrix(nn.Module):
         self.s2 = nn.Parameter(torch.randn(D) * 0.01)
         self.g_mu = nn.Parameter(torch.zeros(D))
         self.g_rho = nn.Parameter(torch.rand(D) - 3)
+        self._register_load_state_dict_pre_hook(_warn_paper_load, with_module=True)
 
     # ------------------------------------------------------------------ noise
     def inject_eps(self, eps: torch.Tensor) -> None:
@@ -123,7 +146,7 @@ class WHVISquarePow2Matrix(nn.Module):
             return 1, True
         return int(self.mc_samples), False
 
-    def sample_lrt(self, h, *, bias=None, relu_out=False, relu_in=False):
+    def sample_lrt(self, h, *, bias=None, relu_out=False, relu_in=False, dy_scale_from=None):
         """W h for a fresh draw of g per MC sample (local reparameterisation).  The
         keyword arguments are the kernel-side fusions (bias add, ReLU on the way out, ReLU
         mask on the way back); they default to the reference's plain behaviour."""
@@ -137,13 +160,14 @@ class WHVISquarePow2Matrix(nn.Module):
                 y = F.relu(y)
         else:
             g = WF.reparam(self.g_mu, self.g_rho, eps)
-            y = WF.whvi_layer(h, g, self.s1, self.s2, None if bias is None else bias.reshape(-1), relu_out, relu_in)
+            y = WF.whvi_layer(h, g, self.s1, self.s2, None if bias is None else bias.reshape(-1), relu_out, relu_in,
+                              dy_scale_from)
         return y[0] if squeeze else y
 
     @property
     def fusable(self):
         """True when the fused-neighbour paths (ReLU / MNLL folded into the kernels) apply."""
-        return self.semantics == "paper" and 4 <= self.D <= 8192  # the backward kernel's range
+        return self.semantics == "paper" and WF.MIN_LAYER_D <= self.D <= 8192  # the backward kernel's range
 
     def forward_sqerr(self, h, target, *, relu_in=False):
         """Forward pass fused with sum (y - target)^2 (see functional.WHVILayerSqErrFunction).
@@ -153,13 +177,13 @@ class WHVISquarePow2Matrix(nn.Module):
         bias = None if self.bias is None else self.bias.reshape(-1)
         return WF.whvi_layer_sqerr(h, g, self.s1, self.s2, bias, target, relu_in)
 
-    def forward_loss(self, h, target, *, relu_in=False, defer_dx_scale=False):
+    def forward_loss(self, h, target, *, relu_in=False, dx_scale_to=None):
         """Training-time fused last layer: sum (y - target)^2 with the layer's backward computed in
         the same pass (functional.WHVILayerLossFunction).  Returns the 0-d sum only."""
         S, _ = self._resolve_samples(h)
         g = WF.reparam(self.g_mu, self.g_rho, self._draw_eps(S))
         bias = None if self.bias is None else self.bias.reshape(-1)
-        return WF.whvi_layer_loss(h, g, self.s1, self.s2, bias, target, relu_in, defer_dx_scale)
+        return WF.whvi_layer_loss(h, g, self.s1, self.s2, bias, target, relu_in, dx_scale_to)
 
     def predictive_moments(self, x, n_samples=64, *, chunk_samples=16, sample_range=None, out=None, generator=None, t2=None,
                            scatter_to=None):
@@ -187,10 +211,10 @@ class WHVISquarePow2Matrix(nn.Module):
             outs.append(hs @ W.T)
         return torch.stack(outs)
 
-    def forward(self, x, use_lrt=True, *, relu_out=False, relu_in=False):
+    def forward(self, x, use_lrt=True, *, relu_out=False, relu_in=False, dy_scale_from=None):
         """x: (batch, D) or (samples, batch, D).  ``use_lrt`` is kept for signature
         compatibility; both branches of the reference compute W x for a sampled W."""
-        return self.sample_lrt(x, bias=self.bias, relu_out=relu_out, relu_in=relu_in)
+        return self.sample_lrt(x, bias=self.bias, relu_out=relu_out, relu_in=relu_in, dy_scale_from=dy_scale_from)
 
 
 class WHVIStackedMatrix(nn.Module):
