@@ -10,14 +10,21 @@ S = 128 MC samples => 2^20 (sample, row) pairs per layer per step.  One "step" =
 ELBO (Gaussian MNLL + KL) + backward of that model over the whole batch, plus the
 parameter-gradient all-reduce (N > 1) and an Adam step.  MC samples are sharded across the
 N GPUs (strong scaling: S stays 128) and processed in chunks of `--chunk` samples per
-kernel launch so that activations stay at 2 GiB per tensor.
+kernel launch so that activations stay at 4 GiB per tensor.
 
 metric  = "WHVILinear fwd+bwd MC-sample rows/s": S*B*3 layer-rows / step time (a row = one
           (sample, minibatch-row) pair pushed through one WHVILinear forward AND backward).
 value   = inputs resident in HBM;   e2e = same step, but x/y start in pinned host memory and
           the loss is read back to the host every step (through the public Python API).
-Also reported: the batched-FWHT GB/s sweep (`fwht`), the roofline of the dominant kernel
-(the fused layer backward, 12*D algorithmic bytes per row), and the CPU baseline.
+Also in the line: `check` (loss and gradient checksum of ONE verification step on fixed noise -- identical
+for every N up to summation order), the roofline of the dominant kernel (fused backward at a position
+with per-sample inputs, 12*D algorithmic bytes per row) with every other kernel position beside it,
+the batched-FWHT GB/s sweep over all ranks (`fwht`), the MC predictive-evaluation throughput of
+BASELINE config 5 over all ranks (`eval`), and -- N = 1 only -- the CPU baseline.
+
+`--impl reference`: the reference's OWN layer code (oracle/_ref/refpy, byte-compiled unmodified from
+/root/reference/src by oracle/build.py) on the host cores: each step = one MC sample of one
+WHVILinear(4096, 4096) over all 8192 rows, forward + backward.
 """
 from __future__ import annotations
 
@@ -39,6 +46,19 @@ METRIC = "WHVILinear fwd+bwd MC-sample rows/s"
 UNIT = "rows/s"
 D_MODEL, B_BATCH, S_TOTAL, N_LAYERS = 4096, 8192, 128, 3
 WORKLOAD = "config4-wide-mlp: 3x WHVILinear(4096,4096)+ReLU, B=8192, S=128 MC samples, fwd+bwd"
+CONFIG = {"workload": WORKLOAD, "D": D_MODEL, "B": B_BATCH, "S": S_TOTAL, "layers": N_LAYERS}
+
+
+def host_threads() -> int:
+    return os.cpu_count() or 1
+
+
+def use_all_host_threads() -> None:
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; a CPU leg that is supposed to use the host's cores
+    must undo that BEFORE torch is imported (round 1 measured 80 instead of 350 rows/s with `cores: 32`)."""
+    n = str(host_threads())
+    os.environ["OMP_NUM_THREADS"] = n
+    os.environ["MKL_NUM_THREADS"] = n
 
 
 def measured_peaks():
@@ -91,32 +111,43 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-# --------------------------------------------------------------------------- CPU baselines
-def cpu_layer_baseline(threads: int, budget_s: float = 12.0):
-    """Reference torch-CPU layer path AS WRITTEN (oracle/ref_torch.py, a restatement of
-    src/weights.py:66-93) on a bounded sample of the workload: whole fwd+bwd passes of one
-    WHVILinear(4096,4096) on 512 of the 8192 rows, one MC sample each, until the budget."""
-    import torch
+# --------------------------------------------------------------------------- CPU legs (the checker's code, never the product's)
+def reference_layer_step_seconds():
+    """One "reference step": ONE MC sample of ONE WHVILinear(4096, 4096) over ALL 8192 rows, forward + backward, on the
+    host cores -- through the reference's own layer code when it travelled (kind "reference"), else through the
+    torch-CPU restatement of it (kind "port").  Returns (seconds, kind)."""
     from oracle import ref_torch
-    torch.set_num_threads(threads)
-    rows, done, t_used = 512, 0, 0.0
-    ref_torch.layer_fwd_bwd_seconds(D_MODEL, 32, 1)  # builds/caches nothing big at D=4096; warms the allocator
-    while t_used < budget_s:
-        t_used += ref_torch.layer_fwd_bwd_seconds(D_MODEL, rows, 1)
+    dt = ref_torch.reference_layer_fwd_bwd_seconds(D_MODEL, B_BATCH, 1)
+    if dt is not None:
+        return dt, "reference"
+    return ref_torch.layer_fwd_bwd_seconds(D_MODEL, B_BATCH, 1), "port"
+
+
+REF_SAMPLE = (f"each step = 1 of {S_TOTAL} MC samples x all {B_BATCH} rows x 1 of {N_LAYERS} layers, D={D_MODEL}, forward + backward, "
+              f"on the host cores; rows/s = {B_BATCH} layer-rows / step time")
+
+
+def cpu_layer_baseline(budget_s: float = 15.0):
+    import torch
+    torch.set_num_threads(host_threads())
+    reference_layer_step_seconds()  # warm-up (allocator, H cache of the matmul path)
+    t_used, done, kind = 0.0, 0, "port"
+    while t_used < budget_s and done < 8:
+        dt, kind = reference_layer_step_seconds()
+        t_used += dt
         done += 1
-    return {"value": rows * done / t_used, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{done} MC sample(s) x {rows} of {B_BATCH} rows x 1 of {N_LAYERS} layers, D={D_MODEL}, "
-                      f"fwd+bwd, torch CPU restatement of the reference layer as written (oracle/ref_torch.py); "
-                      f"{t_used:.1f} s of CPU work"}
+    what = ("the reference's own WHVILinear (oracle/_ref/refpy: src/weights.py:66-93 byte-compiled unmodified)" if kind == "reference"
+            else "torch CPU restatement of the reference layer as written (oracle/ref_torch.py)")
+    return {"value": B_BATCH * done / t_used, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{done} step(s); {REF_SAMPLE}; {what}; {t_used:.1f} s of CPU work"}
 
 
-def cpu_fwht_baseline(threads: int):
+def cpu_fwht_baseline():
     """The reference's own C++ CPU FWHT (oracle/_ref/fwht_cpp.so, compiled unmodified from
     src/fwht/cpp/fwht.cpp) if it travelled, else the C oracle port; D = 1024, 2^18 elements."""
-    import numpy as np
     import torch
     from oracle import ref_torch
-    torch.set_num_threads(threads)
+    torch.set_num_threads(host_threads())
     D, rows = 1024, 256
     mod = ref_torch.fwht_cpp_module()
     x = torch.randn(rows, D)
@@ -134,15 +165,14 @@ def cpu_fwht_baseline(threads: int):
         O.fwht(a)
         dt = time.perf_counter() - t0
         kind = "port"
-    return {"gbs": 8.0 * rows * D / dt / 1e9, "kind": kind, "D": D, "rows": rows, "cores": threads, "seconds": dt}
+    return {"gbs": 8.0 * rows * D / dt / 1e9, "kind": kind, "D": D, "rows": rows, "cores": torch.get_num_threads(), "seconds": dt}
 
 
 def gpu_fwht_reference_baseline(fwht_ours, dev, log2n: int = 28):
     """The reference's own CUDA FWHT (src/fwht/cuda, recompiled for sm_100a into oracle/_ref/fwht_cuda.so
     with the torch-API renames of SURVEY F3 only) timed on this GPU next to this repo's kernel, same
     inputs, through its public entry (which clones its input, fwht_cuda.cpp:11).  D <= 2^12 only: its
-    launch shape is invalid beyond.  Baseline leg: the one other place bench.py may execute
-    oracle/."""
+    launch shape is invalid beyond.  Baseline leg: one of the places bench.py may execute oracle/."""
     import torch
     from oracle import ref_torch
     mod = ref_torch.fwht_cuda_module()
@@ -177,27 +207,23 @@ def gpu_fwht_reference_baseline(fwht_ours, dev, log2n: int = 28):
 
 # --------------------------------------------------------------------------- reference arm
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    threads = os.cpu_count() or 1
+    use_all_host_threads()
     import torch
-    from oracle import ref_torch
-    torch.set_num_threads(threads)
-    rows = 512
+    torch.set_num_threads(host_threads())
+    kind = "port"
     for _ in range(args.warmup):
-        ref_torch.layer_fwd_bwd_seconds(D_MODEL, rows, 1)
+        reference_layer_step_seconds()
     t = 0.0
     for _ in range(args.steps):
-        t += ref_torch.layer_fwd_bwd_seconds(D_MODEL, rows, 1)
-    value = rows * args.steps / t
-    sample = (f"each step = 1 MC sample x {rows} of {B_BATCH} rows x 1 of {N_LAYERS} layers, D={D_MODEL}, fwd+bwd, "
-              f"torch CPU restatement of the reference layer path as written (src/weights.py:66-93)")
+        dt, kind = reference_layer_step_seconds()
+        t += dt
+    value = B_BATCH * args.steps / t
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(CONFIG),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": REF_SAMPLE},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -212,7 +238,8 @@ def run_ours(args):
     import whvi_b200 as W
     from whvi_b200 import functional as WF
     from whvi_b200 import fwht_
-    from whvi_b200.distributed import FlatGradAllReduce, shard_samples
+    from whvi_b200.distributed import shard_samples
+    from whvi_b200.optim import FlatAdam, FlatParams
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,7 +249,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    _, S_local = shard_samples(S_TOTAL, rank, world)
+    first_sample, S_local = shard_samples(S_TOTAL, rank, world)
     assert S_TOTAL % world == 0
     chunk = min(args.chunk, S_local)
     assert S_local % chunk == 0
@@ -232,24 +259,36 @@ def run_ours(args):
     torch.manual_seed(0)  # parameters identical on every rank
     model = W.WHVIRegression([W.WHVILinear(D, D), torch.nn.ReLU(), W.WHVILinear(D, D), torch.nn.ReLU(),
                               W.WHVILinear(D, D)], train_samples=chunk).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    grad_allreduce = FlatGradAllReduce(model.parameters())
+    # all parameters / gradients as views of two flat buffers: one memset, ONE all-reduce without pack/unpack
+    # kernels, ONE fused Adam kernel per step (whvi_b200/optim.py)
+    flat = FlatParams(model.parameters())
+    opt = FlatAdam(flat, lr=1e-3)
     gen = torch.Generator().manual_seed(1)  # the same minibatch on every rank (MC-sample sharding)
     x_host = torch.randn(B, D, generator=gen).pin_memory()
     y_host = torch.randn(B, D, generator=gen).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
-    torch.manual_seed(100 + rank)  # each rank draws its own eps shard
     scale = 1.0 / (n_chunks * world)
+    blocks = [layer.square_blocks()[0] for layer in model._whvi_layers()]
 
-    def step(x, y):
+    def fwd_bwd(x, y, eps=None):
+        """Forward + ELBO + backward over this rank's sample shard in chunks; returns this rank's share of the loss.
+        eps: per layer a (S_TOTAL, D) noise tensor to take this rank's rows from (verification), else fresh draws."""
         total = None
-        for _ in range(n_chunks):
+        for c in range(n_chunks):
+            if eps is not None:
+                lo = first_sample + c * chunk
+                for blk, e in zip(blocks, eps):
+                    blk.inject_eps(e[lo:lo + chunk])
             loss = model.loss(x, y, n=B) * scale
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
-        grad_allreduce()  # one flat NCCL all-reduce of all parameter gradients (no-op at N = 1)
+        return total
+
+    def step(x, y):
+        total = fwd_bwd(x, y)
+        flat.all_reduce()  # one NCCL all-reduce on the flat gradient buffer (no-op at N = 1)
         opt.step()
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         return total
 
     def barrier():
@@ -270,12 +309,30 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # ---- verification step (before any training step: same parameters for every N): one GLOBAL noise tensor per
+    # layer from a fixed seed, rank r takes sample rows [r S/N, (r+1) S/N); the summed loss and a checksum of the
+    # all-reduced gradient must agree across N = 1, 2, 4, 8 up to fp32 summation order
+    geps = torch.Generator().manual_seed(4242)
+    eps_global = [torch.randn(S_TOTAL, D, generator=geps).to(dev) for _ in blocks]
+    opt.zero_grad()
+    check_loss = fwd_bwd(x_dev, y_dev, eps=eps_global).clone()
+    flat.all_reduce()
+    if world > 1:
+        dist.all_reduce(check_loss)
+    gcheck = flat.grad.double()
+    wvec = torch.cos(torch.arange(gcheck.numel(), device=dev, dtype=torch.float64) * 0.37)
+    check = {"loss": float(check_loss), "grad_l2": float(gcheck.norm()), "grad_dot_cos": float((gcheck * wvec).sum()),
+             "note": "one step on fixed global eps (seed 4242), before training; must agree across n_gpus to ~1e-5 relative"}
+    opt.zero_grad()
+    del eps_global, gcheck, wvec
+
     # ---- warm-up, then the device-resident timed region -----------------------------------
+    torch.manual_seed(100 + rank)  # timed steps: each rank draws its own eps shard
     for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
     WF.LAUNCH_COUNTS.clear()
-    WF.EVENT_SINK = {"whvi_layer_bwd_fused_f32": [], "whvi_layer_bwd_scaled_f32": [], "whvi_layer_fwd_fused_f32": [],
-                     "whvi_layer_loss_f32": []}
+    timed_calls = ("whvi_layer_bwd_fused_f32", "whvi_layer_bwd_scaled_f32", "whvi_layer_fwd_fused_f32", "whvi_layer_loss_f32")
+    WF.EVENT_SINK = {k: [] for k in timed_calls}
     with ClockSampler(local_rank) as clk:
         ms_total = timed(lambda: step(x_dev, y_dev), args.steps)
     sink, WF.EVENT_SINK = WF.EVENT_SINK, None
@@ -285,106 +342,126 @@ def run_ours(args):
     value = rows_per_step / (ms_step * 1e-3)
 
     # ---- end to end: pinned host inputs in, loss out, every step ---------------------------
-    # Every step's x/y are copied from pinned host memory (a fresh H2D copy per step) and the
-    # loss is read back to the host; the copy of step i+1 runs on a side stream while step i
-    # computes (whvi_b200.utils.DevicePrefetcher), as a data loader would do it.
+    # Every step's x/y are copied from pinned host memory (a fresh H2D copy per step; N > 1: each rank copies 1/N of the
+    # rows over its own PCIe link and the slices are all-gathered over NVLink) on a side stream while the previous step
+    # computes (whvi_b200.utils.DevicePrefetcher), and every step's loss is copied to pinned host memory asynchronously:
+    # the host reads loss i after it has launched step i+1, so the read-back never drains the GPU.
     from whvi_b200.utils import DevicePrefetcher
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
 
-    # N > 1: every rank needs the full minibatch (the ranks shard MC samples, not rows).  Each rank
-    # copies 1/N of the rows from pinned host memory over its own PCIe link and the slices are
-    # all-gathered over NVLink, all on the prefetch stream while the previous step computes: the
-    # whole job reads the minibatch from host memory once per step.
     def e2e_run(steps):
-        losses = []
-        for x, y in DevicePrefetcher(((x_host, y_host) for _ in range(steps)), dev, shard_over_ranks=True):
-            losses.append(float(step(x, y).item()))
+        losses, pending = [], None
+        for i, (x, y) in enumerate(DevicePrefetcher(((x_host, y_host) for _ in range(steps)), dev, shard_over_ranks=True)):
+            total = step(x, y)
+            loss_host[i % 2].copy_(total, non_blocking=True)
+            loss_ready[i % 2].record()
+            if pending is not None:
+                loss_ready[pending].synchronize()
+                losses.append(float(loss_host[pending]))
+            pending = i % 2
+        if pending is not None:
+            loss_ready[pending].synchronize()
+            losses.append(float(loss_host[pending]))
         return losses
 
     e2e_run(2)
-    ms_e2e = timed(lambda: e2e_run(args.steps), 1) / args.steps
+    e2e_losses = []
+    ms_e2e = timed(lambda: e2e_losses.extend(e2e_run(args.steps)), 1) / args.steps
     e2e_value = rows_per_step / (ms_e2e * 1e-3)
+    assert len(e2e_losses) == args.steps and all(l == l for l in e2e_losses)
 
-    # ---- roofline of the dominant kernel (fused backward) from events inside the timed region
+    # ---- roofline per kernel position, from CUDA events recorded around the calls inside the timed region -------------
     peak, peak_src = measured_peaks()
-    bwd_ms = [a.elapsed_time(b) for a, b in sink["whvi_layer_bwd_fused_f32"] + sink["whvi_layer_bwd_scaled_f32"]]
-    fwd_ms = [a.elapsed_time(b) for a, b in sink["whvi_layer_fwd_fused_f32"]]
-    loss_ms = [a.elapsed_time(b) for a, b in sink["whvi_layer_loss_f32"]]
     rows_per_launch = chunk * B
-    bwd_avg = sum(bwd_ms) / len(bwd_ms)
-    fwd_avg = sum(fwd_ms) / len(fwd_ms)
-    bwd_gbs = 12.0 * D * rows_per_launch / (bwd_avg * 1e-3) / 1e9
-    fwd_gbs = 8.0 * D * rows_per_launch / (fwd_avg * 1e-3) / 1e9
-    traffic = None  # DRAM bytes per launch of that kernel, from the committed ncu --set full capture
-    tp = ROOT / "profiles" / "r01_bwd_traffic.json"
-    if tp.exists():
-        try:
-            traffic = json.loads(tp.read_text())["dram_bytes_per_row"] * rows_per_launch
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "layer_bwd_tma_kernel (+ layer_bwd_reduce_{slabs,fold}_kernel)", "achieved": bwd_gbs, "peak": peak,
-                "unit": "GB/s", "frac": bwd_gbs / peak, "frac_of_8TBs_nominal": bwd_gbs / 8000.0, "traffic": traffic,
-                "traffic_source": "profiles/r01_bwd_traffic.json (ncu dram__bytes_read+write per row x rows per launch)",
-                "algorithmic_bytes_per_launch": 12.0 * D * rows_per_launch,
-                "peak_source": peak_src, "algorithmic_bytes_per_row": 12 * D, "rows_per_launch": rows_per_launch,
-                "avg_launch_ms": bwd_avg, "launches_timed": len(bwd_ms),
-                "share_of_step": sum(bwd_ms) / ms_total,
-                "fwd_kernel": {"achieved": fwd_gbs, "frac": fwd_gbs / peak, "avg_launch_ms": fwd_avg,
-                               "algorithmic_bytes_per_row": 8 * D, "share_of_step": sum(fwd_ms) / ms_total}}
-    if loss_ms:  # fused last layer (forward + MNLL residual + backward in one pass: x in, dx out)
-        loss_avg = sum(loss_ms) / len(loss_ms)
-        loss_gbs = 8.0 * D * rows_per_launch / (loss_avg * 1e-3) / 1e9
-        roofline["loss_kernel"] = {"kernel": "layer_loss_kernel (+ layer_bwd_reduce_{slabs,fold}_kernel)", "achieved": loss_gbs,
-                                   "frac": loss_gbs / peak, "avg_launch_ms": loss_avg, "algorithmic_bytes_per_row": 8 * D,
-                                   "share_of_step": sum(loss_ms) / ms_total,
-                                   "note": "replaces a forward (8 B/elt) + backward (12 B/elt) pair of the last layer"}
 
+    def position(calls, tag, alg_bytes_per_row, dram_note):
+        ms = [a.elapsed_time(b) for name in calls for a, b, t in sink[name] if t == tag]
+        if not ms:
+            return None
+        avg = sum(ms) / len(ms)
+        gbs = alg_bytes_per_row * rows_per_launch / (avg * 1e-3) / 1e9
+        return {"achieved": gbs, "frac": gbs / peak, "frac_of_8TBs_nominal": gbs / 8000.0, "avg_launch_ms": avg, "launches_timed": len(ms),
+                "algorithmic_bytes_per_row": alg_bytes_per_row, "share_of_step": sum(ms) / ms_total, "expected_dram_bytes_per_row": dram_note}
+
+    bwd_calls = ("whvi_layer_bwd_fused_f32", "whvi_layer_bwd_scaled_f32")
+    shared = f"{4 * D} + {4 * D}/{chunk}: the (B,D) input block is shared by the {chunk} samples of a launch and served by L2"
+    pos = {
+        "bwd_layer2 (distinct x, dx written)": position(bwd_calls, "distinct_x", 12 * D, f"{12 * D} (x, dy in; dx out)"),
+        "bwd_layer1 (shared x, no dx)": position(bwd_calls, "shared_x/nodx", 12 * D, shared + "; dy in, no dx"),
+        "fwd_layer1 (shared x)": position(("whvi_layer_fwd_fused_f32",), "shared_x", 8 * D, shared + "; y out"),
+        "fwd_layer2 (distinct x)": position(("whvi_layer_fwd_fused_f32",), "distinct_x", 8 * D, f"{8 * D} (x in, y out)"),
+        "loss_layer3 (fwd + MNLL + bwd in one kernel)": position(("whvi_layer_loss_f32",), "distinct_x", 8 * D,
+                                                                  f"{8 * D} (x in, dx out; the target is L2-resident)"),
+    }
+    dom = pos["bwd_layer2 (distinct x, dx written)"]
+    roofline = {"bound": "hbm", "kernel": "layer_bwd_tm_kernel (+ layer_bwd_reduce_{slabs,fold}_kernel) at the layer-2 position: "
+                                          "per-sample x and dy in, dx out",
+                "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "frac_of_8TBs_nominal": dom["frac_of_8TBs_nominal"], "traffic": None,
+                "traffic_note": "not measured in-run (needs ncu); profiles/r02_ncu_*.txt holds dram__bytes of the same kernel and shape",
+                "algorithmic_bytes_per_launch": 12.0 * D * rows_per_launch, "peak_source": peak_src,
+                "algorithmic_bytes_per_row": 12 * D, "rows_per_launch": rows_per_launch, "avg_launch_ms": dom["avg_launch_ms"],
+                "launches_timed": dom["launches_timed"], "share_of_step": dom["share_of_step"], "positions": pos}
+    lk = pos["loss_layer3 (fwd + MNLL + bwd in one kernel)"]
+    if lk:
+        roofline["loss_kernel"] = dict(lk, kernel="layer_loss_tm_kernel (+ reductions)",
+                                       note="replaces a forward (8 B/elt) + backward (12 B/elt) pair of the last layer")
+    f2 = pos["fwd_layer2 (distinct x)"]
+    if f2:
+        roofline["fwd_kernel"] = dict(f2, kernel="layer_fwd_kernel at the layer-2 position")
     # whole step against the same roofline: SURVEY 8d's 20*D bytes per (sample, row, layer) over all ranks
     step_bytes = 20.0 * D * S_TOTAL * B * N_LAYERS
     step_gbs = step_bytes / (ms_step * 1e-3) / 1e9
     roofline["whole_step"] = {"algorithmic_bytes_per_step": step_bytes, "achieved": step_gbs, "unit": "GB/s",
                               "frac": step_gbs / (peak * world), "n_gpus": world,
-                              "note": "fwd 8*D + bwd 12*D bytes per (sample, row, layer); the fused last layer and the "
-                                      "shared first-layer input move fewer bytes than this yardstick"}
+                              "note": "SURVEY 8d yardstick: fwd 8*D + bwd 12*D bytes per (sample, row, layer); the fused last layer, "
+                                      "the shared first-layer input and the skipped first-layer dx move fewer bytes than this"}
+
+    # ---- FWHT GB/s sweep (second half of BASELINE.json's metric) on every rank: rows sharded, no collective; 2^28
+    # elements = 1 GiB in + 1 GiB out per rank; aggregate = N x bytes / max-over-ranks time
+    n = 1 << 28
+    xf, yf = torch.randn(n, device=dev), torch.empty(n, device=dev)
+    fw = []
+    for k in range(6, 16):
+        Dk = 1 << k
+        xv, yv = xf.view(n // Dk, Dk), yf.view(n // Dk, Dk)
+        for _ in range(3):
+            fwht_(xv, out=yv)
+        ms = timed(lambda: fwht_(xv, out=yv), 10)
+        gbs = world * 8.0 * n * 10 / (ms * 1e-3) / 1e9
+        fw.append({"D": Dk, "gbs": round(gbs, 1), "frac_of_measured": round(gbs / (peak * world), 4),
+                   "frac_of_8TBs_nominal": round(gbs / (8000.0 * world), 4)})
+    del xf, yf
+
+    # ---- MC predictive evaluation (BASELINE config 5) over all ranks
+    ev = None
+    if not args.no_eval:
+        from tools.bench_eval import run_eval
+        ev = run_eval(dev, rank, world, inputs=args.eval_inputs)
 
     out = None
     if rank == 0:
-        # ---- FWHT GB/s sweep (second half of BASELINE.json's metric), 2^28 elements = 1 GiB in + out
-        n = 1 << 28
-        xf, yf = torch.randn(n, device=dev), torch.empty(n, device=dev)
-        fw = []
-        for k in range(6, 16):
-            Dk = 1 << k
-            xv, yv = xf.view(n // Dk, Dk), yf.view(n // Dk, Dk)
-            for _ in range(3):
-                fwht_(xv, out=yv)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(10):
-                fwht_(xv, out=yv)
-            b.record()
-            b.synchronize()
-            gbs = 8.0 * n * 10 / (a.elapsed_time(b) * 1e-3) / 1e9
-            fw.append({"D": Dk, "gbs": round(gbs, 1), "frac_of_measured": round(gbs / peak, 4),
-                       "frac_of_8TBs_nominal": round(gbs / 8000.0, 4)})
-        del xf, yf
-        threads = os.cpu_count() or 1
-        cpu = cpu_layer_baseline(threads) if not args.no_cpu_baseline else None
-        cpu_f = cpu_fwht_baseline(threads) if not args.no_cpu_baseline else None
-        gpu_f = gpu_fwht_reference_baseline(fwht_, dev) if not args.no_cpu_baseline else None
+        cpu = cpu_f = gpu_f = None
+        if world == 1 and not args.no_cpu_baseline:  # CPU legs at N = 1 only: no other ranks spinning on the host cores
+            cpu = cpu_layer_baseline()
+            cpu_f = cpu_fwht_baseline()
+            gpu_f = gpu_fwht_reference_baseline(fwht_, dev)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": WORKLOAD, "D": D, "B": B, "S": S_TOTAL, "layers": N_LAYERS,
-                          "rows_counted": "S*B*layers per step", "parallelism": f"mc-sample-shard x{world}",
-                          "samples_per_launch": chunk, "l2": f"inputs larger than L2 ({chunk * B * D * 4 / 2**30:.0f} GiB activations per launch)",
-                          "step": "fwd + MNLL + KL + bwd + grad all-reduce (N>1) + Adam",
-                          "fusion": "ReLU folded into the layer kernels; last layer fwd+MNLL+bwd in one kernel"},
+               "config": dict(CONFIG, rows_counted="S*B*layers per step", parallelism=f"mc-sample-shard x{world}",
+                              samples_per_launch=chunk,
+                              l2=f"inputs larger than L2 ({chunk * B * D * 4 / 2**30:.0f} GiB activations per launch)",
+                              step="fwd + MNLL + KL + bwd + flat grad all-reduce (N>1) + fused Adam",
+                              fusion="ReLU folded into the layer kernels; last layer fwd+MNLL+bwd in one kernel"),
                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
-                       "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4},
-               "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-               "fwht": {"elements": n, "unit": "GB/s", "sweep": fw, "cpu_baseline": cpu_f, "ref_cuda_baseline": gpu_f},
-               "clocks": clk.summary()}
+                       "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
+                       "last_loss": e2e_losses[-1]},
+               "check": check, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+               "fwht": {"elements_per_gpu": n, "unit": "GB/s", "n_gpus": world, "scaling": "weak (rows sharded, no collective)",
+                        "sweep": fw, "cpu_baseline": cpu_f, "ref_cuda_baseline": gpu_f},
+               "eval": ev, "clocks": clk.summary()}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -400,9 +477,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=32, help="MC samples per kernel launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--eval-inputs", type=int, default=0, help="inputs of the config-5 evaluation leg (0: a bounded default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        use_all_host_threads()  # the CPU-baseline legs of a single-process run use every host core
     return run_ours(args)
 
 

@@ -125,6 +125,7 @@ WHVI_API int whvi_layer_bwd_f32(const float* x, int64_t x_sample_stride, const f
 #define WHVI_LAYER_RELU_OUT 1
 #define WHVI_LAYER_FROM_T2 2
 #define WHVI_LAYER_RELU_IN 1
+#define WHVI_LAYER_ACCUMULATE 4   /* whvi_layer_moments_f32: add to the existing contents of sum_y / sum_y2 */
 WHVI_API int whvi_layer_fwd_partials(int64_t S, int64_t B, int64_t D, int64_t* count);
 WHVI_API int whvi_layer_fwd_fused_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1,
                                       const float* s2, const float* bias, float* y, int64_t S, int64_t B, int64_t D,
@@ -148,7 +149,9 @@ WHVI_API int whvi_layer_bwd_scaled_f32(const float* x, int64_t x_sample_stride, 
  * pass over x (the predictions never touch HBM):
  *   y_hat = s1*H(g[s]*H(s2*x)) (+bias);  r = y_hat - target (target (B,D), shared by the samples)
  *   sq_partials[i], i < sq_count: partial sums of r^2 (their sum is the data term of
- *       GaussianLikelihood.mnll_batch_estimate, src/likelihoods.py:18-29)
+ *       GaussianLikelihood.mnll_batch_estimate, src/likelihoods.py:18-29).  The caller ZERO-FILLS the array:
+ *       sq_count is an upper bound over the kernel variants (with / without bias), entries a variant does
+ *       not use stay zero
  *   dx, dg, ds1, ds2, dbias: the layer's gradients for the upstream gradient dy = r, i.e. for a
  *       unit coefficient; the caller multiplies by 2 * dLoss/d(sum r^2) (the small vectors
  *       directly, dx through whvi_layer_bwd_scaled_f32 of the previous layer).
@@ -196,6 +199,20 @@ WHVI_API int whvi_reparam_bwd_f32(const float* rho, const float* eps, const floa
  */
 WHVI_API int whvi_mc_moments_f32(const float* y, float* sum_y, float* sum_y2, int64_t S, int64_t n, int accumulate,
                                  whvi_stream_t stream);
+/*
+ * The same two sums WITHOUT the (S, B, D) predictions ever existing (8192 <= D <= 32768; BASELINE config 5): the layer
+ * forward over all S samples of the call with the reduction fused in -- one CTA per input row loops over the samples
+ * and keeps sum_s t4 and sum_s t4^2 (t4 = H(g_s * t2)) in tensor memory; s1 and bias are applied once per row in
+ * closed form.  HBM traffic: each input row once, 8*D bytes of sums per row.
+ *   x: (B, D) shared by all samples (x_sample_stride = 0) or (S, B, D) (x_sample_stride = B*D);
+ *   flags & WHVI_LAYER_FROM_T2: x holds t2 = H(s2 * x) already (shared input only; sample-independent by linearity,
+ *       one whvi_fwht_f32 per input chunk), so one transform per (sample, row) pair is left;
+ *   flags & WHVI_LAYER_ACCUMULATE: sum_y / sum_y2 are added to (sample chunks, or per-rank partial sums).
+ * sum_y2 may be NULL; bias may be NULL; g: (S, D).
+ */
+WHVI_API int whvi_layer_moments_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1, const float* s2,
+                                    const float* bias, float* sum_y, float* sum_y2, int64_t S, int64_t B, int64_t D,
+                                    int flags, whvi_stream_t stream);
 /*
  * The same reduction with separate inputs and outputs and a sample stride (so `y` may be a block of
  * rows of a larger (S, B, D) tensor):  out_sum_y[i] = in_sum_y[i] + sum_s y[s*y_sample_stride + i]

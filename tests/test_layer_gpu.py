@@ -186,6 +186,32 @@ def test_predictive_moments_vs_oracle(S, B, D, chunk):
     assert rel_err(oy.cpu().numpy(), y.sum(0)) < TOL and rel_err(oy2.cpu().numpy(), (y * y).sum(0)) < TOL
 
 
+@pytest.mark.parametrize("S,B,D", [(5, 3, 8192), (4, 2, 16384), (7, 3, 32768), (1, 1, 8192)])
+@pytest.mark.parametrize("mode", ["from_t2", "shared", "per_sample"])
+def test_fused_layer_moments_vs_oracle(S, B, D, mode):
+    """whvi_layer_moments_f32: sum_s y and sum_s y^2 with the running sums kept in tensor memory (no prediction in
+    HBM), against the fp64 oracle's explicit predictions; with/without bias, overwrite and accumulate."""
+    from whvi_b200 import functional as F
+    from whvi_b200.fwht import fwht_
+    rng = np.random.default_rng(D + 31 * S + len(mode))
+    x = rng.standard_normal((S, B, D) if mode == "per_sample" else (B, D))
+    g, s1, s2, bias = rng.standard_normal((S, D)), rng.standard_normal(D), rng.standard_normal(D), rng.standard_normal(D)
+    y = O.layer_fwd(x, g, s1, s2, bias)
+    xin = fwht_(t(x) * t(s2)) if mode == "from_t2" else t(x)
+    sy, sy2 = torch.full((B, D), 7.0, device=dev()), torch.full((B, D), -3.0, device=dev())
+    F.layer_moments_raw(xin, t(g), t(s1), t(s2), t(bias), sy, sy2, from_t2=mode == "from_t2")
+    assert rel_err(sy.cpu().numpy(), y.sum(0)) < TOL
+    assert rel_err(sy2.cpu().numpy(), (y * y).sum(0)) < TOL
+    # accumulate a second sample chunk without bias on top
+    y2 = O.layer_fwd(x, g[::-1].copy() if mode != "per_sample" else g, s1, s2)
+    g2 = t(g[::-1].copy()) if mode != "per_sample" else t(g)
+    F.layer_moments_raw(xin, g2, t(s1), t(s2), None, sy, sy2, from_t2=mode == "from_t2", accumulate=True)
+    assert rel_err(sy.cpu().numpy(), y.sum(0) + y2.sum(0)) < TOL
+    assert rel_err(sy2.cpu().numpy(), (y * y).sum(0) + (y2 * y2).sum(0)) < TOL
+    with pytest.raises(RuntimeError):
+        F.layer_moments_raw(t(x[..., :4096]), t(g[:, :4096]), t(s1[:4096]), t(s2[:4096]), None, sy[:, :4096].contiguous())
+
+
 def test_backward_without_dx_and_bias_and_determinism():
     from whvi_b200 import functional as F
     x, g, s1, s2, dy, _ = make_case(3, 41, 256, 5)

@@ -8,6 +8,7 @@
 #if WHVI_PADDED_BWD && !defined(WHVI_PADDED)
 #define WHVI_PADDED 1
 #endif
+#include <cstdlib>
 #include "layer_common.cuh"
 #include "tmem.cuh"
 
@@ -46,6 +47,7 @@ struct BwdArgs {
     const float* coef;     // RESID: device scalar
     const float* dy_scale; // optional device scalar: the upstream gradient is dy_scale[0] * dy (deferred
                            // scaling of a producer that computed its dx for a unit loss coefficient)
+    int stagger = 0;       // layer_bwd_tm_kernel: clock cycles by which the CTA's second tile pair starts late
 };
 
 // Stream-role specialised, TMA-staged backward.  Every tile is worked on by a PAIR of thread
@@ -471,7 +473,8 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
 // pairs are independent, so one pair's shared-memory phase overlaps the other's butterflies.
 // TMEM columns per lane (E = 64 floats per thread, H = E / 2), shared by the X/Y thread pair of that lane:
 //   [0,E) g | [E,2E) ds1 (X) | [2E,2E+H) dg lower half (X) | [2E+H,3E) dg upper half (Y) | [3E,4E) ds2 (Y) |
-//   [4E,5E) s2 (Y) | [5E,5E+H) t2 upper half X->Y | [5E+H,6E) dt3 lower half Y->X | [6E,7E) dbias (X)
+//   [4E,5E) s2 (Y) | [5E,5E+H) t2 upper half X->Y | [5E+H,6E) dt3 lower half Y->X | [6E,7E) the same for odd tiles |
+//   [7E,8E) dbias (X)
 // Everything else (bulk-copy staging ring, roles, workspace layout, second-stage reduction) is the kernel above.
 template <int N, int C, int KT, int ROUNDS, bool WANT_DBIAS, bool RESID>
 __global__ void __launch_bounds__(256, 1) layer_bwd_tm_kernel(const BwdArgs p)
@@ -487,10 +490,14 @@ __global__ void __launch_bounds__(256, 1) layer_bwd_tm_kernel(const BwdArgs p)
     static_assert(E == 64 && PAIRS >= 1 && PAIRS * T == 128, "layer_bwd_tm_kernel: 64 floats per thread, 4 warps per role");
     static_assert(ROUNDS == 3 || rounds_needed(N, C, N) <= 2, "2-view kernel needs FIRST+MID to cover all bits");
     static_assert(rounds_needed(N, C, N) <= 3, "FIRST+MID+LAST must cover every tile bit");
+    // the exchange columns are double-buffered by tile parity (one pair barrier per tile instead of two)
     constexpr uint32_t COL_G = 0, COL_A1 = E, COL_AGX = 2 * E, COL_AGY = 2 * E + H, COL_A2 = 3 * E, COL_S2 = 4 * E,
-                       COL_ST2 = 5 * E, COL_SD3 = 5 * E + H, COL_AB = 6 * E;
+                       COL_ST2 = 5 * E, COL_SD3 = 5 * E + H, COL_AB = 7 * E,   // ST2/SD3: + E * (tile & 1)
+                       COL_PR = 7 * E;   // !WANT_DBIAS: this role's input-side parameter vector lives here, not in registers
+    constexpr bool PR_TMEM = !WANT_DBIAS && !RESID;   // 64 fewer live registers: room for the scheduler to overlap the butterfly stages
     extern __shared__ float4 smem4[];
     __shared__ uint64_t full_bar[PAIRS][NS], empty_bar[PAIRS][NS];
+    __shared__ uint64_t reads_done[PAIRS][2];   // per role: every thread has read the previous transposition out of the scratch
     __shared__ uint32_t tmem_base_smem;
     float* smem = reinterpret_cast<float*>(smem4);
     const int k = KT >= 0 ? KT : p.k;
@@ -506,6 +513,7 @@ __global__ void __launch_bounds__(256, 1) layer_bwd_tm_kernel(const BwdArgs p)
                 mbar_init(&full_bar[q][st], 1);
                 mbar_init(&empty_bar[q][st], 2 * T);
             }
+        for (int q = 0; q < PAIRS; ++q) mbar_init(&reads_done[q][0], T), mbar_init(&reads_done[q][1], T);
         mbar_fence_init();
     }
     if (threadIdx.x < 32) tm_alloc(&tmem_base_smem, 512);
@@ -553,27 +561,35 @@ __global__ void __launch_bounds__(256, 1) layer_bwd_tm_kernel(const BwdArgs p)
                                        : transpose_writer_base<N, C, V_MID, V_FIRST>(tid);
     const uint32_t mid_logical = view_tid_logical(view_mid(N, C), tid);
 
+    int it_now = 0;
+    const uint32_t col_acc = role ? COL_A2 : COL_A1;          // this role's end-product running sum
     auto to_mid = [&](float (&v)[E]) {
         if constexpr (ROUNDS == 3) {
             transform_in<N, C, KT, T, true>(v, scratch, scratch, tid, bar_role, k, wb_fm, wb_ml);
         } else {
             bfly_round<N, C, KT, SEQ2_IN, 0>(v, k);
-            role_sync<T>(bar_role);   // earlier reads of the buffer are done
+            // the previous tile's second transposition has been read out by every thread of the role: an mbarrier
+            // they arrived on right after those reads (a whole end-product section ago), not a blocking barrier
+            if (it_now > 0) mbar_wait(&reads_done[pair][role], (it_now - 1) & 1);
             transpose_write<N, C, V_FIRST, V_MID>(v, scratch, wb_fm);
             role_sync<T>(bar_role);
             transpose_read<C>(v, scratch, tid);
             bfly_round<N, C, KT, SEQ2_IN, 1>(v, k);
         }
     };
-    auto from_mid = [&](float (&v)[E]) {
+    auto from_mid = [&](float (&v)[E], float* acc_lo) {
         if constexpr (ROUNDS == 3) {
             transform_out<N, C, KT, T, true>(v, scratch, scratch, tid, bar_role, k, wb_lm, wb_mf);
+            tm_ld32(acc_lo, tm + col_acc);
         } else {
             bfly_round<N, C, KT, SEQ2_OUT, 0>(v, k);
-            role_sync<T>(bar_role);
+            // no barrier before the write: the pair barrier of the half-stream exchange lies between the first
+            // transposition's reads and this write
             transpose_write<N, C, V_MID, V_FIRST>(v, scratch, wb_mf);
             role_sync<T>(bar_role);
             transpose_read<C>(v, scratch, tid);
+            mbar_arrive(&reads_done[pair][role]);
+            tm_ld32(acc_lo, tm + col_acc);   // the end product's first running-sum chunk: in flight during the butterflies
             bfly_round<N, C, KT, SEQ2_OUT, 1>(v, k);
         }
     };
@@ -680,26 +696,40 @@ __global__ void __launch_bounds__(256, 1) layer_bwd_tm_kernel(const BwdArgs p)
     // 32 KB instruction cache -- "no instruction" was the top stall reason (22% of samples, profiles/r02_bwd_notes.md).
     //   X: v = s2 * x  -> t2  -> t4,   end product ds1 += dy * t4 (dbias += dy)
     //   Y: v = s1 * dy -> dt3 -> dt1,  end product ds2 += x * dt1, dx = s2 * dt1
-    float pr[E];   // this role's input-side parameter vector: X s2, Y s1 (FIRST-view order)
+    float pr[PR_TMEM ? 1 : E];   // this role's input-side parameter vector: X s2, Y s1 (FIRST-view order)
     {
+        // the upstream gradient is dy_scale * dy: folded into Y's s1 once (s1 * dy_scale) and into X's sums at the end
+        // (ds1, dbias are linear in dy), not applied to every element of every tile
         const float* __restrict__ pv = role ? p.s1 : p.s2;
+        const float psc = (!RESID && role) ? dysc : 1.f;
+        float w[E];
         for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t, uint32_t coord) {
             constexpr int m = decltype(m_)::value;
-            const float4 w = ldg4(pv + coord);
-            pr[4 * m] = w.x, pr[4 * m + 1] = w.y, pr[4 * m + 2] = w.z, pr[4 * m + 3] = w.w;
+            const float4 q = ldg4(pv + coord);
+            w[4 * m] = psc * q.x, w[4 * m + 1] = psc * q.y, w[4 * m + 2] = psc * q.z, w[4 * m + 3] = psc * q.w;
         });
-    }
-    const uint32_t col_acc = role ? COL_A2 : COL_A1;          // this role's end-product running sum
-    // the upstream gradient is dy_scale * dy: folded into Y's s1 once (s1 * dy_scale) and into X's sums at the end
-    // (ds1, dbias are linear in dy), not applied to every element of every tile
-    if constexpr (!RESID) {
-        if (role) {
+        if constexpr (PR_TMEM) {
+            // Y's s1 * dy_scale goes to COL_PR; X's vector is s2, which Y already keeps in COL_S2 of the same lane
+            if (role) {
+                tm_st32(w, tm + COL_PR), tm_st32(w + 32, tm + COL_PR + 32);
+                tm_wait_st();
+            }
+        } else {
 #pragma unroll
-            for (int i = 0; i < E; ++i) pr[i] *= dysc;
+            for (int i = 0; i < E; ++i) pr[i] = w[i];
         }
     }
+    const uint32_t col_pr = role ? COL_PR : COL_S2;
     if (role == 0 && tid == 0)
         for (int i = 0; i < NS - 1; ++i) issue_tile(i, pair);
+    // The CTA's tile pairs never synchronise with each other, but they start together and do identical work, so
+    // left alone they hit the shared-memory pipe at the same moments (all eight warps store, then all eight
+    // butterfly).  Starting the second pair a fraction of a phase late interleaves one pair's transpositions with the
+    // other's butterflies for the whole launch.
+    if (PAIRS > 1 && pair == 1 && p.stagger > 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.stagger) {}
+    }
 #pragma unroll 1
     for (int it = 0; it < p.iters_per_group; ++it) {
         const int64_t e0 = tile_of(it, pair);
@@ -727,23 +757,41 @@ __global__ void __launch_bounds__(256, 1) layer_bwd_tm_kernel(const BwdArgs p)
                     mul4(v + 4 * m, raw4(stage_x, off), make_float4(pr[4 * m], pr[4 * m + 1], pr[4 * m + 2], pr[4 * m + 3]));
                 });
             }
+        } else if constexpr (PR_TMEM) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float w[32];
+                tm_ld32(w, tm + col_pr + 32 * c);
+                float4 q[8];
+                static_for<0, 8>([&](auto j_) {
+                    constexpr int j = decltype(j_)::value;
+                    q[j] = raw4(src_in, off_f + tile_reg_offset<N, C, V_FIRST>(8 * c + j));
+                });
+                tm_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mul4(v + 32 * c + 4 * j, q[j], make_float4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
+            }
         } else {
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t) {
                 constexpr int m = decltype(m_)::value;
                 mul4(v + 4 * m, raw4(src_in, off), make_float4(pr[4 * m], pr[4 * m + 1], pr[4 * m + 2], pr[4 * m + 3]));
             });
         }
+        it_now = it;
         to_mid(v);  // X: t2, Y: dt3 (middle layout)
         // half-stream exchange through TMEM: X publishes the upper half of t2 and accumulates the lower half of dg,
-        // Y publishes the lower half of dt3 and accumulates the upper half
-        if (role == 0) tm_st32(v + H, tm + COL_ST2); else tm_st32(v, tm + COL_SD3);
+        // Y publishes the lower half of dt3 and accumulates the upper half.  Columns alternate with the tile parity,
+        // so ONE pair barrier per tile suffices: a thread overwrites buffer p two tiles later, after the barrier of the
+        // tile in between, which its partner only reaches after it has read buffer p.
+        const uint32_t par = uint32_t(it & 1) * E;
+        if (role == 0) tm_st32(v + H, tm + COL_ST2 + par); else tm_st32(v, tm + COL_SD3 + par);
         tm_wait_st();
         tm_fence_before();
         bar_wait<2 * T>(bar_pair);
         tm_fence_after();
         {
             float oth[H], ag[H];
-            tm_ld32(oth, tm + (role ? COL_ST2 : COL_SD3));
+            tm_ld32(oth, tm + (role ? COL_ST2 : COL_SD3) + par);
             tm_ld32(ag, tm + (role ? COL_AGY : COL_AGX));
             tm_wait_ld();
             if (role == 0) {
@@ -757,17 +805,16 @@ __global__ void __launch_bounds__(256, 1) layer_bwd_tm_kernel(const BwdArgs p)
             }
             tm_st32(ag, tm + (role ? COL_AGY : COL_AGX));
         }
-        tm_fence_before();
-        bar_wait<2 * T>(bar_pair);  // both half-stashes consumed
-        tm_fence_after();
         apply_g(v);
-        from_mid(v);  // X: t4, Y: dt1 (FIRST layout)
+        float acc0[32];
+        from_mid(v, acc0);  // X: t4, Y: dt1 (FIRST layout); acc0 = running-sum chunk 0, load in flight
         const bool want_dx = p.dx != nullptr;
         float* __restrict__ dxs = p.dx + int64_t(s) * p.sample_elems + e0;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {   // end product, 32 registers at a time
-            float acc[32];
-            tm_ld32(acc, tm + col_acc + 32 * c);
+            float acc1[32];
+            float* acc = c == 0 ? acc0 : acc1;
+            if (c == 1) tm_ld32(acc1, tm + col_acc + 32);
             float4 q[8];
             if constexpr (RESID) {
                 if (role == 0) {
@@ -1026,6 +1073,8 @@ static int launch_bwd_tm_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     if (ctas > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "layer_bwd: grid too large");
     BwdArgs a{c.x, c.xs, c.dy, c.g, c.s1, c.s2, c.dx, c.ws, c.B * D, static_cast<int>(c.S), plan.ctas_per_sample, plan.iters_per_group, k,
               c.relu_in, c.target, c.coef, c.dy_scale};
+    static const int stagger = [] { const char* e = std::getenv("WHVI_BWD_STAGGER"); return e ? std::atoi(e) : 0; }();
+    a.stagger = stagger;
     auto go = [&](auto kernel, int slot) -> int {
         if (int rc = ensure_smem(kernel, smem, smem_ok[slot])) return rc;
         kernel<<<static_cast<unsigned>(ctas), 256, smem, stream>>>(a);

@@ -6,6 +6,27 @@
 
 namespace whvi {
 
+struct LossArgs {
+    const float* x;
+    int64_t x_sample_stride;
+    const float* g;
+    const float* s1;
+    const float* s2;
+    const float* bias;
+    const float* target;
+    float* dx;             // NULL: skip
+    float* ws;
+    float* sq_partials;    // one float per (slab, X warp)
+    int64_t sample_elems;
+    int n_samples;
+    int ctas_per_sample;
+    int iters_per_group;
+    int k;
+    int relu_in;
+};
+
+int launch_layer_loss_tm(const LayerLossCall& c, int64_t D, cudaStream_t stream);  // layer_loss_tm.cu
+
 constexpr int SEQ_IN = seq_pack(V_FIRST, V_MID, V_LAST);
 constexpr int SEQ_OUT = seq_pack(V_LAST, V_MID2, V_FIRST);
 constexpr int SEQ2_IN = seq_pack(V_FIRST, V_MID);

@@ -37,24 +37,6 @@
 
 namespace whvi {
 
-struct LossArgs {
-    const float* x;
-    int64_t x_sample_stride;
-    const float* g;
-    const float* s1;
-    const float* s2;
-    const float* bias;
-    const float* target;
-    float* dx;             // NULL: skip
-    float* ws;
-    float* sq_partials;    // one float per (slab, X warp)
-    int64_t sample_elems;
-    int n_samples;
-    int ctas_per_sample;
-    int iters_per_group;
-    int k;
-    int relu_in;
-};
 
 template <int N, int C, int KT, int PAIRS, int NS, bool SINGLE, int PREG, int ROUNDS, bool HAS_BIAS>
 __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, 1) layer_loss_kernel(const LossArgs p)
@@ -386,6 +368,25 @@ static int launch_loss_cfg(const LayerLossCall& c, int k, cudaStream_t stream)
 int launch_layer_loss(const LayerLossCall& c, int64_t D, cudaStream_t stream)
 {
     const int k = ilog2(D);
+#ifndef WHVI_LOSS_LEGACY   // -DWHVI_LOSS_LEGACY=1: round 1's three-view register-only kernel at D = 2048, 4096 (A/B builds)
+    if ((k == 11 || k == 12) && c.need_ws) {
+        // size query: the caller does not say whether there will be a bias, and the two kernels split the work
+        // differently -> report the larger of each (unused sq_partials entries must be zero: see whvi_b200.h)
+        size_t ws_a = 0, ws_b = 0;
+        int64_t sq_a = 0, sq_b = 0;
+        LayerLossCall q = c;
+        q.need_ws = &ws_a, q.need_sq = &sq_a;
+        if (int rc = launch_layer_loss_tm(q, D, stream)) return rc;
+        q.need_ws = &ws_b, q.need_sq = &sq_b;
+        const int rc = k == 11 ? launch_loss_cfg<11, 5, 11, 2, 3, false, 1, 3>(q, k, stream)
+                               : launch_loss_cfg<12, 5, 12, 1, 3, false, 1, 3>(q, k, stream);
+        if (rc) return rc;
+        *c.need_ws = ws_a > ws_b ? ws_a : ws_b;
+        *c.need_sq = sq_a > sq_b ? sq_a : sq_b;
+        return WHVI_OK;
+    }
+    if ((k == 11 || k == 12) && c.bias == nullptr) return launch_layer_loss_tm(c, D, stream);
+#endif
     if (k >= 7 && k <= 9) return launch_loss_cfg<10, 5, k_family(7, 9), 4, 3, false, 1, 2>(c, k, stream);
     if (k == 10) return launch_loss_cfg<10, 5, 10, 4, 3, false, 1, 2>(c, k, stream);
     if (k == 11) return launch_loss_cfg<11, 5, 11, 2, 3, false, 1, 3>(c, k, stream);

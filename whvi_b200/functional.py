@@ -23,7 +23,7 @@ _LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_fwht_f64": 1, "whvi_layer_fwd_f3
                       "whvi_layer_fwd_fused_f32": 1, "whvi_layer_bwd_fused_f32": 3,
                       "whvi_layer_bwd_scaled_f32": 3, "whvi_layer_loss_f32": 3, "whvi_reparam_f32": 1,
                       "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1, "whvi_mc_moments_f32": 1,
-                      "whvi_mc_moments_strided_f32": 1, "whvi_adam_f32": 1}
+                      "whvi_mc_moments_strided_f32": 1, "whvi_adam_f32": 1, "whvi_layer_moments_f32": 1}
 # When set to a dict {"name": [(start_event, stop_event), ...]}, the named calls are bracketed
 # by CUDA events on the launching stream (bench.py's per-kernel roofline timing).
 EVENT_SINK: dict[str, list] | None = None
@@ -34,8 +34,9 @@ def _count(name: str) -> None:
 
 
 class _Timed:
-    def __init__(self, name: str):
+    def __init__(self, name: str, tag: str = ""):
         self.name = name
+        self.tag = tag   # position of the call in the model (bench.py's per-position roofline): "shared_x", "distinct_x/nodx" ...
         self.on = EVENT_SINK is not None and name in EVENT_SINK
 
     def __enter__(self):
@@ -49,7 +50,7 @@ class _Timed:
     def __exit__(self, *exc):
         if self.on:
             self.b.record()
-            EVENT_SINK[self.name].append((self.a, self.b))
+            EVENT_SINK[self.name].append((self.a, self.b, self.tag))
 
 
 def _stream(device: torch.device) -> int:
@@ -115,7 +116,7 @@ def layer_forward_raw(x, g, s1, s2, bias=None, out=None, relu_out=False, target=
         n = ctypes.c_int64(0)
         _lib.check(L.whvi_layer_fwd_partials(S, B, D, ctypes.byref(n)), "whvi_layer_fwd_partials")
         partials = torch.empty(max(n.value, 1), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device), _Timed("whvi_layer_fwd_fused_f32"):
+    with torch.cuda.device(x.device), _Timed("whvi_layer_fwd_fused_f32", ("shared_x" if xs == 0 else "distinct_x") + ("/from_t2" if from_t2 else "")):
         rc = L.whvi_layer_fwd_fused_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
                                         out.data_ptr(), S, B, D, (1 if relu_out else 0) | (2 if from_t2 else 0),
                                         _ptr(target), _ptr(partials),
@@ -139,6 +140,28 @@ def mc_moments_(y, sum_y, sum_y2=None, accumulate=True):
         rc = _lib.lib().whvi_mc_moments_f32(y.data_ptr(), sum_y.data_ptr(), _ptr(sum_y2), S, n, 1 if accumulate else 0,
                                             _stream(y.device))
     _lib.check(rc, "whvi_mc_moments_f32")
+    return sum_y, sum_y2
+
+
+FUSED_MOMENTS_MIN_D, FUSED_MOMENTS_MAX_D = 8192, 32768
+
+
+def layer_moments_raw(x, g, s1, s2, bias, sum_y, sum_y2=None, from_t2=False, accumulate=False):
+    """sum_y (+)= sum_s y[s], sum_y2 (+)= sum_s y[s]^2 for y[s] = s1 * H(g[s] * H(s2 * x)) + bias over ALL samples of ``g``
+    in ONE kernel that keeps the running sums in tensor memory: no prediction is ever written to HBM
+    (``whvi_layer_moments_f32``; 8192 <= D <= 32768).  ``x``: (B, D) shared or (S, B, D); ``from_t2``: x holds H(s2 * x)."""
+    x, g, s1, s2 = _f32c(x, "x"), _f32c(g, "g"), _f32c(s1, "s1"), _f32c(s2, "s2")
+    S, B, D, xs = _layer_dims(x, g, s1, s2)
+    if bias is not None:
+        bias = _f32c(bias, "bias").reshape(-1)
+    for t, name in ((sum_y, "sum_y"), (sum_y2, "sum_y2")):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != B * D or t.device != x.device):
+            raise RuntimeError(f"{name} must be a contiguous float32 tensor with {B * D} elements on {x.device}")
+    with torch.cuda.device(x.device), _Timed("whvi_layer_moments_f32", "from_t2" if from_t2 else "full"):
+        rc = _lib.lib().whvi_layer_moments_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
+                                               sum_y.data_ptr(), _ptr(sum_y2), S, B, D,
+                                               (2 if from_t2 else 0) | (4 if accumulate else 0), _stream(x.device))
+    _lib.check(rc, "whvi_layer_moments_f32")
     return sum_y, sum_y2
 
 
@@ -196,6 +219,12 @@ def predictive_moments(x, mu, rho, s1, s2, bias=None, n_samples=64, chunk_sample
         sum_y2 = torch.empty((B, D), dtype=torch.float32, device=x.device)
     if hi <= lo:
         sum_y.zero_(), sum_y2.zero_()
+    if FUSED_MOMENTS_MIN_D <= D <= FUSED_MOMENTS_MAX_D and scatter_to is None and hi > lo:
+        # one kernel for all samples: running sums in tensor memory, nothing but the two results goes to HBM
+        e = eps[lo:hi] if eps is not None else torch.randn((hi - lo, D), device=x.device, generator=generator)
+        g = ReparamFunction.apply(mu, rho, e.contiguous())
+        layer_moments_raw(t2, g, s1, s2, bias, sum_y, sum_y2, from_t2=True, accumulate=False)
+        return sum_y, sum_y2, hi - lo
     ybuf = torch.empty((min(chunk_samples, max(hi - lo, 1)), B, D), dtype=torch.float32, device=x.device)
     for s0 in range(lo, hi, chunk_samples):
         s1_ = min(s0 + chunk_samples, hi)
@@ -236,14 +265,14 @@ def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False, relu_in
         if target is not None:
             raise RuntimeError("dy_scale and target are mutually exclusive")
         dy_scale = _f32c(dy_scale, "dy_scale").reshape(1)
-        with torch.cuda.device(dev), _Timed("whvi_layer_bwd_scaled_f32"):
+        with torch.cuda.device(dev), _Timed("whvi_layer_bwd_scaled_f32", ("shared_x" if xs == 0 else "distinct_x") + ("" if want_dx else "/nodx")):
             rc = L.whvi_layer_bwd_scaled_f32(x.data_ptr(), xs, dy.data_ptr(), dy_scale.data_ptr(), g.data_ptr(),
                                              s1.data_ptr(), s2.data_ptr(), _ptr(dx), dg.data_ptr(), ds1.data_ptr(),
                                              ds2.data_ptr(), _ptr(dbias), ws.data_ptr(), ws.numel(), S, B, D,
                                              1 if relu_in else 0, _stream(dev))
         _lib.check(rc, "whvi_layer_bwd_scaled_f32")
         return dx, dg, ds1, ds2, dbias
-    with torch.cuda.device(dev), _Timed("whvi_layer_bwd_fused_f32"):
+    with torch.cuda.device(dev), _Timed("whvi_layer_bwd_fused_f32", ("shared_x" if xs == 0 else "distinct_x") + ("" if want_dx else "/nodx")):
         rc = L.whvi_layer_bwd_fused_f32(x.data_ptr(), xs, dy.data_ptr(), g.data_ptr(), s1.data_ptr(), s2.data_ptr(),
                                         _ptr(dx), dg.data_ptr(), ds1.data_ptr(), ds2.data_ptr(), _ptr(dbias),
                                         ws.data_ptr(), ws.numel(), S, B, D, 1 if relu_in else 0, _ptr(target),
@@ -292,13 +321,13 @@ def layer_loss_raw(x, g, s1, s2, bias, target, want_dx=True, relu_in=False):
     need, nsq = ctypes.c_size_t(0), ctypes.c_int64(0)
     _lib.check(L.whvi_layer_loss_sizes(S, B, D, ctypes.byref(need), ctypes.byref(nsq)), "whvi_layer_loss_sizes")
     ws = _workspace(dev, need.value)
-    sqp = torch.empty(max(nsq.value, 1), dtype=torch.float32, device=dev)
+    sqp = torch.zeros(max(nsq.value, 1), dtype=torch.float32, device=dev)   # an upper bound: unused entries stay zero
     dx = torch.empty((S, B, D), dtype=torch.float32, device=dev) if want_dx else None
     dg = torch.empty((S, D), dtype=torch.float32, device=dev)
     ds1 = torch.empty(D, dtype=torch.float32, device=dev)
     ds2 = torch.empty(D, dtype=torch.float32, device=dev)
     dbias = torch.empty(D, dtype=torch.float32, device=dev) if bias is not None else None
-    with torch.cuda.device(dev), _Timed("whvi_layer_loss_f32"):
+    with torch.cuda.device(dev), _Timed("whvi_layer_loss_f32", ("shared_x" if xs == 0 else "distinct_x") + ("" if want_dx else "/nodx")):
         rc = L.whvi_layer_loss_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
                                    target.data_ptr(), _ptr(dx), dg.data_ptr(), ds1.data_ptr(), ds2.data_ptr(),
                                    _ptr(dbias), sqp.data_ptr(), ws.data_ptr(), ws.numel(), S, B, D,

@@ -193,6 +193,38 @@ class WHVINetwork(nn.Module, WHVI):
                                          f'MNLL = {float(self.current_mnll):.2f}')
         self.eval()
 
+    @torch.no_grad()
+    def predictive_sums(self, X: torch.Tensor, n_samples: int | None = None):
+        """(sum_s y_hat, sum_s y_hat^2, S) over the MC samples for inputs X, each (batch, out) -- the two reductions
+        ``eval_model`` needs (MC mean for the RMSE, ``src/networks.py:131-132``; squared errors for the MNLL,
+        ``src/likelihoods.py:18-29``) WITHOUT the (batch, out, S) prediction tensor when the network ends in a square
+        WHVI layer: that layer runs with the reduction fused in (``functional.layer_moments_raw`` /
+        ``predictive_moments``; SURVEY 8f N1, BASELINE config 5).  Returns None when the last layer is not one."""
+        modules = list(self.sequential.children())
+        if not (self.fuse and modules and self._fusable_square(modules[-1]) and X.dim() == 2 and X.is_cuda):
+            return None
+        S = int(n_samples if n_samples is not None else (self.train_samples if self.training else self.eval_samples))
+        last = modules[-1].weight_submodule
+        head = WHVINetwork.__new__(WHVINetwork)          # the modules before the last layer, same settings
+        nn.Module.__init__(head)
+        head.sequential, head.rng_mode, head.fuse = nn.Sequential(*modules[:-1]), self.rng_mode, self.fuse
+        if self.rng_mode == "reference":
+            raise RuntimeError("predictive_sums draws batched noise; use forward() with rng_mode='reference'")
+        h = head._run(X, S) if len(modules) > 1 else X
+        if h.dim() == 2 or (h.dim() == 3 and h.stride(0) == 0):   # no WHVI layer before: one input block for all samples
+            hh = h if h.dim() == 2 else h[0]
+            sum_y, sum_y2, _ = last.predictive_moments(hh.contiguous(), S)
+            return sum_y, sum_y2, S
+        bias = None if last.bias is None else last.bias.reshape(-1)
+        g = WF.reparam(last.g_mu, last.g_rho, last._draw_eps(S))
+        sum_y = torch.empty(h.shape[1:], dtype=torch.float32, device=h.device)
+        sum_y2 = torch.empty_like(sum_y)
+        if WF.FUSED_MOMENTS_MIN_D <= last.D <= WF.FUSED_MOMENTS_MAX_D:
+            WF.layer_moments_raw(h, g, last.s1, last.s2, bias, sum_y, sum_y2)
+        else:
+            WF.mc_moments_(WF.layer_forward_raw(h, g, last.s1, last.s2, bias), sum_y, sum_y2, accumulate=False)
+        return sum_y, sum_y2, S
+
     def eval_model(self, X_test: torch.Tensor, y_test: torch.Tensor, loss) -> Tuple[float, float]:
         """Test error (``loss(y_pred, y_true)``) and MNLL on test data."""
         self.eval()
@@ -212,4 +244,21 @@ class WHVIRegression(WHVINetwork):
         super().__init__(modules, likelihood=GaussianLikelihood(sigma), **kwargs)
 
     def eval_model(self, X_test: torch.Tensor, y_test: torch.Tensor, loss=_rmse_of_mc_mean) -> Tuple[float, float]:
+        """RMSE of the MC mean and test MNLL (``src/networks.py:101-115``, ``:130-133``).  With the default loss and a
+        network that ends in a square WHVI layer, both come from ``predictive_sums`` -- sum_s y_hat and sum_s y_hat^2
+        reduced inside the last layer's kernel -- so the (batch, out, S) tensor of the reference never exists
+        (BASELINE config 5 is 1M x 32768 x 256 floats).  Any other loss function gets the full prediction tensor."""
+        if loss is _rmse_of_mc_mean and y_test.dim() == 2:
+            self.eval()
+            sums = self.predictive_sums(X_test)
+            if sums is not None and sums[0].shape == y_test.shape:
+                sum_y, sum_y2, S = sums
+                y = y_test.to(torch.float64)
+                mean = sum_y.to(torch.float64) / S
+                rmse = torch.sqrt(((mean - y) ** 2).mean())
+                # sum_{b,i,s} (y - y_hat)^2 = S y^2 - 2 y sum_s y_hat + sum_s y_hat^2
+                sq = (S * y * y - 2.0 * y * sum_y.to(torch.float64) + sum_y2.to(torch.float64)).sum()
+                m, n_out = y_test.shape
+                mnll = self.likelihood.mnll_from_sq_error(sq.to(torch.float32), m=m, n_out=n_out, n_mc=S, n=m)
+                return float(rmse), float(mnll)
         return super().eval_model(X_test, y_test, loss)
