@@ -22,9 +22,10 @@
 
 * ``build_ref_py()`` byte-compiles the reference's own Python modules on the hot path
   (``/root/reference/src/{utils,weights,layers,likelihoods,networks}.py`` and
-  ``src/fwht/{python,cuda}/fwht.py``) UNMODIFIED, from where they lie, into sourceless ``.pyc`` files
-  under ``oracle/_ref/refpy/src/`` (compiled output only -- no reference source text enters the repo
-  or ``oracle/_ref``).  ``oracle/ref_torch.reference_package()`` imports them there (with the
+  ``src/fwht/{python,cuda}/fwht.py``) UNMODIFIED, from where they lie, into bytecode files
+  ``oracle/_ref/refpy/src/**/*.pycode`` (compiled output only -- no reference source text enters the repo
+  or ``oracle/_ref``; the suffix is not ``.pyc`` because the GPU-box snapshot drops ``*.pyc``).
+  ``oracle/ref_torch.reference_package()`` imports them through a small finder (with the
   ``fwht_cuda`` extension stubbed), which is what ``bench.py --impl reference`` and the
   ``cpu_baseline`` leg time on the GPU box: the reference's own layer code, not a restatement.
 
@@ -140,9 +141,9 @@ REF_PY_MODULES = ["utils", "weights", "layers", "likelihoods", "networks", "fwht
 
 
 def build_ref_py(force: bool = False) -> Path | None:
-    """Byte-compile the unmodified reference modules into oracle/_ref/refpy/src/**.pyc (sourceless import)."""
+    """Byte-compile the unmodified reference modules into oracle/_ref/refpy/src/**.pycode (imported by ref_torch's finder)."""
     import py_compile
-    marker = REF_PY_DIR / "src" / "weights.pyc"
+    marker = REF_PY_DIR / "src" / "weights.pycode"
     if not REF_PY_SRC.exists():
         return REF_PY_DIR if marker.exists() else None
     if not force and _newer(marker, *(REF_PY_SRC / f"{m}.py" for m in REF_PY_MODULES)):
@@ -151,7 +152,7 @@ def build_ref_py(force: bool = False) -> Path | None:
         src = REF_PY_SRC / f"{m}.py"
         if not src.exists():
             continue
-        out = REF_PY_DIR / "src" / f"{m}.pyc"
+        out = REF_PY_DIR / "src" / f"{m}.pycode"
         out.parent.mkdir(parents=True, exist_ok=True)
         # dfile: the path recorded in the code object (tracebacks) -- the reference's own path
         # unchecked-hash pyc: validity does not depend on a source file (there is none on the GPU box)

@@ -109,18 +109,56 @@ def fwht_cuda_module():
         return None
 
 
+class _RefBytecodeFinder:
+    """Import ``src`` / ``src.*`` from the bytecode files oracle/build.py:build_ref_py wrote (``*.pycode`` = a standard
+    .pyc image under another suffix).  Packages are the directories; nothing but the compiled reference code is run."""
+
+    def __init__(self, root: Path):
+        self.root = root
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        if name != "src" and not name.startswith("src."):
+            return None
+        rel = self.root.joinpath(*name.split("."))
+        if rel.is_dir():   # package: optional __init__.pycode
+            init = rel / "__init__.pycode"
+            spec = importlib.machinery.ModuleSpec(name, self, origin=str(init if init.exists() else rel), is_package=True)
+            spec.submodule_search_locations = [str(rel)]
+            return spec
+        code = rel.with_suffix(".pycode")
+        if code.exists():
+            return importlib.machinery.ModuleSpec(name, self, origin=str(code))
+        return None
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        import marshal
+        origin = Path(module.__spec__.origin)
+        if origin.is_dir() or not origin.exists():
+            return
+        data = origin.read_bytes()
+        exec(marshal.loads(data[16:]), module.__dict__)   # 16-byte pyc header (magic, flags, hash), then the code object
+
+
 def reference_package():
     """The reference's OWN layer code (oracle/_ref/refpy: its modules byte-compiled unmodified by
-    oracle/build.py:build_ref_py, importable without sources) or None when it did not travel.
-    ``fwht_cuda`` -- imported unconditionally by src/weights.py:8 even on CPU -- is stubbed
-    exactly as tests/golden/make_golden.py does.  Returns the imported ``src.layers`` module."""
+    oracle/build.py:build_ref_py) or None when it did not travel.  ``fwht_cuda`` -- imported unconditionally by
+    src/weights.py:8 even on CPU -- is stubbed exactly as tests/golden/make_golden.py does.
+    Returns the imported ``src.layers`` module."""
     import importlib
+    import importlib.util
     import types
     ref_dir = Path(__file__).resolve().parent / "_ref" / "refpy"
-    if not (ref_dir / "src" / "weights.pyc").exists():
+    if not (ref_dir / "src" / "weights.pycode").exists():
         return None
-    if str(ref_dir) not in sys.path:
-        sys.path.insert(0, str(ref_dir))
+    if importlib.util.MAGIC_NUMBER != (ref_dir / "src" / "weights.pycode").read_bytes()[:4]:
+        return None   # compiled by another interpreter version
+    if not any(isinstance(f, _RefBytecodeFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefBytecodeFinder(ref_dir))
     sys.modules.setdefault("fwht_cuda", types.ModuleType("fwht_cuda"))
     try:
         return importlib.import_module("src.layers")

@@ -32,7 +32,7 @@ def make_case(S, B, D, seed, shared=False):
 
 
 CASES = [(1, 1, 4), (3, 5, 4), (2, 300, 8), (3, 67, 16), (2, 64, 16), (4, 33, 64), (3, 9, 128), (2, 256, 128),
-         (2, 7, 512), (3, 5, 1024), (2, 3, 2048), (2, 5, 4096), (2, 3, 8192), (5, 1, 1024)]
+         (2, 7, 512), (3, 5, 1024), (2, 3, 2048), (2, 5, 4096), (2, 3, 8192), (5, 1, 1024), (2, 3, 16384), (2, 2, 32768)]
 
 
 @pytest.mark.parametrize("S,B,D", CASES)
@@ -86,15 +86,20 @@ def test_fused_flags(S, B, D):
 
 @pytest.mark.parametrize("S,B,D", [(2, 3, 16384), (2, 2, 32768)])
 def test_forward_large_dims(S, B, D):
-    """D = 2^14, 2^15: forward only (MC predictive evaluation, BASELINE config 5)."""
+    """D = 2^14, 2^15 (BASELINE config 5 width): fused forward; the backward there is the multi-pass composition of the
+    FWHT kernel (functional._layer_backward_multipass), with the fused ReLU mask and deferred scale of the fused path."""
     from whvi_b200 import functional as F
     x, g, s1, s2, dy, bias = make_case(S, B, D, D + S)
     y = F.layer_forward_raw(t(x), t(g), t(s1), t(s2), t(bias), relu_out=False)
     assert rel_err(y.cpu().numpy(), O.layer_fwd(x, g, s1, s2, bias)) < TOL
     ys = F.layer_forward_raw(t(x[0]), t(g), t(s1), t(s2))
     assert rel_err(ys.cpu().numpy(), O.layer_fwd(x[0], g, s1, s2)) < TOL
-    with pytest.raises(RuntimeError, match="outside"):
-        F.layer_backward_raw(t(x), t(dy), t(g), t(s1), t(s2))
+    sc = torch.tensor([0.37], device=dev())
+    dx, dg, ds1, ds2, _ = F.layer_backward_raw(t(x), t(dy), t(g), t(s1), t(s2), relu_in=True, dy_scale=sc)
+    rdx, rdg, rds1, rds2 = O.layer_bwd(x, 0.37 * dy, g, s1, s2)
+    assert rel_err(dx.cpu().numpy(), rdx * (x.astype(np.float32) > 0)) < TOL
+    for got, ref in ((dg, rdg), (ds1, rds1), (ds2, rds2)):
+        assert rel_err(got.cpu().numpy(), ref) < TOL
 
 
 @pytest.mark.parametrize("S,B,D", [(2, 5, 4), (3, 7, 64), (2, 9, 128), (2, 5, 1024), (2, 3, 2048), (2, 3, 4096), (2, 3, 8192),

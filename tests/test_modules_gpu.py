@@ -394,3 +394,34 @@ def test_device_prefetcher_short_last_batch():
         assert torch.equal(dx.cpu(), hx) and torch.equal(dy.cpu(), hy)
         seen += 1
     assert seen == len(sizes)
+
+
+@pytest.mark.parametrize("D,layers", [(64, 2), (8192, 1), (8192, 2)])
+def test_eval_model_from_fused_predictive_sums(D, layers):
+    """WHVIRegression.eval_model (src/networks.py:101-115, :130-133) computed from sum_s y_hat and sum_s y_hat^2 reduced
+    inside the last layer (no (batch, out, S) tensor) equals the reference formulation on the full prediction tensor."""
+    from whvi_b200.networks import WHVINetwork
+    torch.manual_seed(D + layers)
+    mods = []
+    for i in range(layers):
+        mods += [W.WHVILinear(D, D, lambda_=2.0, bias=(i == layers - 1))] + ([torch.nn.ReLU()] if i < layers - 1 else [])
+    model = W.WHVIRegression(mods, eval_samples=6, sigma=0.7).to(dev())
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith(("s1", "s2")):
+                p.mul_(100.0 / D ** 0.5)
+            if name.endswith(("g_mu", "bias")):
+                p.copy_(torch.randn_like(p))
+    B = 5
+    x, y = torch.randn(B, D, device=dev()), torch.randn(B, D, device=dev())
+    eps = [torch.randn(6, D, device=dev()) for _ in range(layers)]
+    out = []
+    for fused in (True, False):
+        for layer, e in zip(model._whvi_layers(), eps):
+            layer.square_blocks()[0].inject_eps(e)
+        if fused:
+            out.append(model.eval_model(x, y))
+        else:
+            out.append(WHVINetwork.eval_model(model, x, y, lambda yp, yt: torch.sqrt(((yp.mean(dim=2) - yt) ** 2).mean())))
+    assert abs(out[0][0] - out[1][0]) < 1e-4 * abs(out[1][0]), out
+    assert abs(out[0][1] - out[1][1]) < 1e-4 * abs(out[1][1]), out

@@ -198,3 +198,27 @@ def test_oracle_backward_is_the_derivative_of_its_forward():
                 b = O.kl(m, rho, 1.7, mode) if pos == 0 else O.kl(mu, m, 1.7, mode)
                 num = (float(a) - float(b)) / (2 * h)
                 assert abs(num - grad[j]) < 1e-6 * max(1.0, abs(num)), (mode, pos, j)
+
+
+def test_reference_bytecode_package_is_the_reference_layer():
+    """bench.py's reference arm runs the reference's OWN layer code (byte-compiled unmodified into oracle/_ref/refpy by
+    oracle/build.py); it must import without the sources and agree bit for bit with the torch restatement
+    (oracle/ref_torch.py) of src/weights.py:66-93 on the same parameters and noise."""
+    import torch
+    from oracle import ref_torch
+    layers = ref_torch.reference_package()
+    if layers is None:
+        pytest.skip("oracle/_ref/refpy not built (python oracle/build.py needs /root/reference)")
+    assert "refpy" in layers.__spec__.origin
+    torch.manual_seed(3)
+    layer = layers.WHVILinear(16, 16)
+    w = layer.weight_submodule
+    with torch.no_grad():
+        w.g_mu.normal_()
+    h = torch.randn(5, 16)
+    torch.manual_seed(9)
+    y = layer(h)
+    torch.manual_seed(9)
+    eps = torch.randn(16)
+    y_port = ref_torch.sample_lrt(h, w.s1, w.s2, w.g_mu, w.g_rho, eps)
+    assert torch.equal(y, y_port)

@@ -1105,6 +1105,8 @@ int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream)
     // D = 2048, 4096: two views, 64 floats per thread, running sums / g / role exchange in tensor memory
     if (k == 11) return launch_bwd_tm_cfg<12, 6, 11, 2>(c, k, stream);
     if (k == 12) return launch_bwd_tm_cfg<12, 6, 12, 2>(c, k, stream);
+    // D = 8192: three views, 64 floats per thread, one tile pair per CTA, same tensor-memory residency
+    if (k == 13) return launch_bwd_tm_cfg<13, 6, 13, 3>(c, k, stream);
 #endif
     if (k == 11) return launch_bwd_tma_cfg<11, 5, 11, 2, 1, 2, false, false, 2, 3>(c, k, stream);
     if (k == 12) return launch_bwd_tma_cfg<12, 5, 12, 1, 1, 2, false, false, 2, 3>(c, k, stream);

@@ -53,7 +53,12 @@ class _Timed:
             EVENT_SINK[self.name].append((self.a, self.b, self.tag))
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)   # the current stream's handle without a Stream object
+
+
 def _stream(device: torch.device) -> int:
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(device).cuda_stream
 
 
@@ -239,6 +244,49 @@ def predictive_moments(x, mu, rho, s1, s2, bias=None, n_samples=64, chunk_sample
     return sum_y, sum_y2, hi - lo
 
 
+FUSED_BWD_MAX_D = 8192   # a row pair, its transposition buffers and two pipeline stages fill an SM's shared memory there
+
+
+@torch.no_grad()
+def _layer_backward_multipass(x, dy, g, s1, s2, want_dx, want_dbias, relu_in, target, coef, dy_scale):
+    """D = 2^14, 2^15 (the config-5 width): the backward as four passes of the batched FWHT kernel (``whvi_fwht_f32``) per
+    MC sample with the elementwise products and column sums between them as tensor ops -- the same math as the fused
+    kernel, ~6x its HBM traffic, O(B.D) extra memory.  The reference's autograd has no width limit
+    (``src/fwht/cuda/fwht.py:14-16``), so neither has the drop-in; the fused single-pass kernels stop at 8192."""
+    from .fwht import fwht_
+    S, D = g.shape
+    shared = x.dim() == 2
+    B = x.size(0) if shared else x.size(1)
+    dev = x.device
+    dx = torch.empty((S, B, D), dtype=torch.float32, device=dev) if want_dx else None
+    dg = torch.empty((S, D), dtype=torch.float32, device=dev)
+    ds1, ds2 = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    dbias = torch.zeros(D, device=dev) if want_dbias else None
+    buf = torch.empty((B, D), dtype=torch.float32, device=dev)
+    for s in range(S):
+        xs_ = x if shared else x[s]
+        if target is not None:
+            dys = coef * (dy[s] - target)
+        elif dy_scale is not None:
+            dys = dy_scale.reshape(()) * dy[s]
+        else:
+            dys = dy[s]
+        t2 = fwht_(xs_ * s2)
+        dt3 = fwht_(dys * s1, out=buf)
+        dg[s] = (dt3 * t2).sum(dim=0)
+        dt1 = fwht_(dt3 * g[s], out=buf)
+        ds2 += (dt1 * xs_).sum(dim=0)
+        if want_dx:
+            torch.mul(dt1, s2, out=dx[s])
+            if relu_in:
+                dx[s].mul_(xs_ > 0)
+        t4 = fwht_(t2.mul_(g[s]), out=buf)
+        ds1 += (dys * t4).sum(dim=0)
+        if want_dbias:
+            dbias += dys.sum(dim=0)
+    return dx, dg, ds1, ds2, dbias
+
+
 def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False, relu_in=False, target=None, coef=None,
                        dy_scale=None):
     """Returns (dx | None, dg, ds1, ds2, dbias | None); dx is (S,B,D) even for shared x.
@@ -252,6 +300,8 @@ def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False, relu_in
     dev = x.device
     if target is not None:
         target, coef = _f32c(target, "target"), _f32c(coef, "coef").reshape(1)
+    if D > FUSED_BWD_MAX_D:
+        return _layer_backward_multipass(x, dy, g, s1, s2, want_dx, want_dbias, relu_in, target, coef, dy_scale)
     dx = torch.empty((S, B, D), dtype=torch.float32, device=dev) if want_dx else None
     dg = torch.empty((S, D), dtype=torch.float32, device=dev)
     ds1 = torch.empty(D, dtype=torch.float32, device=dev)

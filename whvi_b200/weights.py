@@ -167,7 +167,7 @@ class WHVISquarePow2Matrix(nn.Module):
     @property
     def fusable(self):
         """True when the fused-neighbour paths (ReLU / MNLL folded into the kernels) apply."""
-        return self.semantics == "paper" and WF.MIN_LAYER_D <= self.D <= 8192  # the backward kernel's range
+        return self.semantics == "paper" and WF.MIN_LAYER_D <= self.D <= WF.FUSED_BWD_MAX_D  # the fused backward's range
 
     def forward_sqerr(self, h, target, *, relu_in=False):
         """Forward pass fused with sum (y - target)^2 (see functional.WHVILayerSqErrFunction).
