@@ -248,6 +248,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the evaluation leg overlaps a pairwise reduce-scatter with a kernel that leaves 4 SMs free for it
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")
         dist.init_process_group("nccl", device_id=dev)
     first_sample, S_local = shard_samples(S_TOTAL, rank, world)
     assert S_TOTAL % world == 0

@@ -126,6 +126,7 @@ WHVI_API int whvi_layer_bwd_f32(const float* x, int64_t x_sample_stride, const f
 #define WHVI_LAYER_FROM_T2 2
 #define WHVI_LAYER_RELU_IN 1
 #define WHVI_LAYER_ACCUMULATE 4   /* whvi_layer_moments_f32: add to the existing contents of sum_y / sum_y2 */
+#define WHVI_LAYER_RESERVE_SMS(n) (((n) & 0xFF) << 8)   /* whvi_layer_moments_f32: leave n SMs free (for a concurrent collective) */
 WHVI_API int whvi_layer_fwd_partials(int64_t S, int64_t B, int64_t D, int64_t* count);
 WHVI_API int whvi_layer_fwd_fused_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1,
                                       const float* s2, const float* bias, float* y, int64_t S, int64_t B, int64_t D,
@@ -208,6 +209,9 @@ WHVI_API int whvi_mc_moments_f32(const float* y, float* sum_y, float* sum_y2, in
  *   flags & WHVI_LAYER_FROM_T2: x holds t2 = H(s2 * x) already (shared input only; sample-independent by linearity,
  *       one whvi_fwht_f32 per input chunk), so one transform per (sample, row) pair is left;
  *   flags & WHVI_LAYER_ACCUMULATE: sum_y / sum_y2 are added to (sample chunks, or per-rank partial sums).
+ *   flags | WHVI_LAYER_RESERVE_SMS(n): the persistent grid leaves n SMs unoccupied -- its CTAs take whole SMs (all
+ *       registers or all shared memory), so a collective kernel launched next to it (multi-GPU evaluation: the exchange of
+ *       partial sums overlaps the next chunk) would otherwise wait for it to finish.
  * sum_y2 may be NULL; bias may be NULL; g: (S, D).
  */
 WHVI_API int whvi_layer_moments_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1, const float* s2,

@@ -1,17 +1,21 @@
 """BASELINE config 5 on 1..8 GPUs: MC predictive mean/variance of WHVILinear(32768, 32768) over synthetic inputs,
-256 MC samples, the MC samples sharded over the ranks.
+256 MC samples, sharded over the ranks in two dimensions ("sharding MC samples and minibatch rows"):
+    rank = (sample group a, row group b),  sample groups G_s = min(2, N),  row groups G_r = N / G_s
+Per input chunk a rank runs ONE launch of the fused moments kernel (whvi_layer_moments_f32: the forward over its S / G_s
+samples for its rows with sum y / sum y^2 kept in tensor memory -- no prediction ever reaches HBM); the partial sums are
+then reduce-scattered INSIDE the sample-group pair that shares those rows (NCCL, side stream, overlapping the next
+chunk), so each rank finishes mean/variance for rows / G_s of its inputs.  Why not samples over all N ranks: the
+exchange is 8*D bytes per input per rank whatever N is (256 KB at D = 2^15), so with 256/8 = 32 samples per rank it
+would be a quarter of the compute time and an 8-way collective; with two sample groups it is 1/8 of that and pairwise.
+The moments kernel takes whole SMs (all registers), so it leaves a few SMs free for the collective's CTAs
+(WHVI_LAYER_RESERVE_SMS), otherwise the exchange could only start when the next chunk's kernel has finished.
+The noise is ONE (S, D) draw for all inputs, as in the reference's eval_model (src/networks.py:101-115: one forward
+pass of S samples over the whole test batch).
 
-Per input chunk and rank: ONE launch of the fused moments kernel (whvi_layer_moments_f32: the forward over this rank's
-samples with sum y / sum y^2 kept in tensor memory -- no prediction ever reaches HBM), then the partial sums are
-reduce-scattered over NVLink on a side stream so that each rank finishes mean/variance for its 1/N of the chunk's
-inputs while the next chunk computes.  The input side is sharded too: each rank prepares t2 = H(s2 x) for 1/N of the
-chunk's inputs and the slices are all-gathered one chunk ahead.  The noise is ONE (S, D) draw for all inputs, as in the
-reference's eval_model (src/networks.py:101-115: one forward pass of S samples over the whole test batch).
+Inputs are a fixed function of the global row index and the noise comes from a fixed seed, so the printed checksum must
+agree for N = 1, 2, 4, 8 (up to fp32 summation order).
 
-Inputs and noise are generated from fixed seeds in blocks that do not depend on the number of ranks, so the printed
-checksum must agree for N = 1, 2, 4, 8 (up to fp32 summation order).
-
-    python tools/bench_eval.py [--inputs 18944]
+    python tools/bench_eval.py [--inputs 85248]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_eval.py
 
 Also imported by bench.py (`run_eval`), which puts the result under the `eval` key of its JSON line.
@@ -32,48 +36,61 @@ import whvi_b200 as W  # noqa: E402
 from whvi_b200 import functional as WF  # noqa: E402
 from whvi_b200.fwht import fwht_  # noqa: E402
 
-SUB_BLOCKS = 8   # input rows of a chunk are generated in 8 seeded sub-blocks: the same data for 1, 2, 4 or 8 ranks
+RESERVE_SMS = 4   # left to the pairwise reduce-scatter when there is one (N >= 2)
+_PAIR_GROUPS = {}
 
 
-def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, chunk_inputs=592, warmup_chunks=2):
+def _pair_group(world, g_s, rank):
+    """The process group of the ranks that share this rank's rows (same row group, different sample groups)."""
+    if g_s == 1:
+        return None
+    key = (world, g_s)
+    if key not in _PAIR_GROUPS:   # every rank creates every group, in the same order
+        _PAIR_GROUPS[key] = [dist.new_group(list(range(b * g_s, (b + 1) * g_s))) for b in range(world // g_s)]
+    return _PAIR_GROUPS[key][rank // g_s]
+
+
+def synthetic_rows(row0, rows, D, dev):
+    """Inputs as a fixed function of (global row, column): the same data whatever the chunking and the rank count."""
+    r = torch.arange(row0, row0 + rows, device=dev, dtype=torch.float32).unsqueeze(1) * 12.9898
+    c = torch.arange(D, device=dev, dtype=torch.float32).unsqueeze(0) * 78.233
+    return torch.add(r, c).sin_()
+
+
+def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2):
     """Returns (on every rank) the result dict; timing = CUDA events, barrier on both sides, max over ranks."""
-    D, S, cb = 1 << log2d, samples, chunk_inputs
-    assert S % world == 0 and cb % SUB_BLOCKS == 0 and SUB_BLOCKS % world == 0
-    n_chunks = max(1, (inputs or 32 * cb) // cb)
-    lo, hi = rank * (S // world), (rank + 1) * (S // world)
+    D, S = 1 << log2d, samples
+    g_s = 2 if world >= 2 else 1
+    g_r = world // g_s
+    a_idx, b_idx = rank % g_s, rank // g_s
+    assert world == g_s * g_r and S % g_s == 0
+    reserve = RESERVE_SMS if g_s > 1 else 0
+    rows_mine = 4 * (148 - reserve)                       # four tiles per CTA of the persistent grid, every chunk
+    cb = rows_mine * g_r                                  # inputs per chunk over all row groups
+    # default: 85248 inputs = a whole number of chunks for N = 1 (592 rows), 2 (576), 4 (1152) and 8 (2304 rows per chunk):
+    # every N evaluates the same input set (strong scaling; same checksum)
+    n_chunks = max(1, (inputs or 85248) // cb)
+    lo, hi = a_idx * (S // g_s), (a_idx + 1) * (S // g_s)
+    group = _pair_group(world, g_s, rank)
     torch.manual_seed(0)                                   # replicated parameters
     layer = W.WHVISquarePow2Matrix(D, lambda_=1.0).to(dev)
     with torch.no_grad():
         layer.g_mu.copy_(torch.randn(D, generator=torch.Generator().manual_seed(7)).to(dev))
         eps = torch.randn(S, D, generator=torch.Generator().manual_seed(11))[lo:hi].to(dev)
-        g = WF.reparam(layer.g_mu, layer.g_rho, eps)       # (S/N, D): this rank's weight samples, for ALL inputs
+        g = WF.reparam(layer.g_mu, layer.g_rho, eps)       # (S / G_s, D): this rank's weight samples, for ALL inputs
         s1, s2 = layer.s1.detach(), layer.s2.detach()
-    sub = cb // SUB_BLOCKS
-    n_mine = cb // world
-    gen_x = torch.Generator(device=dev)
-    buckets = [torch.empty(2, cb, D, device=dev) for _ in range(2)]        # (sum y, sum y^2) partials, double-buffered
-    mine = [torch.empty(2, n_mine, D, device=dev) for _ in range(2)]       # this rank's share after the reduce-scatter
-    t2_full = [torch.empty(cb, D, device=dev) for _ in range(2)]
-    t2_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    n_fin = rows_mine // g_s                               # rows this rank finishes after the exchange
+    buckets = [torch.empty(2, rows_mine, D, device=dev) for _ in range(2)]   # (sum y, sum y^2) partials, double-buffered
+    mine = [torch.empty(2, n_fin, D, device=dev) for _ in range(2)]
+    t2buf = [torch.empty(rows_mine, D, device=dev) for _ in range(2)]
     comm = torch.cuda.Stream(device=dev)
     checksum = torch.zeros(2, device=dev, dtype=torch.float64)
 
     def prepare(c):
-        """t2 of input chunk c: this rank's row slice on the main stream, the all-gather on `comm`."""
-        full = t2_full[c % 2]
-        sl = full[rank * n_mine:(rank + 1) * n_mine]
-        x = torch.empty(n_mine, D, device=dev)
-        for j in range(SUB_BLOCKS // world):               # rank-count independent data
-            gen_x.manual_seed(1000 + c * SUB_BLOCKS + rank * (SUB_BLOCKS // world) + j)
-            x[j * sub:(j + 1) * sub].normal_(generator=gen_x)
-        fwht_(x * s2, out=sl)
-        if world > 1:
-            comm.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(comm):
-                dist.all_gather_into_tensor(full, sl)
-                t2_ready[c % 2].record(comm)
-        else:
-            t2_ready[c % 2].record()
+        """t2 = H(s2 x) of this rank's rows of chunk c (the sample-group partner computes the same rows redundantly: a
+        fraction of a percent of the chunk's work, and it saves a collective)."""
+        x = synthetic_rows(c * cb + b_idx * rows_mine, rows_mine, D, dev)
+        fwht_(x.mul_(s2), out=t2buf[c % 2])
 
     def finish(part, ev):
         torch.cuda.current_stream().wait_event(ev)
@@ -86,22 +103,21 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, chunk_inputs=592
         pending = None
         prepare(first_chunk)
         for c in range(first_chunk, first_chunk + count):
-            if c + 1 < first_chunk + count:
-                prepare(c + 1)                             # one chunk ahead: overlaps this chunk's kernel
-            torch.cuda.current_stream().wait_event(t2_ready[c % 2])
             bucket = buckets[c % 2]
-            WF.layer_moments_raw(t2_full[c % 2], g, s1, s2, None, bucket[0], bucket[1], from_t2=True)
+            WF.layer_moments_raw(t2buf[c % 2], g, s1, s2, None, bucket[0], bucket[1], from_t2=True, reserve_sms=reserve)
             ev = torch.cuda.Event()
             part = bucket
-            if world > 1:
+            if g_s > 1:
                 part = mine[c % 2]
                 comm.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(comm):              # overlaps the next chunk's kernel
-                    dist.reduce_scatter_tensor(part[0], bucket[0])
-                    dist.reduce_scatter_tensor(part[1], bucket[1])
+                with torch.cuda.stream(comm):              # overlaps the next chunk's kernel (which leaves SMs free for it)
+                    dist.reduce_scatter_tensor(part[0], bucket[0], group=group)
+                    dist.reduce_scatter_tensor(part[1], bucket[1], group=group)
                     ev.record(comm)
             else:
                 ev.record()
+            if c + 1 < first_chunk + count:
+                prepare(c + 1)
             if pending is not None:
                 finish(*pending)
             pending = (part, ev)
@@ -128,16 +144,18 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, chunk_inputs=592
     pairs = n_chunks * cb * S
     n_el = float(n_chunks * cb * D)
     return {"metric": "MC predictive (sample, input) pairs/s", "value": pairs / (ms.item() * 1e-3), "unit": "rows/s",
-            "n_gpus": world, "ms": ms.item(), "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+            "n_gpus": world, "ms": ms.item(), "higher_is_better": True, "scaling": "strong",
+            "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"config5-large-eval: WHVILinear({D},{D}) MC predictive mean/var, {n_chunks * cb} inputs "
-                                   f"(bounded sample of 1M) x {S} MC samples", "parallelism": f"mc-sample-shard x{world}",
-                       "chunk_inputs": cb, "samples_per_rank": S // world,
+                                   f"(bounded sample of 1M) x {S} MC samples", "parallelism": f"{g_s} sample groups x {g_r} row groups",
+                       "chunk_inputs": cb, "samples_per_rank": S // g_s, "rows_per_rank_per_chunk": rows_mine,
                        "kernel": "layer_moments_kernel (forward + sum y, sum y^2 in tensor memory, one launch per chunk per rank)",
-                       "collective": "none" if world == 1 else "all-gather of t2 slices (one chunk ahead) + reduce-scatter of "
-                                                              "(sum y, sum y^2) per input chunk, both overlapped on a side stream"},
+                       "collective": "none" if g_s == 1 else f"pairwise reduce-scatter of (sum y, sum y^2) inside each sample-group pair, "
+                                                            f"overlapped on a side stream ({reserve} SMs left free for it)"},
             "equiv_algorithmic_gbs": 8.0 * D * pairs / ms.item() / 1e6,
             "checksum": {"mean_abs_pred_mean": float(checksum[0]) / n_el, "mean_pred_var": float(checksum[1]) / n_el,
-                         "note": "fixed seeds, rank-count independent data: must agree across n_gpus"}}
+                         "inputs": n_chunks * cb,
+                         "note": "fixed seeds, data a function of the global row: agrees across n_gpus when `inputs` does"}}
 
 
 def main():
@@ -145,14 +163,13 @@ def main():
     ap.add_argument("--inputs", type=int, default=0)
     ap.add_argument("--log2d", type=int, default=15)
     ap.add_argument("--samples", type=int, default=256)
-    ap.add_argument("--chunk-inputs", type=int, default=592)
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    res = run_eval(dev, rank, world, inputs=args.inputs, log2d=args.log2d, samples=args.samples, chunk_inputs=args.chunk_inputs)
+    res = run_eval(dev, rank, world, inputs=args.inputs, log2d=args.log2d, samples=args.samples)
     if rank == 0:
         print(json.dumps(res))
     if world > 1:

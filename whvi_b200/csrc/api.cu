@@ -231,14 +231,14 @@ int whvi_layer_moments_f32(const float* x, int64_t x_sample_stride, const float*
 {
     if (int rc = check_layer_shape("layer_moments", S, B, D, x_sample_stride, 32768)) return rc;
     if (D < 8192) return fail(WHVI_E_SHAPE, "layer_moments: D = %lld outside [8192, 32768] (use whvi_layer_fwd_fused_f32 + whvi_mc_moments_f32)", (long long)D);
-    if (flags & ~(WHVI_LAYER_FROM_T2 | WHVI_LAYER_ACCUMULATE)) return fail(WHVI_E_MODE, "layer_moments: unknown flags %d", flags);
+    if (flags & ~(WHVI_LAYER_FROM_T2 | WHVI_LAYER_ACCUMULATE | 0xFF00)) return fail(WHVI_E_MODE, "layer_moments: unknown flags %d", flags);
     if ((flags & WHVI_LAYER_FROM_T2) && x_sample_stride != 0) return fail(WHVI_E_MODE, "layer_moments: FROM_T2 needs a shared (B, D) input");
     if (B == 0) return WHVI_OK;
     if (!x || !s1 || !s2 || !sum_y || (S > 0 && !g)) return fail(WHVI_E_NULL, "layer_moments: null pointer");
     if (!aligned16(x) || !aligned16(g) || !aligned16(s1) || !aligned16(s2) || !aligned16(bias) || !aligned16(sum_y) || !aligned16(sum_y2))
         return fail(WHVI_E_ALIGN, "layer_moments: pointers must be 16-byte aligned");
     return launch_layer_moments(x, x_sample_stride, g, s1, s2, bias, sum_y, sum_y2, S, B, D, (flags & WHVI_LAYER_FROM_T2) ? 1 : 0,
-                                (flags & WHVI_LAYER_ACCUMULATE) ? 1 : 0, static_cast<cudaStream_t>(stream));
+                                (flags & WHVI_LAYER_ACCUMULATE) ? 1 : 0, (flags >> 8) & 0xFF, static_cast<cudaStream_t>(stream));
 }
 
 int whvi_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

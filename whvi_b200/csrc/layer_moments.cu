@@ -33,6 +33,7 @@ struct MomArgs {
     int n_samples;
     int k;
     int accumulate;
+    int reserve_sms;           // SMs to leave free (a concurrent NCCL kernel needs somewhere to run: these CTAs take whole SMs)
 };
 
 // CTAs per SM are bounded by tensor-memory columns: 128 per thread, T / 128 warps per lane quadrant
@@ -175,7 +176,8 @@ static int launch_moments_cfg(const MomArgs& a, bool from_t2, cudaStream_t strea
     constexpr int T = 1 << (N - C);
     constexpr size_t smem = sizeof(float) * size_t(scratch_words(N, C));
     constexpr int ctas_per_sm = moments_ctas_per_sm(N, C);
-    int64_t grid = a.tiles < 148 * ctas_per_sm ? a.tiles : 148 * ctas_per_sm;
+    const int sms = 148 - (a.reserve_sms > 0 && a.reserve_sms < 148 ? a.reserve_sms : 0);
+    int64_t grid = a.tiles < int64_t(sms) * ctas_per_sm ? a.tiles : int64_t(sms) * ctas_per_sm;
     auto go = [&](auto kernel, int slot) -> int {
         if (int rc = ensure_smem(kernel, smem, smem_ok[slot])) return rc;
         kernel<<<static_cast<unsigned>(grid), T, smem, stream>>>(a);
@@ -185,11 +187,11 @@ static int launch_moments_cfg(const MomArgs& a, bool from_t2, cudaStream_t strea
 }
 
 int launch_layer_moments(const float* x, int64_t xs, const float* g, const float* s1, const float* s2, const float* bias, float* sum_y,
-                         float* sum_y2, int64_t S, int64_t B, int64_t D, int from_t2, int accumulate, cudaStream_t stream)
+                         float* sum_y2, int64_t S, int64_t B, int64_t D, int from_t2, int accumulate, int reserve_sms, cudaStream_t stream)
 {
     const int k = ilog2(D);
     const int64_t tile = D;   // one row per tile
-    MomArgs a{x, xs, g, s1, s2, bias, sum_y, sum_y2, B * D, (B * D + tile - 1) / tile, static_cast<int>(S), k, accumulate};
+    MomArgs a{x, xs, g, s1, s2, bias, sum_y, sum_y2, B * D, (B * D + tile - 1) / tile, static_cast<int>(S), k, accumulate, reserve_sms};
     if (k == 13) return launch_moments_cfg<13, 6, 13>(a, from_t2, stream);
     if (k == 14) return launch_moments_cfg<14, 6, 14>(a, from_t2, stream);
     if (k == 15) return launch_moments_cfg<15, 6, 15>(a, from_t2, stream);

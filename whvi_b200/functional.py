@@ -151,10 +151,11 @@ def mc_moments_(y, sum_y, sum_y2=None, accumulate=True):
 FUSED_MOMENTS_MIN_D, FUSED_MOMENTS_MAX_D = 8192, 32768
 
 
-def layer_moments_raw(x, g, s1, s2, bias, sum_y, sum_y2=None, from_t2=False, accumulate=False):
+def layer_moments_raw(x, g, s1, s2, bias, sum_y, sum_y2=None, from_t2=False, accumulate=False, reserve_sms=0):
     """sum_y (+)= sum_s y[s], sum_y2 (+)= sum_s y[s]^2 for y[s] = s1 * H(g[s] * H(s2 * x)) + bias over ALL samples of ``g``
     in ONE kernel that keeps the running sums in tensor memory: no prediction is ever written to HBM
-    (``whvi_layer_moments_f32``; 8192 <= D <= 32768).  ``x``: (B, D) shared or (S, B, D); ``from_t2``: x holds H(s2 * x)."""
+    (``whvi_layer_moments_f32``; 8192 <= D <= 32768).  ``x``: (B, D) shared or (S, B, D); ``from_t2``: x holds H(s2 * x);
+    ``reserve_sms``: SMs the persistent grid leaves free for a collective kernel running next to it."""
     x, g, s1, s2 = _f32c(x, "x"), _f32c(g, "g"), _f32c(s1, "s1"), _f32c(s2, "s2")
     S, B, D, xs = _layer_dims(x, g, s1, s2)
     if bias is not None:
@@ -165,7 +166,8 @@ def layer_moments_raw(x, g, s1, s2, bias, sum_y, sum_y2=None, from_t2=False, acc
     with torch.cuda.device(x.device), _Timed("whvi_layer_moments_f32", "from_t2" if from_t2 else "full"):
         rc = _lib.lib().whvi_layer_moments_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
                                                sum_y.data_ptr(), _ptr(sum_y2), S, B, D,
-                                               (2 if from_t2 else 0) | (4 if accumulate else 0), _stream(x.device))
+                                               (2 if from_t2 else 0) | (4 if accumulate else 0) | ((int(reserve_sms) & 0xFF) << 8),
+                                               _stream(x.device))
     _lib.check(rc, "whvi_layer_moments_f32")
     return sum_y, sum_y2
 
