@@ -168,16 +168,34 @@ WHVI_API int whvi_layer_loss_f32(const float* x, int64_t x_sample_stride, const 
 /*
  * Reparameterisation (src/weights.py:43-50, :82-83, :92-93), one eps row per MC sample:
  *   mode 0:  g[s,:] = mu + softplus(rho) * eps[s,:]              (diagonal; the reference)
- *   mode 1:  g[s,:] = mu + L eps[s,:], L (D,D) row-major lower triangular passed in `rho`
- *            (entries above the diagonal are ignored); a tcgen05 tensor-core GEMM with a
- *            3xTF32 operand split (fp32-level accuracy); D must be a multiple of 128.  Not in
- *            the reference (its posterior is diagonal) -- a superset feature.
+ *   mode 1:  reserved -- the dense form g[s,:] = mu + L eps[s,:] is whvi_reparam_dense_f32 below (it needs a workspace).
  * eps, g: (S,D); mu, rho: (D).
  */
 #define WHVI_REPARAM_DIAG 0
 #define WHVI_REPARAM_DENSE 1
 WHVI_API int whvi_reparam_f32(const float* mu, const float* rho, const float* eps, float* g, int64_t S, int64_t D,
                               int mode, whvi_stream_t stream);
+/*
+ * Dense-covariance superset of the reference's diagonal posterior (north-star kernel (4) as a tensor-core
+ * GEMM, kernel (5) with the log-determinant).  L: (D, D) row-major lower triangular (entries above the diagonal are
+ * ignored), D a multiple of 128.  All three products run on tcgen05 (kind::tf32, 3xTF32 operand split for fp32-level
+ * accuracy, TMA-fed 128-byte-swizzled tiles, TMEM accumulators):
+ *   whvi_reparam_dense_f32      g[s,:] = mu + L eps[s,:]            eps, g: (S, D); workspace from ..._workspace_bytes
+ *   whvi_reparam_dense_bwd_f32  dL = tril( dgT epsT^T )             dgT, epsT: (D, S_padded) = the TRANSPOSES of dg and eps,
+ *                               zero-padded to S_padded % 32 == 0; dL: (D, D), the caller zero-fills it (tiles above the
+ *                               diagonal are not written); dmu = sum_s dg[s] is a column sum the caller does
+ *   whvi_kl_dense_f32           KL( N(mu, L L^T) || N(0, lambda I) ) = 0.5 ( D ln lambda - 2 sum ln L_ii - D + |L|_F^2 / lambda
+ *                               + |mu|^2 / lambda ) into out_kl[0]; dmu = grad_scale mu / lambda, dL = grad_scale ( L / lambda -
+ *                               diag(1 / L_ii) ) (zero above the diagonal), both or neither; workspace: D doubles
+ */
+WHVI_API int whvi_reparam_dense_workspace_bytes(int64_t S, int64_t D, size_t* bytes);
+WHVI_API int whvi_reparam_dense_f32(const float* mu, const float* L, const float* eps, float* g, int64_t S, int64_t D,
+                                    void* workspace, size_t workspace_bytes, whvi_stream_t stream);
+WHVI_API int whvi_reparam_dense_bwd_f32(const float* dgT, const float* epsT, float* dL, int64_t S_padded, int64_t D,
+                                        whvi_stream_t stream);
+WHVI_API int whvi_kl_dense_f32(const float* mu, const float* L, float lambda_, int64_t D, float* out_kl, float* dmu, float* dL,
+                               float grad_scale, void* workspace, size_t workspace_bytes, whvi_stream_t stream);
+
 /* dmu = sum_s dg[s];  drho = (sum_s dg[s]*eps[s]) * sigmoid(rho).  accumulate != 0: += */
 WHVI_API int whvi_reparam_bwd_f32(const float* rho, const float* eps, const float* dg, float* dmu, float* drho,
                                   int64_t S, int64_t D, int mode, int accumulate, whvi_stream_t stream);

@@ -244,6 +244,27 @@ def kl(mu, rho, lambda_: float, mode: int = 0, grads: bool = False):
     return (v, dmu, drho) if grads else v
 
 
+def reparam_dense_bwd(eps, dg):
+    """Gradients of g[s] = mu + L eps[s] (dense lower-triangular L; superset of src/weights.py:82-83, parity unpinned --
+    not in the reference): dmu = sum_s dg[s], dL = tril(dg^T eps)."""
+    eps, dg = np.asarray(eps, dtype=np.float64), np.asarray(dg, dtype=np.float64)
+    return dg.sum(0), np.tril(dg.T @ eps)
+
+
+def kl_dense(mu, L, lambda_: float, grads: bool = False):
+    """KL( N(mu, L L^T) || N(0, lambda I) ), L lower triangular with a positive diagonal (entries above the diagonal are
+    ignored): 0.5 (D ln lambda - 2 sum ln L_ii - D + |L|_F^2 / lambda + |mu|^2 / lambda).  The dense superset of
+    src/utils.py:49-71 (parity unpinned -- the reference's posterior is diagonal); with L = diag(sigma) it equals
+    kl(mode=1), which tests/test_oracle.py checks."""
+    mu, L = np.asarray(mu, dtype=np.float64), np.tril(np.asarray(L, dtype=np.float64))
+    D = mu.shape[0]
+    d = np.diagonal(L)
+    v = 0.5 * (D * np.log(lambda_) - 2.0 * np.log(d).sum() - D + (L * L).sum() / lambda_ + (mu * mu).sum() / lambda_)
+    if not grads:
+        return float(v)
+    return float(v), mu / lambda_, L / lambda_ - np.diag(1.0 / d)
+
+
 def mnll(y, y_hat, sigma: float, n: int) -> float:
     """MNLL estimator, src/likelihoods.py:18-29; y (m,n_out), y_hat (m,n_out,n_mc)."""
     y_hat = np.asarray(y_hat)

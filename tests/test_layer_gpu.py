@@ -327,7 +327,8 @@ def test_layer_full_size_properties():
         assert rel_err(y[s, b].cpu().numpy(), ref) < TOL
 
 
-@pytest.mark.parametrize("S,D", [(16, 128), (64, 256), (37, 512), (128, 1024), (300, 256)])
+@pytest.mark.parametrize("S,D", [(16, 128), (64, 256), (37, 512), (128, 1024), (300, 256), (1, 128), (128, 2048), (128, 4096), (40, 8192),
+                                 (256, 4096), (513, 640)])
 def test_reparam_dense_tcgen05_vs_oracle(S, D):
     """Kernel (4): g = mu + eps @ L^T on the tcgen05 tensor cores (3xTF32 split).  Not in the
     reference (parity unpinned): checked against the fp64 oracle formula and torch autograd."""
@@ -342,8 +343,64 @@ def test_reparam_dense_tcgen05_vs_oracle(S, D):
     assert rel_err(g.detach().cpu().numpy(), ref) < 1e-5
     dg = rng.standard_normal((S, D))
     (g * t(dg)).sum().backward()
-    assert rel_err(mt.grad.cpu().numpy(), dg.sum(0)) < 1e-5
-    assert rel_err(Lt.grad.cpu().numpy(), np.tril(dg.T @ eps)) < 1e-5
+    rdmu, rdL = O.reparam_dense_bwd(eps, dg)
+    assert rel_err(mt.grad.cpu().numpy(), rdmu) < 1e-5
+    dL = Lt.grad.cpu().numpy()
+    assert rel_err(dL, rdL) < 1e-5
+    assert np.all(np.triu(dL, 1) == 0)
+
+
+@pytest.mark.parametrize("D", [128, 384, 1024, 4096])
+def test_kl_dense_vs_oracle(D):
+    """Kernel (5), dense form: KL(N(mu, L L^T) || N(0, lambda I)) with the log-determinant and its gradients
+    (whvi_kl_dense_f32) against the fp64 oracle formula (tests/test_oracle.py ties that to torch's MVN KL)."""
+    from whvi_b200 import functional as F
+    rng = np.random.default_rng(D)
+    lam = 0.05
+    mu = rng.standard_normal(D)
+    L = np.tril(rng.standard_normal((D, D))) / np.sqrt(D)
+    L[np.arange(D), np.arange(D)] = np.abs(np.diagonal(L)) + 0.05
+    Lg = L + np.triu(rng.standard_normal((D, D)), 1)
+    mt, Lt = t(mu).requires_grad_(), t(Lg).requires_grad_()
+    kl = F.kl_gaussian_dense(mt, Lt, lam)
+    v, dmu, dL = O.kl_dense(mu.astype(np.float32).astype(np.float64), L.astype(np.float32).astype(np.float64), lam, grads=True)
+    assert abs(kl.item() - v) < 1e-5 * abs(v)
+    (3.0 * kl).backward()
+    assert rel_err(mt.grad.cpu().numpy(), 3.0 * dmu) < 1e-5
+    assert rel_err(Lt.grad.cpu().numpy(), 3.0 * dL) < 1e-5
+    with torch.no_grad():
+        assert abs(F.kl_gaussian_dense(mt, Lt, lam).item() - v) < 1e-5 * abs(v)   # value-only call (no gradient buffers)
+
+
+def test_dense_covariance_module():
+    """WHVISquarePow2Matrix(covariance="dense"): starts at the reference's diagonal posterior (L = diag(softplus(rho)),
+    same init RNG order), so with the same noise its outputs, KL (sigma^2 form) and non-L gradients equal the diagonal
+    module's; the L gradient is tril(dg^T eps) of the oracle."""
+    from whvi_b200.weights import WHVISquarePow2Matrix
+    D, S, B = 256, 5, 9
+    torch.manual_seed(3)
+    a = WHVISquarePow2Matrix(D, lambda_=0.1, bias=True, kl_mode=1).to(dev())
+    torch.manual_seed(3)
+    b = WHVISquarePow2Matrix(D, lambda_=0.1, bias=True, covariance="dense").to(dev())
+    assert "g_L" in b.state_dict() and "g_rho" not in b.state_dict()
+    eps = torch.randn(S, D, device=dev())
+    x = torch.randn(B, D, device=dev())
+    outs = []
+    for m in (a, b):
+        m.mc_samples = S
+        m._eps_queue.append(eps.clone())
+        y = m(x)
+        kl = m.kl
+        (y.square().sum() + kl).backward()
+        outs.append((y.detach().cpu().numpy(), kl.item()))
+    assert rel_err(outs[1][0], outs[0][0]) < 1e-5
+    assert abs(outs[1][1] - outs[0][1]) < 1e-5 * abs(outs[0][1])
+    for n in ("s1", "s2", "g_mu", "bias"):
+        assert rel_err(getattr(b, n).grad.cpu().numpy(), getattr(a, n).grad.cpu().numpy()) < 1e-4
+    # d/d sigma_i of the diagonal module = the diagonal of dL
+    sig_grad = a.g_rho.grad / torch.sigmoid(a.g_rho.detach())
+    assert rel_err(torch.diagonal(b.g_L.grad).cpu().numpy(), sig_grad.cpu().numpy()) < 1e-4
+    assert np.all(np.triu(b.g_L.grad.cpu().numpy(), 1) == 0)
 
 
 @pytest.mark.parametrize("S,B,D,bias,shared", [(2, 37, 128, True, False), (3, 9, 512, False, False), (2, 21, 1024, True, False),

@@ -61,6 +61,34 @@ def test_kl_matches_reference(golden):
     assert np.allclose(g["gen_kl"], g["gen_kl_torch"])
 
 
+def test_dense_kl_restatement():
+    """The dense-covariance KL (not in the reference, "parity unpinned") is tied to pinned things: with L = diag(sigma)
+    it is the oracle's sigma^2-form diagonal KL, and for a full L it is torch's closed-form MVN KL (the check the
+    reference's test/utils.py:22-34 makes for the diagonal formula); its gradients are its own finite differences."""
+    import torch
+    rng = np.random.default_rng(5)
+    D, lam = 24, 0.37
+    mu, rho = rng.standard_normal(D), rng.standard_normal(D) - 1.0
+    sigma = np.log1p(np.exp(rho))
+    assert abs(O.kl_dense(mu, np.diag(sigma), lam) - O.kl(mu, rho, lam, 1)) < 1e-9 * D
+    L = np.tril(rng.standard_normal((D, D))) * 0.3
+    L[np.arange(D), np.arange(D)] = np.abs(np.diagonal(L)) + 0.2
+    v, dmu, dL = O.kl_dense(mu, L + np.triu(rng.standard_normal((D, D)), 1), lam, grads=True)   # upper part ignored
+    q = torch.distributions.MultivariateNormal(torch.tensor(mu), scale_tril=torch.tensor(L))
+    p = torch.distributions.MultivariateNormal(torch.zeros(D, dtype=torch.float64), covariance_matrix=lam * torch.eye(D, dtype=torch.float64))
+    assert abs(v - torch.distributions.kl_divergence(q, p).item()) < 1e-9 * abs(v)
+    h = 1e-6
+    for (i, j) in ((0, 0), (5, 2), (23, 23), (7, 7), (2, 5)):
+        Lp, Lm = L.copy(), L.copy()
+        Lp[i, j] += h
+        Lm[i, j] -= h
+        fd = (O.kl_dense(mu, Lp, lam) - O.kl_dense(mu, Lm, lam)) / (2 * h)
+        assert abs(fd - dL[i, j]) < 1e-5 * max(1.0, abs(fd))
+    assert rel_err(dmu, mu / lam) < 1e-12
+    dmu_r, dL_r = O.reparam_dense_bwd(rng.standard_normal((3, D)), np.ones((3, D)))
+    assert dmu_r.shape == (D,) and np.all(np.triu(dL_r, 1) == 0)
+
+
 def test_mnll_matches_reference(golden):
     g = golden("mnll")
     assert abs(O.mnll(g["fixed_y"], g["fixed_yhat"], 1.0, 12) - float(g["fixed_mnll"])) < 1e-4

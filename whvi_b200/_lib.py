@@ -47,6 +47,11 @@ SIGNATURES = {
     "whvi_reparam_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "whvi_reparam_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                      c_void_p]),
+    "whvi_reparam_dense_workspace_bytes": (c_int, [c_int64, c_int64, POINTER(c_size_t)]),
+    "whvi_reparam_dense_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "whvi_reparam_dense_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "whvi_kl_dense_f32": (c_int, [c_void_p, c_void_p, c_float, c_int64, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_size_t,
+                                  c_void_p]),
     "whvi_fwht_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "whvi_mc_moments_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "whvi_mc_moments_strided_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,

@@ -197,12 +197,48 @@ int whvi_reparam_f32(const float* mu, const float* rho, const float* eps, float*
     if (mode != WHVI_REPARAM_DIAG && mode != WHVI_REPARAM_DENSE) return fail(WHVI_E_MODE, "reparam: unknown mode %d", mode);
     if (S == 0) return WHVI_OK;
     if (!mu || !rho || !eps || !g) return fail(WHVI_E_NULL, "reparam: null pointer");
-    if (mode == WHVI_REPARAM_DENSE) {
-        if (D % 128 != 0) return fail(WHVI_E_SHAPE, "reparam(dense): D = %lld must be a multiple of 128", (long long)D);
-        if (!aligned16(rho) || !aligned16(eps)) return fail(WHVI_E_ALIGN, "reparam(dense): pointers must be 16-byte aligned");
-        return launch_reparam_dense(mu, rho, eps, g, S, D, static_cast<cudaStream_t>(stream));
-    }
+    if (mode == WHVI_REPARAM_DENSE)
+        return fail(WHVI_E_MODE, "reparam: the dense form needs a workspace -- call whvi_reparam_dense_f32");
     return launch_reparam_diag(mu, rho, eps, g, S, D, static_cast<cudaStream_t>(stream));
+}
+
+int whvi_reparam_dense_workspace_bytes(int64_t S, int64_t D, size_t* bytes)
+{
+    if (!bytes) return fail(WHVI_E_NULL, "reparam_dense_workspace_bytes: null pointer");
+    if (S < 0 || D < 128 || D % 128 != 0) return fail(WHVI_E_SHAPE, "reparam(dense): S=%lld, D=%lld (D must be a multiple of 128)", (long long)S, (long long)D);
+    *bytes = reparam_dense_workspace_bytes(S, D);
+    return WHVI_OK;
+}
+
+int whvi_reparam_dense_f32(const float* mu, const float* L, const float* eps, float* g, int64_t S, int64_t D, void* workspace,
+                           size_t workspace_bytes, whvi_stream_t stream)
+{
+    if (S < 0 || D < 128 || D % 128 != 0) return fail(WHVI_E_SHAPE, "reparam(dense): S=%lld, D=%lld (D must be a multiple of 128)", (long long)S, (long long)D);
+    if (S == 0) return WHVI_OK;
+    if (!mu || !L || !eps || !g) return fail(WHVI_E_NULL, "reparam(dense): null pointer");
+    if (!aligned16(L) || !aligned16(eps) || !aligned16(workspace)) return fail(WHVI_E_ALIGN, "reparam(dense): pointers must be 16-byte aligned");
+    return launch_reparam_dense(mu, L, eps, g, S, D, static_cast<float*>(workspace), workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int whvi_reparam_dense_bwd_f32(const float* dgT, const float* epsT, float* dL, int64_t S_padded, int64_t D, whvi_stream_t stream)
+{
+    if (S_padded <= 0 || S_padded % 32 != 0 || D < 128 || D % 128 != 0)
+        return fail(WHVI_E_SHAPE, "reparam_bwd(dense): S_padded=%lld (multiple of 32), D=%lld (multiple of 128)", (long long)S_padded, (long long)D);
+    if (!dgT || !epsT || !dL) return fail(WHVI_E_NULL, "reparam_bwd(dense): null pointer");
+    if (!aligned16(dgT) || !aligned16(epsT) || !aligned16(dL)) return fail(WHVI_E_ALIGN, "reparam_bwd(dense): pointers must be 16-byte aligned");
+    return launch_reparam_dense_bwd(dgT, epsT, dL, S_padded, D, static_cast<cudaStream_t>(stream));
+}
+
+int whvi_kl_dense_f32(const float* mu, const float* L, float lambda_, int64_t D, float* out_kl, float* dmu, float* dL, float grad_scale,
+                      void* workspace, size_t workspace_bytes, whvi_stream_t stream)
+{
+    if (D < 1) return fail(WHVI_E_SHAPE, "kl(dense): D=%lld", (long long)D);
+    if (!(lambda_ > 0.f)) return fail(WHVI_E_SHAPE, "kl(dense): lambda must be positive");
+    if (!mu || !L || !out_kl) return fail(WHVI_E_NULL, "kl(dense): null pointer");
+    if ((dmu == nullptr) != (dL == nullptr)) return fail(WHVI_E_NULL, "kl(dense): dmu and dL must both be given or both NULL");
+    if (!workspace || workspace_bytes < sizeof(double) * size_t(D) || (reinterpret_cast<uintptr_t>(workspace) & 7u))
+        return fail(WHVI_E_WORKSPACE, "kl(dense): workspace of %zu bytes (8-byte aligned) needed", sizeof(double) * size_t(D));
+    return launch_kl_dense(mu, L, lambda_, D, out_kl, dmu, dL, grad_scale, static_cast<double*>(workspace), static_cast<cudaStream_t>(stream));
 }
 
 int whvi_reparam_bwd_f32(const float* rho, const float* eps, const float* dg, float* dmu, float* drho, int64_t S,

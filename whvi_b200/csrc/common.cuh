@@ -87,7 +87,12 @@ int launch_layer_fwd(const LayerFwdCall& c, int64_t D, cudaStream_t stream);
 int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream);
 int launch_reparam_diag(const float* mu, const float* rho, const float* eps, float* g, int64_t S, int64_t D,
                         cudaStream_t stream);
-int launch_reparam_dense(const float* mu, const float* L, const float* eps, float* g, int64_t S, int64_t D, cudaStream_t stream);
+size_t reparam_dense_workspace_bytes(int64_t S, int64_t D);
+int launch_reparam_dense(const float* mu, const float* L, const float* eps, float* g, int64_t S, int64_t D, float* ws, size_t ws_bytes,
+                         cudaStream_t stream);
+int launch_reparam_dense_bwd(const float* dgT, const float* eT, float* dL, int64_t Sp, int64_t D, cudaStream_t stream);
+int launch_kl_dense(const float* mu, const float* L, float lambda_, int64_t D, float* out, float* dmu, float* dL, float grad_scale,
+                    double* row_sq, cudaStream_t stream);
 int launch_reparam_diag_bwd(const float* rho, const float* eps, const float* dg, float* dmu, float* drho, int64_t S,
                             int64_t D, int accumulate, cudaStream_t stream);
 int launch_layer_moments(const float* x, int64_t xs, const float* g, const float* s1, const float* s2, const float* bias, float* sum_y,

@@ -23,7 +23,8 @@ _LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_fwht_f64": 1, "whvi_layer_fwd_f3
                       "whvi_layer_fwd_fused_f32": 1, "whvi_layer_bwd_fused_f32": 3,
                       "whvi_layer_bwd_scaled_f32": 3, "whvi_layer_loss_f32": 3, "whvi_reparam_f32": 1,
                       "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1, "whvi_mc_moments_f32": 1,
-                      "whvi_mc_moments_strided_f32": 1, "whvi_adam_f32": 1, "whvi_layer_moments_f32": 1}
+                      "whvi_mc_moments_strided_f32": 1, "whvi_adam_f32": 1, "whvi_layer_moments_f32": 1,
+                      "whvi_reparam_dense_f32": 2, "whvi_reparam_dense_bwd_f32": 1, "whvi_kl_dense_f32": 2}
 # When set to a dict {"name": [(start_event, stop_event), ...]}, the named calls are bracketed
 # by CUDA events on the launching stream (bench.py's per-kernel roofline timing).
 EVENT_SINK: dict[str, list] | None = None
@@ -551,9 +552,9 @@ def reparam(mu, rho, eps):
 
 
 class ReparamDenseFunction(Function):
-    """g[s] = mu + L eps[s] with a dense lower-triangular L (D, D): the tcgen05 tensor-core
-    kernel (3xTF32 split).  Superset of the reference (whose posterior is diagonal).  The
-    backward is two plain library ops (column sum and one cuBLAS GEMM, dL = tril(dg^T eps))."""
+    """g[s] = mu + L eps[s] with a dense lower-triangular L (D, D), D a multiple of 128: superset of the reference (whose
+    posterior is diagonal).  Forward AND backward are the hand-written tcgen05 GEMM of ``csrc/reparam_dense.cu``
+    (TMA-fed, 3xTF32 operand split, TMEM accumulators): g = mu + E L^T, dL = tril(dg^T E); dmu is a column sum."""
 
     @staticmethod
     def forward(ctx, mu, L, eps):
@@ -562,21 +563,70 @@ class ReparamDenseFunction(Function):
         if L.shape != (D, D):
             raise RuntimeError(f"L must be {(D, D)}, got {tuple(L.shape)}")
         g = torch.empty_like(eps)
-        with torch.cuda.device(eps.device), _Timed("whvi_reparam_f32"):
-            rc = _lib.lib().whvi_reparam_f32(mu.data_ptr(), L.data_ptr(), eps.data_ptr(), g.data_ptr(), S, D, 1,
-                                             _stream(eps.device))
-        _lib.check(rc, "whvi_reparam_f32(dense)")
+        lib = _lib.lib()
+        need = ctypes.c_size_t(0)
+        _lib.check(lib.whvi_reparam_dense_workspace_bytes(S, D, ctypes.byref(need)), "whvi_reparam_dense_workspace_bytes")
+        ws = _workspace(eps.device, need.value)
+        with torch.cuda.device(eps.device), _Timed("whvi_reparam_dense_f32"):
+            rc = lib.whvi_reparam_dense_f32(mu.data_ptr(), L.data_ptr(), eps.data_ptr(), g.data_ptr(), S, D, ws.data_ptr(),
+                                            ws.numel(), _stream(eps.device))
+        _lib.check(rc, "whvi_reparam_dense_f32")
         ctx.save_for_backward(eps)
         return g
 
     @staticmethod
     def backward(ctx, dg):
         (eps,) = ctx.saved_tensors
-        return dg.sum(dim=0), torch.tril(dg.t() @ eps), None
+        dg = _f32c(dg, "dg")
+        S, D = eps.shape
+        Sp = (S + 31) // 32 * 32
+        # K-major operands for the tensor core: the transposes, zero-padded to a multiple of the 32-wide K block
+        dgT = torch.zeros((D, Sp), dtype=torch.float32, device=eps.device)
+        eT = torch.zeros((D, Sp), dtype=torch.float32, device=eps.device)
+        dgT[:, :S].copy_(dg.t())
+        eT[:, :S].copy_(eps.t())
+        dL = torch.zeros((D, D), dtype=torch.float32, device=eps.device)   # tiles above the diagonal are not written
+        with torch.cuda.device(eps.device), _Timed("whvi_reparam_dense_bwd_f32"):
+            rc = _lib.lib().whvi_reparam_dense_bwd_f32(dgT.data_ptr(), eT.data_ptr(), dL.data_ptr(), Sp, D, _stream(eps.device))
+        _lib.check(rc, "whvi_reparam_dense_bwd_f32")
+        return dg.sum(dim=0), dL, None
 
 
 def reparam_dense(mu, L, eps):
     return ReparamDenseFunction.apply(mu, L, eps)
+
+
+class KLDenseFunction(Function):
+    """KL( N(mu, L L^T) || N(0, lambda I) ) = 0.5 (D ln lambda - 2 sum ln L_ii - D + |L|_F^2 / lambda + |mu|^2 / lambda) with its
+    gradients in one pass over L (north-star kernel (5), dense form: the log-determinant is 2 sum ln L_ii)."""
+
+    @staticmethod
+    def forward(ctx, mu, L, lambda_):
+        mu, L = _f32c(mu, "g_mu"), _f32c(L, "g_L")
+        D = mu.numel()
+        if L.shape != (D, D):
+            raise RuntimeError(f"L must be {(D, D)}, got {tuple(L.shape)}")
+        out = torch.empty(1, dtype=torch.float32, device=mu.device)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        dmu = torch.empty_like(mu) if need_grad else None
+        dL = torch.empty_like(L) if need_grad else None
+        ws = torch.empty(D, dtype=torch.float64, device=mu.device)
+        with torch.cuda.device(mu.device), _Timed("whvi_kl_dense_f32"):
+            rc = _lib.lib().whvi_kl_dense_f32(mu.data_ptr(), L.data_ptr(), float(lambda_), D, out.data_ptr(), _ptr(dmu), _ptr(dL),
+                                              1.0, ws.data_ptr(), ws.numel() * 8, _stream(mu.device))
+        _lib.check(rc, "whvi_kl_dense_f32")
+        if need_grad:
+            ctx.save_for_backward(dmu, dL)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, dkl):
+        dmu, dL = ctx.saved_tensors
+        return dmu * dkl, dL * dkl, None
+
+
+def kl_gaussian_dense(mu, L, lambda_):
+    return KLDenseFunction.apply(mu, L, lambda_)
 
 
 class KLFunction(Function):

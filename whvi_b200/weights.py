@@ -65,7 +65,7 @@ def _rowscale(d: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
 
 
 class WHVISquarePow2Matrix(nn.Module):
-    def __init__(self, D, lambda_=1e-5, bias=False, *, semantics="paper", kl_mode=0):
+    def __init__(self, D, lambda_=1e-5, bias=False, *, semantics="paper", kl_mode=0, covariance="diag"):
         """Square WHVI matrix of size (D, D), D a power of two.
 
         :param int D: rows/columns; power of two.
@@ -74,6 +74,10 @@ class WHVISquarePow2Matrix(nn.Module):
         :param str semantics: "paper" or "reference" (module docstring).
         :param int kl_mode: 0 = the reference's KL formula (sigma used as a variance,
             src/utils.py:49-71), 1 = the statistically consistent sigma^2 form.
+        :param str covariance: "diag" -- the reference's posterior, g = mu + softplus(rho) * eps (src/weights.py:43-50);
+            "dense" -- superset: g = mu + L eps with a lower-triangular ``g_L`` (D, D) parameter in place of ``g_rho``
+            (D a multiple of 128, PAPER semantics), reparameterisation / its backward / the KL with log-determinant on
+            the tcgen05 kernels of ``csrc/reparam_dense.cu``.  Not in the reference: state_dicts differ (``g_L``).
         """
         super().__init__()
         if D < 1 or D & (D - 1):
@@ -83,8 +87,13 @@ class WHVISquarePow2Matrix(nn.Module):
         self.D = D
         self.lambda_ = lambda_
         self.padding = 0
+        if covariance not in ("diag", "dense"):
+            raise ValueError('covariance must be "diag" or "dense"')
+        if covariance == "dense" and (semantics != "paper" or D % 128 != 0):
+            raise ValueError('covariance="dense" needs semantics="paper" and D a multiple of 128')
         self.semantics = semantics
         self.kl_mode = kl_mode
+        self.covariance = covariance
         self.mc_samples = None      # set by WHVINetwork while it runs a forward pass
         self._eps_queue = []        # injected noise, consumed first-in first-out
 
@@ -93,7 +102,11 @@ class WHVISquarePow2Matrix(nn.Module):
         self.s1 = nn.Parameter(torch.randn(D) * 0.01)
         self.s2 = nn.Parameter(torch.randn(D) * 0.01)
         self.g_mu = nn.Parameter(torch.zeros(D))
-        self.g_rho = nn.Parameter(torch.rand(D) - 3)
+        g_rho = torch.rand(D) - 3
+        if covariance == "dense":   # start from the reference's diagonal posterior: L = diag(softplus(rho))
+            self.g_L = nn.Parameter(torch.diag(F.softplus(g_rho)))
+        else:
+            self.g_rho = nn.Parameter(g_rho)
         self._register_load_state_dict_pre_hook(_warn_paper_load, with_module=True)
 
     # ------------------------------------------------------------------ noise
@@ -115,14 +128,22 @@ class WHVISquarePow2Matrix(nn.Module):
 
     @property
     def g_sigma(self):
-        """Standard deviations of g: softplus(g_rho) (src/weights.py:43-50)."""
-        return F.softplus(self.g_rho)
+        """Standard deviations of g: softplus(g_rho) (src/weights.py:43-50); dense: the diagonal of L."""
+        return torch.diagonal(self.g_L) if self.covariance == "dense" else F.softplus(self.g_rho)
+
+    def _g(self, eps):
+        """(S, D) reparameterised samples of g for noise eps (S, D)."""
+        if self.covariance == "dense":
+            return WF.reparam_dense(self.g_mu, self.g_L, eps)
+        return WF.reparam(self.g_mu, self.g_rho, eps)
 
     @property
     def kl(self):
         """KL from the N(0, lambda I) prior to the posterior of g (src/weights.py:52-64)."""
         if self.g_mu.device.type != "cuda":
             raise RuntimeError("whvi_b200 runs on CUDA only (no CPU fallback); move the module to a GPU")
+        if self.covariance == "dense":
+            return WF.kl_gaussian_dense(self.g_mu, self.g_L, self.lambda_)
         return WF.kl_gaussian(self.g_mu, self.g_rho, self.lambda_, self.kl_mode)
 
     def w_bar(self, u):
@@ -134,8 +155,10 @@ class WHVISquarePow2Matrix(nn.Module):
 
     def sample(self):
         """One dense sample W (D x D)."""
-        eps = self._draw_eps(1)[0]
-        return self.w_bar(self.g_mu + self.g_sigma * eps)
+        eps = self._draw_eps(1)
+        if self.covariance == "dense":
+            return self.w_bar(self._g(eps)[0])
+        return self.w_bar(self.g_mu + self.g_sigma * eps[0])
 
     def _resolve_samples(self, x):
         if x.dim() == 3:
@@ -159,7 +182,7 @@ class WHVISquarePow2Matrix(nn.Module):
             if relu_out:
                 y = F.relu(y)
         else:
-            g = WF.reparam(self.g_mu, self.g_rho, eps)
+            g = self._g(eps)
             y = WF.whvi_layer(h, g, self.s1, self.s2, None if bias is None else bias.reshape(-1), relu_out, relu_in,
                               dy_scale_from)
         return y[0] if squeeze else y
@@ -173,7 +196,7 @@ class WHVISquarePow2Matrix(nn.Module):
         """Forward pass fused with sum (y - target)^2 (see functional.WHVILayerSqErrFunction).
         h: (B, D) or (S, B, D); target: (B, D).  Returns ((S, B, D) predictions, 0-d sum)."""
         S, _ = self._resolve_samples(h)
-        g = WF.reparam(self.g_mu, self.g_rho, self._draw_eps(S))
+        g = self._g(self._draw_eps(S))
         bias = None if self.bias is None else self.bias.reshape(-1)
         return WF.whvi_layer_sqerr(h, g, self.s1, self.s2, bias, target, relu_in)
 
@@ -181,7 +204,7 @@ class WHVISquarePow2Matrix(nn.Module):
         """Training-time fused last layer: sum (y - target)^2 with the layer's backward computed in
         the same pass (functional.WHVILayerLossFunction).  Returns the 0-d sum only."""
         S, _ = self._resolve_samples(h)
-        g = WF.reparam(self.g_mu, self.g_rho, self._draw_eps(S))
+        g = self._g(self._draw_eps(S))
         bias = None if self.bias is None else self.bias.reshape(-1)
         return WF.whvi_layer_loss(h, g, self.s1, self.s2, bias, target, relu_in, dx_scale_to)
 
@@ -189,8 +212,8 @@ class WHVISquarePow2Matrix(nn.Module):
                            scatter_to=None):
         """MC predictive sums (sum_s y, sum_s y^2, samples done) for inputs x (B, D) without the
         (S, B, D) tensor: see functional.predictive_moments (BASELINE config 5)."""
-        if self.semantics != "paper":
-            raise RuntimeError("predictive_moments implements the PAPER formula only")
+        if self.semantics != "paper" or self.covariance != "diag":
+            raise RuntimeError("predictive_moments implements the PAPER formula with the diagonal posterior only")
         eps = self._eps_queue.pop(0).to(device=self.g_mu.device, dtype=torch.float32) if self._eps_queue else None
         bias = None if self.bias is None else self.bias.reshape(-1)
         return WF.predictive_moments(x, self.g_mu, self.g_rho, self.s1, self.s2, bias, n_samples=n_samples,
