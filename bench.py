@@ -434,7 +434,19 @@ def run_ours(args):
         gbs = world * 8.0 * n * 10 / (ms * 1e-3) / 1e9
         fw.append({"D": Dk, "gbs": round(gbs, 1), "frac_of_measured": round(gbs / (peak * world), 4),
                    "frac_of_8TBs_nominal": round(gbs / (8000.0 * world), 4)})
-    del xf, yf
+    # the same sweep with bf16 activations in HBM (fp32 butterflies, one rounding at the store): 4 B/element
+    xb, yb = xf.to(torch.bfloat16), torch.empty(n, device=dev, dtype=torch.bfloat16)
+    fw16 = []
+    for k in (6, 8, 10, 12, 13, 15):
+        Dk = 1 << k
+        xv, yv = xb.view(n // Dk, Dk), yb.view(n // Dk, Dk)
+        for _ in range(3):
+            fwht_(xv, out=yv)
+        ms = timed(lambda: fwht_(xv, out=yv), 10)
+        gbs = world * 4.0 * n * 10 / (ms * 1e-3) / 1e9
+        fw16.append({"D": Dk, "gbs": round(gbs, 1), "frac_of_measured": round(gbs / (peak * world), 4),
+                     "elements_per_s_vs_f32": round((gbs / 4.0) / (fw[k - 6]["gbs"] / 8.0), 3)})
+    del xf, yf, xb, yb
 
     # ---- MC predictive evaluation (BASELINE config 5) over all ranks
     ev = None
@@ -462,7 +474,7 @@ def run_ours(args):
                        "last_loss": e2e_losses[-1]},
                "check": check, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                "fwht": {"elements_per_gpu": n, "unit": "GB/s", "n_gpus": world, "scaling": "weak (rows sharded, no collective)",
-                        "sweep": fw, "cpu_baseline": cpu_f, "ref_cuda_baseline": gpu_f},
+                        "sweep": fw, "bf16_io_sweep": fw16, "cpu_baseline": cpu_f, "ref_cuda_baseline": gpu_f},
                "eval": ev, "clocks": clk.summary()}
         print(json.dumps(out))
     if world > 1:

@@ -70,6 +70,10 @@ WHVI_API int whvi_fwht_f32(const float* in, float* out, int64_t rows, int64_t D,
  * src/fwht/cuda/fwht_cuda_kernel.cu:170, and its gradient check runs in double,
  * src/fwht/grad_check.py:26).  Parity tooling: correct for every D the fp32 entry accepts, not
  * tuned for bandwidth.  in == out allowed. */
+/* bf16 activations in HBM (not in the reference): the same transform with fp32 butterflies in registers and ONE
+ * rounding (to nearest even) at the store, i.e. out = bf16( whvi_fwht_f32( float(in) ) ); 4 B/element of HBM traffic instead
+ * of 8.  D <= 2^15 (single pass); pointers 8-byte aligned. */
+WHVI_API int whvi_fwht_bf16(const void* in, void* out, int64_t rows, int64_t D, whvi_stream_t stream);
 WHVI_API int whvi_fwht_f64(const double* in, double* out, int64_t rows, int64_t D, whvi_stream_t stream);
 
 /*
@@ -84,6 +88,12 @@ WHVI_API int whvi_fwht_f64(const double* in, double* out, int64_t rows, int64_t 
 WHVI_API int whvi_layer_fwd_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1,
                                 const float* s2, const float* bias, float* y, int64_t S, int64_t B, int64_t D,
                                 whvi_stream_t stream);
+
+/* The forward with bf16 activations in HBM (x, y bf16; g, s1, s2, bias fp32; arithmetic fp32, one rounding at the store):
+ * y = bf16( whvi_layer_fwd_fused_f32( float(x) ) ).  Inference-side variant: flags as the fused forward's
+ * (WHVI_LAYER_RELU_OUT, WHVI_LAYER_FROM_T2), no target. */
+WHVI_API int whvi_layer_fwd_bf16(const void* x, int64_t x_sample_stride, const float* g, const float* s1, const float* s2,
+                                 const float* bias, void* y, int64_t S, int64_t B, int64_t D, int flags, whvi_stream_t stream);
 
 /* Bytes of device workspace whvi_layer_bwd_f32 needs for this shape. */
 WHVI_API int whvi_layer_bwd_workspace_bytes(int64_t S, int64_t B, int64_t D, size_t* bytes);
@@ -195,6 +205,54 @@ WHVI_API int whvi_reparam_dense_bwd_f32(const float* dgT, const float* epsT, flo
                                         whvi_stream_t stream);
 WHVI_API int whvi_kl_dense_f32(const float* mu, const float* L, float lambda_, int64_t D, float* out_kl, float* dmu, float* dL,
                                float grad_scale, void* workspace, size_t workspace_bytes, whvi_stream_t stream);
+
+/*
+ * WHVIStackedMatrix (src/weights.py:111-208) as ONE call per direction: the G = ceil(n_out / D) square blocks of a
+ * non-square layer run as a second sample axis of the fused layer kernels instead of G launches + torch.cat (:179-180),
+ * with the reparameterisation (:82-83), the bias add (:204-205), the ReLU that follows the layer, the concatenation and
+ * the drop of the padded output columns (:207) inside the call.
+ *   x      (B, D) [x_sample_stride = 0] or (S, B, D): the input, zero-padded to D = next_pow2(n_in) columns
+ *          (whvi_pad_rows_f32 does src/weights.py:197-198)
+ *   mu, rho, s1, s2: block k's (D) vectors at + k * param_stride floats (param_stride >= D, multiple of 4): the blocks'
+ *          separate parameters are used where they lie when they are evenly spaced
+ *   eps    (G, S, D) noise, block-major;  bias (G * D) or NULL;  g (G, S, D) out: the reparameterised vectors (kept for backward)
+ *   y_blocks (G, S, B, D) scratch;  y (S, B, n_out) out, (G - 1) D < n_out <= G D
+ * Backward: dy (S, B, n_out) -> dmu, drho, ds1, ds2 (G, D) each, dbias (G * D) or NULL, dx (S, B, n_in) or NULL (the sum over
+ * the blocks, already un-padded; with a shared input the caller sums it over s).  Reductions are fixed-order.
+ */
+WHVI_API int whvi_pad_rows_f32(const float* in, float* out, int64_t rows, int64_t n_in, int64_t D, whvi_stream_t stream);
+WHVI_API int whvi_stacked_fwd_f32(const float* x, int64_t x_sample_stride, const float* mu, const float* rho, const float* s1,
+                                  const float* s2, int64_t param_stride, const float* eps, const float* bias, float* g,
+                                  float* y_blocks, float* y, int64_t S, int64_t B, int64_t D, int64_t G, int64_t n_out, int flags,
+                                  whvi_stream_t stream);
+WHVI_API int whvi_stacked_bwd_workspace_bytes(int64_t S, int64_t B, int64_t D, int64_t G, int want_dx, size_t* bytes);
+WHVI_API int whvi_stacked_bwd_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* g, const float* rho,
+                                  const float* s1, const float* s2, int64_t param_stride, const float* eps, float* dx, int64_t n_in,
+                                  float* dmu, float* drho, float* ds1, float* ds2, float* dbias, void* workspace,
+                                  size_t workspace_bytes, int64_t S, int64_t B, int64_t D, int64_t G, int64_t n_out, int flags,
+                                  whvi_stream_t stream);
+/* sum of the G blocks' KL terms (WHVIStackedMatrix.kl, src/weights.py:162-164) and their gradients (G, D), one launch */
+WHVI_API int whvi_kl_grouped_f32(const float* mu, const float* rho, float lambda_, int64_t D, int64_t G, int64_t param_stride,
+                                 int mode, float* out_kl, float* dmu, float* drho, float grad_scale, whvi_stream_t stream);
+
+/*
+ * WHVIColumnMatrix (src/weights.py:211-251), PAPER semantics, as ONE call per direction.  The reference samples the whole
+ * D x D matrix and keeps the first n entries of its flattening (:239-245), i.e. of row 0:
+ *     w[s, j] = s1[0] * s2[j] * (H g_s)[j], j < n,  g_s = mu + softplus(rho) * eps_s,  D = next_pow2(n) <= 32768
+ *   transposed != 0  (n_in = n, n_out = 1):  x (B, n) or (S, B, n);  y[s, b]    = sum_j x[s, b, j] w[s, j] + bias[0]
+ *   transposed == 0  (n_in = 1, n_out = n):  x (B, 1) or (S, B, 1);  y[s, b, j] = x[s, b] w[s, j] + bias[j]   (RELU_OUT allowed)
+ * mu, rho, s1, s2: (D); eps: (S, D); g: (S, D) scratch; hg: (S, D) out = H g, kept for the backward.
+ * Backward: dy as y; dx as x per sample (or NULL; RELU_IN masks it by x > 0, transposed form only); dmu, drho, ds1, ds2: (D);
+ * dbias: (1) / (n) or NULL.  Fixed-order reductions.
+ */
+WHVI_API int whvi_column_fwd_f32(const float* x, int64_t x_sample_stride, const float* mu, const float* rho, const float* s1,
+                                 const float* s2, const float* eps, const float* bias, float* g, float* hg, float* y, int64_t S,
+                                 int64_t B, int64_t D, int64_t n, int transposed, int flags, whvi_stream_t stream);
+WHVI_API int whvi_column_bwd_workspace_bytes(int64_t S, int64_t D, int64_t n, size_t* bytes);
+WHVI_API int whvi_column_bwd_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* hg, const float* rho,
+                                 const float* s1, const float* s2, const float* eps, float* dx, float* dmu, float* drho, float* ds1,
+                                 float* ds2, float* dbias, void* workspace, size_t workspace_bytes, int64_t S, int64_t B, int64_t D,
+                                 int64_t n, int transposed, int flags, whvi_stream_t stream);
 
 /* dmu = sum_s dg[s];  drho = (sum_s dg[s]*eps[s]) * sigmoid(rho).  accumulate != 0: += */
 WHVI_API int whvi_reparam_bwd_f32(const float* rho, const float* eps, const float* dg, float* dmu, float* drho,

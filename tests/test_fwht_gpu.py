@@ -191,3 +191,27 @@ def test_fp64_gradcheck():
     from whvi_b200 import FWHTFunction
     x = torch.randn(3, 16, dtype=torch.float64, device="cuda", requires_grad=True)
     assert torch.autograd.gradcheck(FWHTFunction.apply, (x,), eps=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("k,rows", [(0, 5), (1, 7), (2, 9), (6, 100), (9, 33), (10, 19), (11, 5), (12, 3), (13, 4), (15, 2)])
+def test_bf16_io_equals_fp32_kernel_rounded_once(k, rows):
+    """bf16 activations in HBM (not in the reference): fp32 butterflies in registers, ONE rounding at the store.
+    Stated tolerance: the result equals bf16(fp32 kernel(float(x))) bit for bit, i.e. it is within half a bf16 ulp
+    (2^-9 relative) of the fp32 transform of the same inputs."""
+    from whvi_b200 import FWHTFunction
+    D = 1 << k
+    torch.manual_seed(k)
+    x = torch.randn(rows, D, device=dev()).to(torch.bfloat16)
+    y = FWHTFunction.apply(x)
+    assert y.dtype == torch.bfloat16 and y.shape == x.shape
+    ref32 = FWHTFunction.apply(x.float())
+    assert torch.equal(y, ref32.to(torch.bfloat16))
+    # and the fp64 oracle on the same (bf16-representable) inputs, at bf16 resolution
+    ref64 = O.fwht(x.float().cpu().numpy().astype(np.float64))
+    err = np.abs(y.float().cpu().numpy() - ref64)
+    assert np.all(err <= 2.0 ** -8 * np.abs(ref64) + 1e-5 * np.abs(ref64).max())
+    # in place
+    z = x.clone()
+    from whvi_b200 import fwht_
+    fwht_(z, out=z)
+    assert torch.equal(z, y)

@@ -458,3 +458,26 @@ def test_deferred_scale_rides_on_the_graph():
     for shared, hook in ((True, False), (True, True), (False, True)):
         got = run(shared, hook)
         assert rel_err(got[0], base[0]) < 1e-6 and rel_err(got[1], base[1]) < 1e-6
+
+
+@pytest.mark.parametrize("S,B,D", [(2, 37, 16), (3, 9, 128), (2, 7, 1024), (2, 5, 4096), (2, 3, 8192), (2, 2, 32768)])
+@pytest.mark.parametrize("shared", [False, True])
+def test_forward_bf16_io(S, B, D, shared):
+    """whvi_layer_fwd_bf16: bf16 activations in HBM, fp32 parameters and arithmetic.  Stated tolerance: equal,
+    bit for bit, to the fp32 kernel's output on the same inputs rounded once to bf16 (so within 2^-9 relative of it)."""
+    from whvi_b200 import functional as F
+    x, g, s1, s2, _, bias = make_case(S, B, D, 3 * D + S, shared)
+    xb = t(x).to(torch.bfloat16)
+    for relu in (False, True):
+        y = F.layer_forward_bf16(xb, t(g), t(s1), t(s2), t(bias), relu_out=relu)
+        ref = F.layer_forward_raw(xb.float(), t(g), t(s1), t(s2), t(bias), relu_out=relu)
+        assert y.dtype == torch.bfloat16 and torch.equal(y, ref.to(torch.bfloat16))
+    y_ref = O.layer_fwd(xb.float().cpu().numpy().astype(np.float64), g, s1, s2, bias)
+    assert rel_err(F.layer_forward_bf16(xb, t(g), t(s1), t(s2), t(bias)).float().cpu().numpy(), y_ref) < 2.0 ** -8
+    if shared:   # hoisted first transform (config 5's evaluation path) with bf16 t2
+        t2 = F.layer_forward_raw  # noqa: F841 (documented pairing: t2 = H(s2 * x) from the fp32 FWHT, stored as bf16)
+        from whvi_b200 import fwht_
+        t2b = fwht_((xb.float() * t(s2))).to(torch.bfloat16)
+        y2 = F.layer_forward_bf16(t2b, t(g), t(s1), t(s2), t(bias), from_t2=True)
+        ref2 = F.layer_forward_raw(t2b.float(), t(g), t(s1), t(s2), t(bias), from_t2=True)
+        assert torch.equal(y2, ref2.to(torch.bfloat16))

@@ -157,6 +157,136 @@ def test_paper_semantics_vs_oracle(n_in, n_out, bias, shared):
     assert rel_err(y.detach().cpu().numpy(), ref) < TOL
 
 
+@pytest.mark.parametrize("n_in,n_out,bias", [(3, 16, False), (13, 128, True), (20, 50, True), (16, 40, False), (128, 300, True), (1024, 2048, False)])
+@pytest.mark.parametrize("shared", [True, False])
+@pytest.mark.parametrize("relu", [False, True])
+def test_stacked_one_launch_equals_block_by_block(n_in, n_out, bias, shared, relu):
+    """WHVIStackedMatrix as one grouped launch per direction (whvi_stacked_fwd/bwd_f32, src/weights.py:179-208) against the
+    same module run block after block like the reference: outputs, KL, input and every parameter gradient."""
+    import copy
+    torch.manual_seed(n_in + n_out)
+    S, B = 3, 7
+    a = W.WHVILinear(n_in, n_out, lambda_=3.0, bias=bias).to(dev())
+    with torch.no_grad():
+        for name, p in a.named_parameters():
+            p.copy_(torch.randn_like(p) * (0.5 if name.endswith("g_rho") else 1.0))
+    b = copy.deepcopy(a)
+    b.weight_submodule.one_launch = False
+    assert a.weight_submodule.grouped and not b.weight_submodule.grouped
+    x = torch.randn((B, n_in) if shared else (S, B, n_in), device=dev())
+    if relu:
+        x = x.relu()     # the layer as the consumer of a fused ReLU: dx is masked by (x > 0)
+    G, D = a.weight_submodule.stack, a.weight_submodule.D_in
+    eps = torch.randn(G, S, D, device=dev())
+    dy = torch.randn(S, B, n_out, device=dev())
+    res = []
+    for layer, fused in ((a, True), (b, False)):
+        for k, blk in enumerate(layer.square_blocks()):
+            blk.inject_eps(eps[k])
+        layer.mc_samples = S
+        xi = x.clone().requires_grad_()
+        if fused:
+            y = layer.weight_submodule.forward(xi, relu_out=relu, relu_in=relu)
+        else:
+            y = layer.weight_submodule.forward(xi)
+            y = y.relu() if relu else y
+        layer.mc_samples = None
+        kl = layer.kl
+        # a fused ReLU's mask is applied by the CONSUMER's backward (relu_in), so the upstream gradient arrives masked
+        w = dy * (y.detach() > 0) if relu else dy
+        ((y * w).sum() + 0.7 * kl).backward()
+        dx = xi.grad * (x > 0) if (relu and not fused) else xi.grad
+        res.append((y.detach(), kl.detach(), dx, {n: p.grad for n, p in layer.named_parameters()}))
+    (y1, kl1, dx1, g1), (y0, kl0, dx0, g0) = res
+    assert y1.shape == (S, B, n_out)
+    assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) < 1e-5
+    assert abs(kl1.item() - kl0.item()) < 1e-5 * abs(kl0.item())
+    assert rel_err(dx1.cpu().numpy(), dx0.cpu().numpy()) < TOL
+    for n in g0:
+        assert rel_err(g1[n].cpu().numpy(), g0[n].cpu().numpy()) < TOL, n
+    # the parameters were packed evenly spaced on the first call: the kernels read them where they lie
+    from whvi_b200 import functional as F
+    assert F.uniform_stride([blk.s1 for blk in a.square_blocks()]) is not None
+
+
+@pytest.mark.parametrize("n,transposed,bias", [(128, True, True), (100, True, False), (1, True, True), (8, False, True), (50, False, False),
+                                               (2, True, False), (3000, True, True), (3000, False, True)])
+@pytest.mark.parametrize("shared", [True, False])
+def test_column_one_call_equals_op_chain(n, transposed, bias, shared):
+    """WHVIColumnMatrix in one C-ABI call per direction (whvi_column_fwd/bwd_f32, src/weights.py:231-251) against round 1's op
+    chain (reparam -> FWHT of g -> torch products), which test_paper_semantics_vs_oracle pins to the fp64 oracle."""
+    import copy
+    torch.manual_seed(n)
+    S, B = 3, 9
+    a = (W.WHVILinear(n, 1, lambda_=3.0, bias=bias) if transposed else W.WHVILinear(1, n, lambda_=3.0, bias=bias)).to(dev())
+    if n == 1:
+        a = W.WHVILinear(1, 1, lambda_=3.0, bias=bias).to(dev())
+    with torch.no_grad():
+        for name, p in a.named_parameters():
+            p.copy_(torch.randn_like(p) * (0.5 if name.endswith("g_rho") else 1.0))
+    b = copy.deepcopy(a)
+    b.weight_submodule.one_launch = False
+    assert a.weight_submodule.fused and not b.weight_submodule.fused
+    width = a.weight_submodule.D if a.weight_submodule.transposed else 1
+    x = torch.randn((B, width) if shared else (S, B, width), device=dev())
+    relu = a.weight_submodule.transposed   # as the consumer of a folded ReLU
+    if relu:
+        x = x.relu()
+    D = a.weight_submodule.D_adjusted
+    eps = torch.randn(S, D, device=dev())
+    res = []
+    for layer, fused in ((a, True), (b, False)):
+        layer.square_blocks()[0].inject_eps(eps)
+        layer.mc_samples = S
+        xi = x.clone().requires_grad_()
+        y = layer.weight_submodule.forward(xi, relu_in=relu) if fused else layer.weight_submodule.forward(xi)
+        layer.mc_samples = None
+        dy = torch.cos(torch.arange(y.numel(), device=dev(), dtype=torch.float32)).reshape(y.shape)
+        (y * dy).sum().backward()
+        dx = xi.grad * (x > 0) if (relu and not fused) else xi.grad
+        res.append((y.detach(), dx, {k: p.grad for k, p in layer.named_parameters()}))
+    (y1, dx1, g1), (y0, dx0, g0) = res
+    assert y1.shape == y0.shape == (S, B, 1 if a.weight_submodule.transposed else n)
+    assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) < 1e-5
+    assert rel_err(dx1.cpu().numpy(), dx0.cpu().numpy()) < TOL
+    for k in g0:
+        ref = g0[k].cpu().numpy()
+        if np.abs(ref).max() == 0:
+            assert np.abs(g1[k].cpu().numpy()).max() == 0, k
+        else:
+            assert rel_err(g1[k].cpu().numpy(), ref) < TOL, k
+
+
+def test_stacked_network_fused_equals_unfused():
+    """BASELINE config 3's shape (13 -> 128 -> 128 -> 1 with ReLUs): the grouped Stacked launch with the ReLU folded into it
+    and into the consumer's backward gives the same loss and gradients as every module run on its own."""
+    import copy
+    torch.manual_seed(5)
+    S, B = 4, 33
+    fused = W.WHVIRegression([W.WHVILinear(13, 128, lambda_=3.0, bias=True), torch.nn.ReLU(), W.WHVILinear(128, 128, lambda_=3.0),
+                              torch.nn.ReLU(), W.WHVILinear(128, 1, lambda_=3.0)], train_samples=S).to(dev()).train()
+    plain = copy.deepcopy(fused)
+    plain.fuse = False
+    for m in plain._whvi_layers():
+        if isinstance(m.weight_submodule, (W.WHVIStackedMatrix, W.WHVIColumnMatrix)):
+            m.weight_submodule.one_launch = False
+    x, y = torch.randn(B, 13, device=dev()), torch.randn(B, 1, device=dev())
+    blocks = [b for layer in fused._whvi_layers() for b in layer.square_blocks()]
+    eps = [torch.randn(S, b.D, device=dev()) for b in blocks]
+    out = []
+    for model in (fused, plain):
+        for b, e in zip([b for layer in model._whvi_layers() for b in layer.square_blocks()], eps):
+            b.inject_eps(e)
+        loss = model.loss(x, y, n=1000)
+        loss.backward()
+        out.append((loss.item(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    assert abs(out[0][0] - out[1][0]) < 1e-5 * abs(out[1][0])
+    assert out[0][1].keys() == out[1][1].keys()
+    scale = max(float(v.abs().max()) for v in out[1][1].values())
+    for n, v in out[1][1].items():
+        assert float((out[0][1][n] - v).abs().max()) < TOL * scale, n
+
+
 def test_standalone_call_is_two_dimensional_and_dense_sample_agrees():
     torch.manual_seed(3)
     layer = W.WHVISquarePow2Matrix(64, lambda_=1.0).to(dev())

@@ -139,8 +139,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
     ap.add_argument("--c5-inputs", type=int, default=8192)
+    ap.add_argument("--only", default="", help="comma-separated subset, e.g. C1,C3")
     args = ap.parse_args()
-    res = {"C1": c1(), "C2": c2(), "C3": c3(), "C5": c5(args.c5_inputs)}
+    runs = {"C1": c1, "C2": c2, "C3": c3, "C5": lambda: c5(args.c5_inputs)}
+    only = [k for k in args.only.split(",") if k] or list(runs)
+    res = {k: runs[k]() for k in only}
     print(json.dumps(res, indent=1))
     if args.out:
         Path(args.out).parent.mkdir(parents=True, exist_ok=True)

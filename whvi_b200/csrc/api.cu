@@ -30,6 +30,16 @@ int whvi_fwht_f32(const float* in, float* out, int64_t rows, int64_t D, whvi_str
     return launch_fwht(in, out, rows, D, static_cast<cudaStream_t>(stream));
 }
 
+int whvi_fwht_bf16(const void* in, void* out, int64_t rows, int64_t D, whvi_stream_t stream)
+{
+    if (rows < 0 || D < 1) return fail(WHVI_E_SHAPE, "fwht_bf16: rows=%lld D=%lld", (long long)rows, (long long)D);
+    if (!is_pow2(D)) return fail(WHVI_E_SHAPE, "fwht_bf16: n must be a power of 2 (got %lld)", (long long)D);
+    if (rows == 0) return WHVI_OK;
+    if (!in || !out) return fail(WHVI_E_NULL, "fwht_bf16: null pointer");
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 7u) return fail(WHVI_E_ALIGN, "fwht_bf16: pointers must be 8-byte aligned");
+    return launch_fwht_bf16(in, out, rows, D, static_cast<cudaStream_t>(stream));
+}
+
 int whvi_fwht_f64(const double* in, double* out, int64_t rows, int64_t D, whvi_stream_t stream)
 {
     if (rows < 0 || D < 1) return fail(WHVI_E_SHAPE, "fwht_f64: rows=%lld D=%lld", (long long)rows, (long long)D);
@@ -80,6 +90,23 @@ int whvi_layer_fwd_fused_f32(const float* x, int64_t x_sample_stride, const floa
         return fail(WHVI_E_ALIGN, "layer_fwd: pointers must be 16-byte aligned");
     LayerFwdCall c{x, g, s1, s2, bias, target, y, sq_partials, x_sample_stride, S, B, flags & WHVI_LAYER_RELU_OUT, nullptr};
     c.from_t2 = (flags & WHVI_LAYER_FROM_T2) ? 1 : 0;
+    return launch_layer_fwd(c, D, static_cast<cudaStream_t>(stream));
+}
+
+int whvi_layer_fwd_bf16(const void* x, int64_t x_sample_stride, const float* g, const float* s1, const float* s2, const float* bias,
+                        void* y, int64_t S, int64_t B, int64_t D, int flags, whvi_stream_t stream)
+{
+    if (int rc = check_layer_shape("layer_fwd_bf16", S, B, D, x_sample_stride, 32768)) return rc;
+    if (flags & ~(WHVI_LAYER_RELU_OUT | WHVI_LAYER_FROM_T2)) return fail(WHVI_E_MODE, "layer_fwd_bf16: unknown flags %d", flags);
+    if (S == 0 || B == 0) return WHVI_OK;
+    if (!x || !g || !s1 || !s2 || !y) return fail(WHVI_E_NULL, "layer_fwd_bf16: null pointer");
+    if (!aligned16(g) || !aligned16(s1) || !aligned16(s2) || !aligned16(bias) ||
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 7u))
+        return fail(WHVI_E_ALIGN, "layer_fwd_bf16: fp32 pointers must be 16-byte aligned, bf16 pointers 8-byte aligned");
+    LayerFwdCall c{static_cast<const float*>(x), g, s1, s2, bias, nullptr, static_cast<float*>(y), nullptr, x_sample_stride, S, B,
+                   flags & WHVI_LAYER_RELU_OUT, nullptr};
+    c.from_t2 = (flags & WHVI_LAYER_FROM_T2) ? 1 : 0;
+    c.bf16 = 1;
     return launch_layer_fwd(c, D, static_cast<cudaStream_t>(stream));
 }
 
@@ -259,6 +286,189 @@ int whvi_kl_f32(const float* mu, const float* rho, float lambda_, int64_t D, int
     if (!mu || !rho || !out_kl) return fail(WHVI_E_NULL, "kl: null pointer");
     if ((dmu == nullptr) != (drho == nullptr)) return fail(WHVI_E_NULL, "kl: dmu and drho must both be given or both NULL");
     return launch_kl(mu, rho, lambda_, D, mode, out_kl, dmu, drho, grad_scale, accumulate, static_cast<cudaStream_t>(stream));
+}
+
+// ---- WHVIStackedMatrix as one call per direction (csrc/stacked.cu) ------------------------------------------------------
+static int check_stacked(const char* who, int64_t S, int64_t B, int64_t D, int64_t G, int64_t n_out, int64_t xs, int64_t pstride)
+{
+    if (int rc = check_layer_shape(who, S, B, D, xs)) return rc;
+    if (G < 1 || n_out <= (G - 1) * D || n_out > G * D)
+        return fail(WHVI_E_SHAPE, "%s: G=%lld blocks of D=%lld do not match n_out=%lld", who, (long long)G, (long long)D, (long long)n_out);
+    if (G > 1 && (pstride < D || pstride % 4 != 0))
+        return fail(WHVI_E_SHAPE, "%s: param_stride=%lld must be >= D and a multiple of 4", who, (long long)pstride);
+    if (S * G > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "%s: too many virtual samples", who);
+    return WHVI_OK;
+}
+
+int whvi_pad_rows_f32(const float* in, float* out, int64_t rows, int64_t n_in, int64_t D, whvi_stream_t stream)
+{
+    if (rows < 0 || n_in < 1 || D < n_in || D % 4 != 0) return fail(WHVI_E_SHAPE, "pad_rows: rows=%lld n_in=%lld D=%lld", (long long)rows, (long long)n_in, (long long)D);
+    if (rows == 0) return WHVI_OK;
+    if (!in || !out) return fail(WHVI_E_NULL, "pad_rows: null pointer");
+    if (!aligned16(out)) return fail(WHVI_E_ALIGN, "pad_rows: out must be 16-byte aligned");
+    return launch_stack_split(in, out, rows, D, 1, n_in, static_cast<cudaStream_t>(stream));
+}
+
+int whvi_stacked_fwd_f32(const float* x, int64_t x_sample_stride, const float* mu, const float* rho, const float* s1, const float* s2,
+                         int64_t param_stride, const float* eps, const float* bias, float* g, float* y_blocks, float* y, int64_t S,
+                         int64_t B, int64_t D, int64_t G, int64_t n_out, int flags, whvi_stream_t stream)
+{
+    if (int rc = check_stacked("stacked_fwd", S, B, D, G, n_out, x_sample_stride, param_stride)) return rc;
+    if (flags & ~WHVI_LAYER_RELU_OUT) return fail(WHVI_E_MODE, "stacked_fwd: unknown flags %d", flags);
+    if (S == 0 || B == 0) return WHVI_OK;
+    if (!x || !mu || !rho || !s1 || !s2 || !eps || !g || !y_blocks || !y) return fail(WHVI_E_NULL, "stacked_fwd: null pointer");
+    if (!aligned16(x) || !aligned16(s1) || !aligned16(s2) || !aligned16(bias) || !aligned16(g) || !aligned16(y_blocks))
+        return fail(WHVI_E_ALIGN, "stacked_fwd: pointers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (int rc = launch_reparam_diag(mu, rho, eps, g, G * S, D, st, G, param_stride)) return rc;
+    LayerFwdCall c{x, g, s1, s2, bias, nullptr, y_blocks, nullptr, x_sample_stride, G * S, B, flags & WHVI_LAYER_RELU_OUT, nullptr};
+    c.groups = G;
+    c.pstride = param_stride;
+    c.bstride = D;
+    if (int rc = launch_layer_fwd(c, D, st)) return rc;
+    return launch_stack_concat(y_blocks, y, S * B, D, G, n_out, st);
+}
+
+static size_t stacked_bwd_layout(int64_t S, int64_t B, int64_t D, int64_t G, int want_dx, size_t layer_ws, size_t* off_dx, size_t* off_dg,
+                                 size_t* off_ws)
+{
+    const size_t blocks = sizeof(float) * size_t(G) * S * B * D;
+    size_t o = blocks;                       // [0, blocks): dy in the block layout
+    *off_dx = o;
+    if (want_dx) o += blocks;
+    *off_dg = o;
+    o += sizeof(float) * size_t(G) * S * D;
+    o = (o + 255) / 256 * 256;
+    *off_ws = o;
+    return o + layer_ws;
+}
+
+int whvi_stacked_bwd_workspace_bytes(int64_t S, int64_t B, int64_t D, int64_t G, int want_dx, size_t* bytes)
+{
+    if (!bytes) return fail(WHVI_E_NULL, "stacked_bwd_workspace_bytes: null pointer");
+    if (int rc = check_stacked("stacked_bwd_workspace_bytes", S, B, D, G, G * D, 0, D)) return rc;
+    *bytes = 0;
+    if (S == 0 || B == 0) return WHVI_OK;
+    size_t layer_ws = 0;
+    LayerBwdCall c{};
+    c.S = S * G;
+    c.B = B;
+    c.need_only = &layer_ws;
+    if (int rc = launch_layer_bwd(c, D, nullptr)) return rc;
+    size_t a, b, d;
+    *bytes = stacked_bwd_layout(S, B, D, G, want_dx, layer_ws, &a, &b, &d);
+    return WHVI_OK;
+}
+
+int whvi_stacked_bwd_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* g, const float* rho, const float* s1,
+                         const float* s2, int64_t param_stride, const float* eps, float* dx, int64_t n_in, float* dmu, float* drho,
+                         float* ds1, float* ds2, float* dbias, void* workspace, size_t workspace_bytes, int64_t S, int64_t B, int64_t D,
+                         int64_t G, int64_t n_out, int flags, whvi_stream_t stream)
+{
+    if (int rc = check_stacked("stacked_bwd", S, B, D, G, n_out, x_sample_stride, param_stride)) return rc;
+    if (flags & ~WHVI_LAYER_RELU_IN) return fail(WHVI_E_MODE, "stacked_bwd: unknown flags %d", flags);
+    if (dx && (n_in < 1 || n_in > D)) return fail(WHVI_E_SHAPE, "stacked_bwd: n_in=%lld outside [1, D]", (long long)n_in);
+    if (!dmu || !drho || !ds1 || !ds2) return fail(WHVI_E_NULL, "stacked_bwd: null output pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (S == 0 || B == 0) {
+        for (float* p : {dmu, drho, ds1, ds2, dbias})
+            if (p) cudaMemsetAsync(p, 0, sizeof(float) * size_t(G) * D, st);
+        return check_launch("stacked_bwd(empty)");
+    }
+    if (!x || !dy || !g || !rho || !s1 || !s2 || !eps) return fail(WHVI_E_NULL, "stacked_bwd: null pointer");
+    if (!aligned16(x) || !aligned16(g) || !aligned16(s1) || !aligned16(s2) || !aligned16(workspace))
+        return fail(WHVI_E_ALIGN, "stacked_bwd: pointers must be 16-byte aligned");
+    size_t layer_ws = 0;
+    {
+        LayerBwdCall q{};
+        q.S = S * G;
+        q.B = B;
+        q.need_only = &layer_ws;
+        if (int rc = launch_layer_bwd(q, D, nullptr)) return rc;
+    }
+    size_t off_dx, off_dg, off_ws;
+    const size_t need = stacked_bwd_layout(S, B, D, G, dx != nullptr, layer_ws, &off_dx, &off_dg, &off_ws);
+    if (!workspace || workspace_bytes < need) return fail(WHVI_E_WORKSPACE, "stacked_bwd: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    char* base = static_cast<char*>(workspace);
+    float* dyb = reinterpret_cast<float*>(base);
+    float* dxb = dx ? reinterpret_cast<float*>(base + off_dx) : nullptr;
+    float* dg = reinterpret_cast<float*>(base + off_dg);
+    if (int rc = launch_stack_split(dy, dyb, S * B, D, G, n_out, st)) return rc;
+    LayerBwdCall c{x, dyb, g, s1, s2, nullptr, nullptr, nullptr, dxb, dg, ds1, ds2, dbias, reinterpret_cast<float*>(base + off_ws),
+                   layer_ws, x_sample_stride, S * G, B, flags & WHVI_LAYER_RELU_IN, nullptr};
+    c.groups = G;
+    c.pstride = param_stride;
+    if (int rc = launch_layer_bwd(c, D, st)) return rc;
+    if (int rc = launch_reparam_diag_bwd(rho, eps, dg, dmu, drho, S, D, 0, st, G, param_stride)) return rc;
+    if (dx) return launch_stack_sum(dxb, dx, S * B, D, G, n_in, st);
+    return WHVI_OK;
+}
+
+int whvi_kl_grouped_f32(const float* mu, const float* rho, float lambda_, int64_t D, int64_t G, int64_t param_stride, int mode,
+                        float* out_kl, float* dmu, float* drho, float grad_scale, whvi_stream_t stream)
+{
+    if (D < 1 || G < 1 || (G > 1 && param_stride < D)) return fail(WHVI_E_SHAPE, "kl_grouped: D=%lld G=%lld stride=%lld", (long long)D, (long long)G, (long long)param_stride);
+    if (mode != WHVI_KL_REFERENCE && mode != WHVI_KL_CONSISTENT) return fail(WHVI_E_MODE, "kl_grouped: unknown mode %d", mode);
+    if (!(lambda_ > 0.f)) return fail(WHVI_E_SHAPE, "kl_grouped: lambda must be positive");
+    if (!mu || !rho || !out_kl) return fail(WHVI_E_NULL, "kl_grouped: null pointer");
+    if ((dmu == nullptr) != (drho == nullptr)) return fail(WHVI_E_NULL, "kl_grouped: dmu and drho must both be given or both NULL");
+    return launch_kl(mu, rho, lambda_, D, mode, out_kl, dmu, drho, grad_scale, 0, static_cast<cudaStream_t>(stream), G, param_stride);
+}
+
+// ---- WHVIColumnMatrix as one call per direction (csrc/column.cu) --------------------------------------------------------
+static int check_column(const char* who, int64_t S, int64_t B, int64_t D, int64_t n, int64_t xs, int transposed)
+{
+    if (S < 0 || B < 0 || D < 1 || !is_pow2(D) || D > (int64_t(1) << kMaxLog2D) || n < 1 || n > D || (D > 1 && n <= D / 2))
+        return fail(WHVI_E_SHAPE, "%s: S=%lld B=%lld D=%lld n=%lld (D = next_pow2(n) <= 32768)", who, (long long)S, (long long)B, (long long)D, (long long)n);
+    const int64_t row = transposed ? n : 1;
+    if (xs != 0 && xs != B * row) return fail(WHVI_E_SHAPE, "%s: x_sample_stride must be 0 or B * %lld", who, (long long)row);
+    return WHVI_OK;
+}
+
+int whvi_column_fwd_f32(const float* x, int64_t x_sample_stride, const float* mu, const float* rho, const float* s1, const float* s2,
+                        const float* eps, const float* bias, float* g, float* hg, float* y, int64_t S, int64_t B, int64_t D, int64_t n,
+                        int transposed, int flags, whvi_stream_t stream)
+{
+    if (int rc = check_column("column_fwd", S, B, D, n, x_sample_stride, transposed)) return rc;
+    if (flags & ~WHVI_LAYER_RELU_OUT) return fail(WHVI_E_MODE, "column_fwd: unknown flags %d", flags);
+    if ((flags & WHVI_LAYER_RELU_OUT) && transposed) return fail(WHVI_E_MODE, "column_fwd: RELU_OUT applies to the (.., 1) -> (.., n) form only");
+    if (S == 0 || B == 0) return WHVI_OK;
+    if (!x || !mu || !rho || !s1 || !s2 || !eps || !g || !hg || !y) return fail(WHVI_E_NULL, "column_fwd: null pointer");
+    if (!aligned16(g) || !aligned16(hg)) return fail(WHVI_E_ALIGN, "column_fwd: g and hg must be 16-byte aligned");
+    return launch_column_fwd(x, x_sample_stride, mu, rho, s1, s2, eps, bias, g, hg, y, S, B, D, n, transposed, flags & WHVI_LAYER_RELU_OUT,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int whvi_column_bwd_workspace_bytes(int64_t S, int64_t D, int64_t n, size_t* bytes)
+{
+    if (!bytes) return fail(WHVI_E_NULL, "column_bwd_workspace_bytes: null pointer");
+    if (S < 0 || D < 1 || n < 1 || n > D) return fail(WHVI_E_SHAPE, "column_bwd_workspace_bytes: S=%lld D=%lld n=%lld", (long long)S, (long long)D, (long long)n);
+    *bytes = column_bwd_workspace_bytes(S, D, n);
+    return WHVI_OK;
+}
+
+int whvi_column_bwd_f32(const float* x, int64_t x_sample_stride, const float* dy, const float* hg, const float* rho, const float* s1,
+                        const float* s2, const float* eps, float* dx, float* dmu, float* drho, float* ds1, float* ds2, float* dbias,
+                        void* workspace, size_t workspace_bytes, int64_t S, int64_t B, int64_t D, int64_t n, int transposed, int flags,
+                        whvi_stream_t stream)
+{
+    if (int rc = check_column("column_bwd", S, B, D, n, x_sample_stride, transposed)) return rc;
+    if (flags & ~WHVI_LAYER_RELU_IN) return fail(WHVI_E_MODE, "column_bwd: unknown flags %d", flags);
+    if ((flags & WHVI_LAYER_RELU_IN) && !transposed) return fail(WHVI_E_MODE, "column_bwd: RELU_IN applies to the (.., n) -> (.., 1) form only");
+    if (!dmu || !drho || !ds1 || !ds2) return fail(WHVI_E_NULL, "column_bwd: null output pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (S == 0 || B == 0) {
+        for (float* p : {dmu, drho, ds1, ds2})
+            cudaMemsetAsync(p, 0, sizeof(float) * size_t(D), st);
+        if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * size_t(transposed ? 1 : n), st);
+        return check_launch("column_bwd(empty)");
+    }
+    if (!x || !dy || !hg || !rho || !s1 || !s2 || !eps) return fail(WHVI_E_NULL, "column_bwd: null pointer");
+    if (!aligned16(workspace)) return fail(WHVI_E_ALIGN, "column_bwd: workspace must be 16-byte aligned");
+    const size_t need = column_bwd_workspace_bytes(S, D, n);
+    if (!workspace || workspace_bytes < need) return fail(WHVI_E_WORKSPACE, "column_bwd: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    return launch_column_bwd(x, x_sample_stride, dy, hg, rho, s1, s2, eps, dx, dmu, drho, ds1, ds2, dbias, static_cast<float*>(workspace), S,
+                             B, D, n, transposed, flags & WHVI_LAYER_RELU_IN, st);
 }
 
 int whvi_layer_moments_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1, const float* s2,

@@ -54,6 +54,7 @@ constexpr int kMaxLog2D = 15;       // single-pass kernels keep a whole row in o
 constexpr int kMaxLog2Dmulti = 30;  // multi-pass global variant beyond that
 
 int launch_fwht(const float* in, float* out, int64_t rows, int64_t D, cudaStream_t stream);
+int launch_fwht_bf16(const void* in, void* out, int64_t rows, int64_t D, cudaStream_t stream);
 int launch_fwht_f64(const double* in, double* out, int64_t rows, int64_t D, cudaStream_t stream);
 struct LayerFwdCall {
     const float *x, *g, *s1, *s2, *bias, *target;
@@ -62,6 +63,11 @@ struct LayerFwdCall {
     int relu_out;
     size_t* partials_needed;  // query mode: number of floats of sq_partials
     int from_t2 = 0;          // x already holds H(s2 * x)
+    // grouped launch (a Stacked layer's blocks as extra samples, src/weights.py:179-180): S counts VIRTUAL samples
+    // s' = block * (S / groups) + sample; block k reads s1/s2 at + k * pstride floats, bias at + k * bstride, and the input
+    // of sample s' % (S / groups)
+    int64_t groups = 1, pstride = 0, bstride = 0;
+    int bf16 = 0;             // x and y are bf16 in HBM (arithmetic stays fp32)
 };
 struct LayerBwdCall {
     const float *x, *dy, *g, *s1, *s2, *target, *coef, *dy_scale;
@@ -70,6 +76,7 @@ struct LayerBwdCall {
     int64_t xs, S, B;
     int relu_in;
     size_t* need_only;  // query mode: workspace bytes
+    int64_t groups = 1, pstride = 0;  // grouped launch (see LayerFwdCall): ds1 / ds2 / dbias are (groups, D)
 };
 struct LayerLossCall {  // fused last layer: forward + Gaussian-MNLL residual + backward in one pass
     const float *x, *g, *s1, *s2, *bias, *target;
@@ -82,11 +89,11 @@ struct LayerLossCall {  // fused last layer: forward + Gaussian-MNLL residual + 
 };
 int launch_layer_loss(const LayerLossCall& c, int64_t D, cudaStream_t stream);
 int launch_bwd_reduce(float* ws, float* dg, float* ds1, float* ds2, float* dbias, int64_t S, int slabs_per_sample,
-                      int64_t tile, int64_t D, cudaStream_t stream);
+                      int64_t tile, int64_t D, cudaStream_t stream, int64_t groups = 1);
 int launch_layer_fwd(const LayerFwdCall& c, int64_t D, cudaStream_t stream);
 int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream);
 int launch_reparam_diag(const float* mu, const float* rho, const float* eps, float* g, int64_t S, int64_t D,
-                        cudaStream_t stream);
+                        cudaStream_t stream, int64_t groups = 1, int64_t pstride = 0);
 size_t reparam_dense_workspace_bytes(int64_t S, int64_t D);
 int launch_reparam_dense(const float* mu, const float* L, const float* eps, float* g, int64_t S, int64_t D, float* ws, size_t ws_bytes,
                          cudaStream_t stream);
@@ -94,7 +101,17 @@ int launch_reparam_dense_bwd(const float* dgT, const float* eT, float* dL, int64
 int launch_kl_dense(const float* mu, const float* L, float lambda_, int64_t D, float* out, float* dmu, float* dL, float grad_scale,
                     double* row_sq, cudaStream_t stream);
 int launch_reparam_diag_bwd(const float* rho, const float* eps, const float* dg, float* dmu, float* drho, int64_t S,
-                            int64_t D, int accumulate, cudaStream_t stream);
+                            int64_t D, int accumulate, cudaStream_t stream, int64_t groups = 1, int64_t pstride = 0);
+int launch_stack_split(const float* in, float* blocks, int64_t R, int64_t D, int64_t G, int64_t n_out, cudaStream_t stream);
+int launch_stack_concat(const float* blocks, float* out, int64_t R, int64_t D, int64_t G, int64_t n_out, cudaStream_t stream);
+int launch_stack_sum(const float* dxb, float* dx, int64_t R, int64_t D, int64_t G, int64_t n_in, cudaStream_t stream);
+int launch_column_fwd(const float* x, int64_t xs, const float* mu, const float* rho, const float* s1, const float* s2, const float* eps,
+                      const float* bias, float* g, float* hg, float* y, int64_t S, int64_t B, int64_t D, int64_t n, int transposed, int relu_out,
+                      cudaStream_t st);
+size_t column_bwd_workspace_bytes(int64_t S, int64_t D, int64_t n);
+int launch_column_bwd(const float* x, int64_t xs, const float* dy, const float* hg, const float* rho, const float* s1, const float* s2,
+                      const float* eps, float* dx, float* dmu, float* drho, float* ds1, float* ds2, float* dbias, float* ws, int64_t S,
+                      int64_t B, int64_t D, int64_t n, int transposed, int relu_in, cudaStream_t st);
 int launch_layer_moments(const float* x, int64_t xs, const float* g, const float* s1, const float* s2, const float* bias, float* sum_y,
                          float* sum_y2, int64_t S, int64_t B, int64_t D, int from_t2, int accumulate, int reserve_sms, cudaStream_t stream);
 int launch_mc_moments(const float* y, int64_t y_sample_stride, const float* in_y, const float* in_y2, float* out_y, float* out_y2,
@@ -102,6 +119,6 @@ int launch_mc_moments(const float* y, int64_t y_sample_stride, const float* in_y
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, const float* step,
                 float b1, float b2, float eps, float grad_scale, cudaStream_t stream);
 int launch_kl(const float* mu, const float* rho, float lambda_, int64_t D, int mode, float* out, float* dmu, float* drho,
-              float grad_scale, int accumulate, cudaStream_t stream);
+              float grad_scale, int accumulate, cudaStream_t stream, int64_t groups = 1, int64_t pstride = 0);
 
 }  // namespace whvi

@@ -2,6 +2,7 @@
 // transpositions between the views of layout.cuh.  sm_100a only.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <type_traits>
 #include "layout.cuh"
 
@@ -69,6 +70,33 @@ __device__ __forceinline__ void stg_stream(float* p, const float4& v)
                  "f"(v.w)
                  : "memory");
 }
+
+// ---- activation I/O types: fp32, or bf16 in HBM with fp32 arithmetic in registers ----------------------
+// Io<T>::ld4 / st4 move four consecutive elements (16 bytes of fp32, 8 bytes of bf16) with the streaming cache hints.
+template <class T>
+struct Io;
+template <>
+struct Io<float> {
+    static __device__ __forceinline__ float4 ld4(const float* p) { return ldg_stream(p); }
+    static __device__ __forceinline__ void st4(float* p, const float4& v) { stg_stream(p, v); }
+};
+template <>
+struct Io<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p)
+    {
+        uint32_t a, b;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+        // bf16 -> fp32 is exact: the 16 bits are the top half of the fp32 pattern
+        return make_float4(__uint_as_float(a << 16), __uint_as_float(a & 0xFFFF0000u), __uint_as_float(b << 16), __uint_as_float(b & 0xFFFF0000u));
+    }
+    static __device__ __forceinline__ void st4(__nv_bfloat16* p, const float4& v)
+    {
+        uint32_t a, b;   // round to nearest even, two at a time (the first source operand lands in the upper half)
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a) : "f"(v.y), "f"(v.x));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b) : "f"(v.w), "f"(v.z));
+        asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+    }
+};
 
 // Barrier among the T threads of one tile group.
 template <int T, int GROUPS>

@@ -12,9 +12,9 @@
 
 namespace whvi {
 
-template <int N, int C, int K, int GROUPS>
+template <int N, int C, int K, int GROUPS, class IO>
 __global__ void __launch_bounds__((1 << (N - C)) * GROUPS)
-fwht_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total)
+fwht_kernel(const IO* __restrict__ in, IO* __restrict__ out, int64_t total)
 {
     constexpr int T = 1 << (N - C);
     constexpr int E = 1 << C;
@@ -38,7 +38,7 @@ fwht_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total
         constexpr uint32_t roff = tile_reg_offset<N, C, V_FIRST>(m);
         const int64_t g = base + toff + roff;
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g < total) q = ldg_stream(in + g);
+        if (g < total) q = Io<IO>::ld4(in + g);
         v[4 * m + 0] = q.x;
         v[4 * m + 1] = q.y;
         v[4 * m + 2] = q.z;
@@ -51,7 +51,7 @@ fwht_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total
             constexpr int m = decltype(m_)::value;
             constexpr uint32_t roff = tile_reg_offset<N, C, V_FIRST>(m);
             const int64_t g = base + toff + roff;
-            if (g < total) stg_stream(out + g, make_float4(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]));
+            if (g < total) Io<IO>::st4(out + g, make_float4(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]));
         });
     } else {
         transpose_write<N, C, V_FIRST, V_MID>(v, buf, transpose_writer_base<N, C, V_FIRST, V_MID>(tid));
@@ -69,21 +69,23 @@ fwht_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total
             constexpr int m = decltype(m_)::value;
             constexpr uint32_t roff = tile_reg_offset<N, C, V_LAST>(m);
             const int64_t g = base + soff + roff;
-            if (g < total) stg_stream(out + g, make_float4(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]));
+            if (g < total) Io<IO>::st4(out + g, make_float4(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]));
         });
     }
 }
 
 // D = 1 (identity) and D = 2: too narrow for a float4; one thread per row.
-__global__ void fwht_tiny_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int D)
+template <class IO>
+__global__ void fwht_tiny_kernel(const IO* __restrict__ in, IO* __restrict__ out, int64_t rows, int D)
 {
     const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     if (D == 1) {
         out[r] = in[r];
     } else {
-        const float2 q = reinterpret_cast<const float2*>(in)[r];
-        reinterpret_cast<float2*>(out)[r] = make_float2(q.x + q.y, q.x - q.y);
+        const float a = static_cast<float>(in[2 * r]), b = static_cast<float>(in[2 * r + 1]);
+        out[2 * r] = static_cast<IO>(a + b);
+        out[2 * r + 1] = static_cast<IO>(a - b);
     }
 }
 
@@ -138,13 +140,13 @@ static int launch_strided(float* data, int64_t total, int log2_stride, int r, cu
     return check_launch("fwht_strided_kernel");
 }
 
-template <int N, int C, int K, int GROUPS>
-static int launch_cfg(const float* in, float* out, int64_t total, cudaStream_t stream)
+template <int N, int C, int K, int GROUPS, class IO>
+static int launch_cfg(const IO* in, IO* out, int64_t total, cudaStream_t stream)
 {
     static unsigned char smem_ok[64] = {};
     constexpr int threads = (1 << (N - C)) * GROUPS;
     constexpr size_t smem = (K <= 2) ? 0 : sizeof(float) * size_t(scratch_words(N, C)) * GROUPS;
-    auto kernel = fwht_kernel<N, C, K, GROUPS>;
+    auto kernel = fwht_kernel<N, C, K, GROUPS, IO>;
     if (int rc = ensure_smem(kernel, smem, smem_ok)) return rc;
     const int64_t tiles = (total + (int64_t(1) << N) - 1) >> N;
     const int64_t ctas = (tiles + GROUPS - 1) / GROUPS;
@@ -153,14 +155,16 @@ static int launch_cfg(const float* in, float* out, int64_t total, cudaStream_t s
     return check_launch("fwht_kernel");
 }
 
-int launch_fwht(const float* in, float* out, int64_t rows, int64_t D, cudaStream_t stream)
+// single-pass range (D <= 2^15); returns -1 when D is beyond it
+template <class IO>
+static int launch_fwht_single(const IO* in, IO* out, int64_t rows, int64_t D, cudaStream_t stream)
 {
     const int K = ilog2(D);
     const int64_t total = rows * D;
     if (K <= 1) {
         const int threads = 256;
         const int64_t blocks = (rows + threads - 1) / threads;
-        fwht_tiny_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(in, out, rows, static_cast<int>(D));
+        fwht_tiny_kernel<IO><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(in, out, rows, static_cast<int>(D));
         return check_launch("fwht_tiny_kernel");
     }
     switch (K) {
@@ -182,6 +186,25 @@ int launch_fwht(const float* in, float* out, int64_t rows, int64_t D, cudaStream
     case 14: return launch_cfg<14, 6, 14, 1>(in, out, total, stream);
     case 15: return launch_cfg<15, 6, 15, 1>(in, out, total, stream);
     default: break;
+    }
+    return -1;
+}
+
+// bf16 in HBM, fp32 butterflies in registers, one rounding (to nearest even) at the store
+int launch_fwht_bf16(const void* in, void* out, int64_t rows, int64_t D, cudaStream_t stream)
+{
+    const int rc = launch_fwht_single(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), rows, D, stream);
+    if (rc == -1) return fail(WHVI_E_SHAPE, "fwht_bf16: D = %lld exceeds the single-pass limit 2^%d", (long long)D, kMaxLog2D);
+    return rc;
+}
+
+int launch_fwht(const float* in, float* out, int64_t rows, int64_t D, cudaStream_t stream)
+{
+    const int K = ilog2(D);
+    const int64_t total = rows * D;
+    {
+        const int rc = launch_fwht_single(in, out, rows, D, stream);
+        if (rc != -1) return rc;
     }
     if (K > kMaxLog2Dmulti) return fail(WHVI_E_SHAPE, "fwht: D = %lld exceeds the limit 2^%d", (long long)D, kMaxLog2Dmulti);
     // D > 2^15: low 15 bits in one pass (every 2^15-float segment is a "row"), then the high bits

@@ -48,6 +48,8 @@ struct BwdArgs {
     const float* dy_scale; // optional device scalar: the upstream gradient is dy_scale[0] * dy (deferred
                            // scaling of a producer that computed its dx for a unit loss coefficient)
     int stagger = 0;       // layer_bwd_tm_kernel: clock cycles by which the CTA's second tile pair starts late
+    int spg = 0x7fffffff;  // grouped launch (LayerFwdCall): samples per parameter group
+    int pstride = 0;       // floats between consecutive groups' s1 / s2 vectors
 };
 
 // Stream-role specialised, TMA-staged backward.  Every tile is worked on by a PAIR of thread
@@ -109,7 +111,10 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
     // sample-minor CTA order (see layer_fwd.cu): shared x / target tiles are reused out of L2
     const int s = blockIdx.x % p.n_samples;
     const int cta_in_sample = blockIdx.x / p.n_samples;
-    const float* __restrict__ xbase = p.x + int64_t(s) * p.x_sample_stride;
+    const int grp = s / p.spg;   // parameter group (Stacked block); the group's virtual samples read the inputs of samples 0 .. spg-1
+    const float* __restrict__ xbase = p.x + int64_t(s - grp * p.spg) * p.x_sample_stride;
+    const float* __restrict__ s1p = p.s1 + int64_t(grp) * p.pstride;
+    const float* __restrict__ s2p = p.s2 + int64_t(grp) * p.pstride;
     const float* __restrict__ dybase = p.dy + int64_t(s) * p.sample_elems;
 
     if (threadIdx.x == 0) {
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
         if constexpr (PREG) {
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
-                const float4 w = ldg4(p.s2 + coord);
+                const float4 w = ldg4(s2p + coord);
                 s2r[4 * m] = w.x, s2r[4 * m + 1] = w.y, s2r[4 * m + 2] = w.z, s2r[4 * m + 3] = w.w;
             });
             load_g_regs(gr);
@@ -345,7 +350,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
                 const float4 q = raw4(stage_x, off);
-                const float4 w = PREG ? make_float4(s2r[4 * m], s2r[4 * m + 1], s2r[4 * m + 2], s2r[4 * m + 3]) : ldg4(p.s2 + coord);
+                const float4 w = PREG ? make_float4(s2r[4 * m], s2r[4 * m + 1], s2r[4 * m + 2], s2r[4 * m + 3]) : ldg4(s2p + coord);
                 mul4(a + 4 * m, q, w);
             });
             to_mid(a);  // a = t2 (middle layout)
@@ -389,10 +394,10 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
         if constexpr (PREG) {
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
-                const float4 w = ldg4(p.s1 + coord);
+                const float4 w = ldg4(s1p + coord);
                 s1r[4 * m] = w.x, s1r[4 * m + 1] = w.y, s1r[4 * m + 2] = w.z, s1r[4 * m + 3] = w.w;
                 if constexpr (PREG == 2) {
-                    const float4 u = ldg4(p.s2 + coord);
+                    const float4 u = ldg4(s2p + coord);
                     s2r[4 * m] = u.x, s2r[4 * m + 1] = u.y, s2r[4 * m + 2] = u.z, s2r[4 * m + 3] = u.w;
                 }
             });
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
                 const float4 q = to_dy(raw4(stage_dy, off), tgt, off, left);
-                const float4 w = PREG ? make_float4(s1r[4 * m], s1r[4 * m + 1], s1r[4 * m + 2], s1r[4 * m + 3]) : ldg4(p.s1 + coord);
+                const float4 w = PREG ? make_float4(s1r[4 * m], s1r[4 * m + 1], s1r[4 * m + 2], s1r[4 * m + 3]) : ldg4(s1p + coord);
                 mul4(b + 4 * m, q, w);
             });
             to_mid(b);  // b = dt3 (middle layout)
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__((2 << (N - C)) * PAIRS, MINB) layer_bwd_tma_ke
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
                 const float4 q = raw4(stage_x, off);
-                const float4 w = PREG == 2 ? make_float4(s2r[4 * m], s2r[4 * m + 1], s2r[4 * m + 2], s2r[4 * m + 3]) : ldg4(p.s2 + coord);
+                const float4 w = PREG == 2 ? make_float4(s2r[4 * m], s2r[4 * m + 1], s2r[4 * m + 2], s2r[4 * m + 3]) : ldg4(s2p + coord);
                 fma4(acc_2 + 4 * m, q, b + 4 * m);
                 const float4 o = make_float4(q.x > relu_thr ? b[4 * m] * w.x : 0.f, q.y > relu_thr ? b[4 * m + 1] * w.y : 0.f,
                                              q.z > relu_thr ? b[4 * m + 2] * w.z : 0.f, q.w > relu_thr ? b[4 * m + 3] * w.w : 0.f);
@@ -504,7 +509,10 @@ __global__ void __launch_bounds__(256, 1) layer_bwd_tm_kernel(const BwdArgs p)
     const uint32_t cmask = (1u << k) - 1u;
     const int s = blockIdx.x % p.n_samples;   // sample-minor CTA order
     const int cta_in_sample = blockIdx.x / p.n_samples;
-    const float* __restrict__ xbase = p.x + int64_t(s) * p.x_sample_stride;
+    const int grp = s / p.spg;   // parameter group (Stacked block); the group's virtual samples read the inputs of samples 0 .. spg-1
+    const float* __restrict__ xbase = p.x + int64_t(s - grp * p.spg) * p.x_sample_stride;
+    const float* __restrict__ s1p = p.s1 + int64_t(grp) * p.pstride;
+    const float* __restrict__ s2p = p.s2 + int64_t(grp) * p.pstride;
     const float* __restrict__ dybase = p.dy + int64_t(s) * p.sample_elems;
 
     if (threadIdx.x == 0) {
@@ -679,7 +687,7 @@ __global__ void __launch_bounds__(256, 1) layer_bwd_tm_kernel(const BwdArgs p)
             float sr[E];
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
-                const float4 w = ldg4(p.s2 + coord);
+                const float4 w = ldg4(s2p + coord);
                 sr[4 * m] = w.x, sr[4 * m + 1] = w.y, sr[4 * m + 2] = w.z, sr[4 * m + 3] = w.w;
             });
             tm_st32(sr, tm + COL_S2), tm_st32(sr + 32, tm + COL_S2 + 32);
@@ -700,7 +708,7 @@ __global__ void __launch_bounds__(256, 1) layer_bwd_tm_kernel(const BwdArgs p)
     {
         // the upstream gradient is dy_scale * dy: folded into Y's s1 once (s1 * dy_scale) and into X's sums at the end
         // (ds1, dbias are linear in dy), not applied to every element of every tile
-        const float* __restrict__ pv = role ? p.s1 : p.s2;
+        const float* __restrict__ pv = role ? s1p : s2p;
         const float psc = (!RESID && role) ? dysc : 1.f;
         float w[E];
         for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t, uint32_t coord) {
@@ -944,7 +952,7 @@ layer_bwd_reduce_slabs_kernel(float* __restrict__ ws, float* __restrict__ dg_dir
 __global__ void __launch_bounds__(256)
 layer_bwd_reduce_fold_kernel(const float* __restrict__ ws, float* __restrict__ dg, float* __restrict__ ds1,
                              float* __restrict__ ds2, float* __restrict__ dbias, int S, int slabs_per_sample, int64_t tile, int D,
-                             int dg_blocks, int cta_per_output)
+                             int dg_blocks, int cta_per_output, int groups)
 {
     __shared__ float red[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -966,10 +974,12 @@ layer_bwd_reduce_fold_kernel(const float* __restrict__ ws, float* __restrict__ d
     }
     // ds1, ds2, dbias: S * reps terms per coordinate; a whole CTA per output when that is many
     const int64_t o = cta_per_output ? int64_t(blockIdx.x) - dg_blocks : (int64_t(blockIdx.x) - dg_blocks) * 8 + warp;
-    if (o >= int64_t(nq) * D) return;
-    const int q = 1 + static_cast<int>(o / D), i = static_cast<int>(o % D);
-    const float* base = ws + int64_t(q) * tile + i;
-    const int terms = S * reps;
+    const int64_t GD = int64_t(groups) * D;   // grouped launch: one (D) output vector per parameter group, over that group's samples
+    if (o >= int64_t(nq) * GD) return;
+    const int q = 1 + static_cast<int>(o / GD), gi = static_cast<int>(o % GD), grp = gi / D, i = gi - grp * D;
+    const int spg = S / groups;
+    const float* base = ws + int64_t(q) * tile + i + int64_t(grp) * spg * sample_stride;
+    const int terms = spg * reps;
     const int first = cta_per_output ? threadIdx.x : lane, step = cta_per_output ? 256 : 32;
     float acc = 0.f;
 #pragma unroll 4
@@ -986,11 +996,11 @@ layer_bwd_reduce_fold_kernel(const float* __restrict__ ws, float* __restrict__ d
     } else if (lane != 0) {
         return;
     }
-    (q == 1 ? ds1 : q == 2 ? ds2 : dbias)[i] = acc;
+    (q == 1 ? ds1 : q == 2 ? ds2 : dbias)[gi] = acc;
 }
 
 int launch_bwd_reduce(float* ws, float* dg, float* ds1, float* ds2, float* dbias, int64_t S, int slabs_per_sample,
-                      int64_t tile, int64_t D, cudaStream_t stream)
+                      int64_t tile, int64_t D, cudaStream_t stream, int64_t groups)
 {
     const int64_t tile4 = tile / 4;
     const bool direct = D == tile;  // one row per tile: pass A's dg sums are final
@@ -1000,12 +1010,12 @@ int launch_bwd_reduce(float* ws, float* dg, float* ds1, float* ds2, float* dbias
         if (int rc = check_launch("layer_bwd_reduce_slabs_kernel")) return rc;
     }
     const int64_t dg_blocks = direct ? 0 : (S * D + 7) / 8;
-    const int64_t ds_outputs = (dbias ? 3 : 2) * D;
-    const int cta_per_output = S * (tile / D) >= 1024;
+    const int64_t ds_outputs = (dbias ? 3 : 2) * D * groups;
+    const int cta_per_output = (S / groups) * (tile / D) >= 1024;
     const int64_t ds_blocks = cta_per_output ? ds_outputs : (ds_outputs + 7) / 8;
     layer_bwd_reduce_fold_kernel<<<static_cast<unsigned>(dg_blocks + ds_blocks), 256, 0, stream>>>(
         ws, dg, ds1, ds2, dbias, static_cast<int>(S), slabs_per_sample, tile, static_cast<int>(D), static_cast<int>(dg_blocks),
-        cta_per_output);
+        cta_per_output, static_cast<int>(groups));
     return check_launch("layer_bwd_reduce_fold_kernel");
 }
 
@@ -1035,6 +1045,8 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     if (ctas > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "layer_bwd: grid too large");
     BwdArgs a{c.x, c.xs, c.dy, c.g, c.s1, c.s2, c.dx, c.ws, c.B * D, static_cast<int>(c.S), plan.ctas_per_sample, plan.iters_per_group, k,
               c.relu_in, c.target, c.coef, c.dy_scale};
+    a.spg = static_cast<int>(c.S / c.groups);
+    a.pstride = static_cast<int>(c.pstride);
     auto go = [&](auto kernel, int slot) -> int {
         if (int rc = ensure_smem(kernel, smem, smem_ok[slot])) return rc;
         kernel<<<static_cast<unsigned>(ctas), threads, smem, stream>>>(a);
@@ -1047,7 +1059,7 @@ static int launch_bwd_tma_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     else if (rs) rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, ROUNDS, false, true>, 2);
     else rc = go(layer_bwd_tma_kernel<N, C, KT, PAIRS, MINB, NS, SINGLE, ALIAS, PREG, ROUNDS, false, false>, 3);
     if (rc) return rc;
-    return launch_bwd_reduce(c.ws, c.dg, c.ds1, c.ds2, c.dbias, c.S, plan.ctas_per_sample * PAIRS, int64_t(tile), D, stream);
+    return launch_bwd_reduce(c.ws, c.dg, c.ds1, c.ds2, c.dbias, c.S, plan.ctas_per_sample * PAIRS, int64_t(tile), D, stream, c.groups);
 }
 
 template <int N, int C, int KT, int ROUNDS>
@@ -1073,6 +1085,8 @@ static int launch_bwd_tm_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     if (ctas > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "layer_bwd: grid too large");
     BwdArgs a{c.x, c.xs, c.dy, c.g, c.s1, c.s2, c.dx, c.ws, c.B * D, static_cast<int>(c.S), plan.ctas_per_sample, plan.iters_per_group, k,
               c.relu_in, c.target, c.coef, c.dy_scale};
+    a.spg = static_cast<int>(c.S / c.groups);
+    a.pstride = static_cast<int>(c.pstride);
     static const int stagger = [] { const char* e = std::getenv("WHVI_BWD_STAGGER"); return e ? std::atoi(e) : 0; }();
     a.stagger = stagger;
     auto go = [&](auto kernel, int slot) -> int {
@@ -1087,7 +1101,7 @@ static int launch_bwd_tm_cfg(const LayerBwdCall& c, int k, cudaStream_t stream)
     else if (rs) rc = go(layer_bwd_tm_kernel<N, C, KT, ROUNDS, false, true>, 2);
     else rc = go(layer_bwd_tm_kernel<N, C, KT, ROUNDS, false, false>, 3);
     if (rc) return rc;
-    return launch_bwd_reduce(c.ws, c.dg, c.ds1, c.ds2, c.dbias, c.S, plan.ctas_per_sample * PAIRS, int64_t(tile), D, stream);
+    return launch_bwd_reduce(c.ws, c.dg, c.ds1, c.ds2, c.dbias, c.S, plan.ctas_per_sample * PAIRS, int64_t(tile), D, stream, c.groups);
 }
 
 int launch_layer_bwd(const LayerBwdCall& c, int64_t D, cudaStream_t stream)

@@ -37,6 +37,8 @@ struct FwdArgs {
     // computed once per input row with whvi_fwht_f32), so one transform per (sample, row) is left
     const float* target;    // HAS_TARGET: (B, D); sum (y - target)^2 goes to sq_partials[cta]
     float* sq_partials;
+    int spg;                // grouped launch: samples per parameter group (n_samples when there is one group)
+    int pstride, bstride;   // floats between consecutive groups' s1 / s2 vectors, bias vectors
 };
 
 // ------------------------------------------------------------------------------ forward
@@ -46,7 +48,9 @@ struct FwdArgs {
 // transposition but half the shared memory).
 // Flags that guard LOADS are template parameters: a run-time branch around a load inside the
 // unrolled float4 loops stops the compiler from batching the loads (measured: 2x slower).
-template <int N, int C, int KT, int GROUPS, int ROUNDS, int BUFS, int MINB, bool HAS_BIAS, bool HAS_TARGET, bool FROM_T2>
+// IO: the activations' type in HBM (float, or __nv_bfloat16 with fp32 arithmetic in registers: SURVEY 8f N4); a.x / a.y are
+// then IO pointers behind the float* of FwdArgs.  Parameters, g and the target are always fp32.
+template <int N, int C, int KT, int GROUPS, int ROUNDS, int BUFS, int MINB, bool HAS_BIAS, bool HAS_TARGET, bool FROM_T2, class IO = float>
 __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kernel(const FwdArgs a)
 {
     constexpr int T = 1 << (N - C);
@@ -67,6 +71,10 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
     const int s = blockIdx.x % a.n_samples;
     const int cta_in_sample = blockIdx.x / a.n_samples;
     const float* __restrict__ gs = a.g + (int64_t(s) << k);
+    const int grp = s / a.spg, sx = s - grp * a.spg;   // parameter group (Stacked block) and the sample whose input it reads
+    const float* __restrict__ s1p = a.s1 + int64_t(grp) * a.pstride;
+    const float* __restrict__ s2p = a.s2 + int64_t(grp) * a.pstride;
+    const float* __restrict__ biasp = HAS_BIAS ? a.bias + int64_t(grp) * a.bstride : nullptr;
     constexpr size_t SW = scratch_words(N, C);  // one transposition buffer / g table (== TILE unless WHVI_PADDED)
     float* gt = smem;  // ROUNDS == 2 only
     float* bufA = smem + (ROUNDS == 2 ? SW : 0) + size_t(group) * BUFS * SW;
@@ -95,13 +103,13 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
         const int64_t e0 = tile * TILE;  // element offset inside the sample
         if (e0 >= a.sample_elems) break;  // uniform per group
         const int64_t left = a.sample_elems - e0;
-        const float* __restrict__ xs = a.x + int64_t(s) * a.x_sample_stride + e0;
-        float* __restrict__ ys = a.y + int64_t(s) * a.sample_elems + e0;
+        const IO* __restrict__ xs = reinterpret_cast<const IO*>(a.x) + int64_t(sx) * a.x_sample_stride + e0;
+        IO* __restrict__ ys = reinterpret_cast<IO*>(a.y) + int64_t(s) * a.sample_elems + e0;
         if (tid == 0 && it + 1 < a.iters_per_group) {  // pull the group's next tile towards L2
             const int64_t e1 = e0 + GROUPS * TILE;
             if (e1 < a.sample_elems) {
                 const int64_t left1 = a.sample_elems - e1;
-                l2_prefetch_bulk(xs + GROUPS * TILE, static_cast<uint32_t>((left1 < TILE ? left1 : TILE) * sizeof(float)));
+                l2_prefetch_bulk(xs + GROUPS * TILE, static_cast<uint32_t>((left1 < TILE ? left1 : TILE) * sizeof(IO)));
             }
         }
 
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
             for_each_vec<N, C, V_LAST>(off_l, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
                 float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (off < left) q = ldg_stream(xs + off);
+                if (off < left) q = Io<IO>::ld4(xs + off);
                 const float4 w = ldg4(gs + coord);
                 mul4(v + 4 * m, q, w);
             });
@@ -120,11 +128,11 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
             for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
                 constexpr int m = decltype(m_)::value;
                 float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (off < left) q = ldg_stream(xs + off);
+                if (off < left) q = Io<IO>::ld4(xs + off);
                 if constexpr (FROM_T2) {
                     v[4 * m] = q.x, v[4 * m + 1] = q.y, v[4 * m + 2] = q.z, v[4 * m + 3] = q.w;
                 } else {
-                    const float4 w = ldg4(a.s2 + coord);
+                    const float4 w = ldg4(s2p + coord);
                     mul4(v + 4 * m, q, w);
                 }
             });
@@ -158,10 +166,10 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
         }
         for_each_vec<N, C, V_FIRST>(off_f, cmask, [&](auto m_, uint32_t off, uint32_t coord) {
             constexpr int m = decltype(m_)::value;
-            const float4 w = ldg4(a.s1 + coord);
+            const float4 w = ldg4(s1p + coord);
             float4 o = make_float4(v[4 * m] * w.x, v[4 * m + 1] * w.y, v[4 * m + 2] * w.z, v[4 * m + 3] * w.w);
             if constexpr (HAS_BIAS) {
-                const float4 b = ldg4(a.bias + coord);
+                const float4 b = ldg4(biasp + coord);
                 o.x += b.x;
                 o.y += b.y;
                 o.z += b.z;
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
                     const float d0 = o.x - tg.x, d1 = o.y - tg.y, d2 = o.z - tg.z, d3 = o.w - tg.w;
                     sq = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, sq))));
                 }
-                stg_stream(ys + off, o);
+                Io<IO>::st4(ys + off, o);
             }
         });
     }
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__((1 << (N - C)) * GROUPS, MINB) layer_fwd_kerne
 template <int N, int C, int KT, int GROUPS, int ROUNDS, int BUFS, int MINB>
 static int launch_fwd_cfg(const LayerFwdCall& c, int k, cudaStream_t stream)
 {
-    static unsigned char smem_ok[6][64] = {};
+    static unsigned char smem_ok[10][64] = {};
     constexpr int threads = (1 << (N - C)) * GROUPS;
     constexpr size_t tile = size_t(1) << N;
     constexpr size_t sw = scratch_words(N, C);
@@ -218,13 +226,22 @@ static int launch_fwd_cfg(const LayerFwdCall& c, int k, cudaStream_t stream)
     }
     if (ctas > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "layer_fwd: grid too large");
     FwdArgs a{c.x, c.xs, c.g, c.s1, c.s2, c.bias, c.y, c.B * D, static_cast<int>(c.S), plan.ctas_per_sample, plan.iters_per_group, k,
-              c.relu_out, c.target, c.sq_partials};
+              c.relu_out, c.target, c.sq_partials, static_cast<int>(c.S / c.groups), static_cast<int>(c.pstride), static_cast<int>(c.bstride)};
     auto go = [&](auto kernel, int slot) -> int {
         if (int rc = ensure_smem(kernel, smem, smem_ok[slot])) return rc;
         kernel<<<static_cast<unsigned>(ctas), threads, smem, stream>>>(a);
         return check_launch("layer_fwd_kernel");
     };
     const bool hb = c.bias != nullptr, ht = c.target != nullptr;
+    if (c.bf16) {   // bf16 activations in HBM (inference paths: no target)
+        if (ht) return fail(WHVI_E_MODE, "layer_fwd: bf16 activations cannot be combined with a target");
+        if (c.from_t2) {
+            if (hb) return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, true, false, true, __nv_bfloat16>, 6);
+            return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, false, false, true, __nv_bfloat16>, 7);
+        }
+        if (hb) return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, true, false, false, __nv_bfloat16>, 8);
+        return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, false, false, false, __nv_bfloat16>, 9);
+    }
     if (c.from_t2) {
         if (ht) return fail(WHVI_E_MODE, "layer_fwd: FROM_T2 cannot be combined with a target");
         if (hb) return go(layer_fwd_kernel<N, C, KT, GROUPS, ROUNDS, BUFS, MINB, true, false, true>, 4);

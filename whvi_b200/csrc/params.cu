@@ -15,24 +15,38 @@ namespace whvi {
 __device__ __forceinline__ float softplus_f(float r) { return r > 20.f ? r : log1pf(expf(r)); }
 __device__ __forceinline__ float sigmoid_f(float r) { return 1.f / (1.f + expf(-r)); }
 
+// grouped form (a Stacked layer's blocks, src/weights.py:179-180): samples s / spg share the parameter vectors at + (s / spg) * pstride
 __global__ void reparam_diag_kernel(const float* __restrict__ mu, const float* __restrict__ rho,
-                                    const float* __restrict__ eps, float* __restrict__ g, int64_t S, int64_t D)
+                                    const float* __restrict__ eps, float* __restrict__ g, int64_t S, int64_t D, int64_t spg, int64_t pstride)
 {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= D) return;
-    const float m = mu[i], sg = softplus_f(rho[i]);
-    for (int64_t s = blockIdx.y; s < S; s += gridDim.y) g[s * D + i] = fmaf(sg, eps[s * D + i], m);
+    if (spg >= S) {
+        const float m = mu[i], sg = softplus_f(rho[i]);
+        for (int64_t s = blockIdx.y; s < S; s += gridDim.y) g[s * D + i] = fmaf(sg, eps[s * D + i], m);
+    } else {
+        for (int64_t s = blockIdx.y; s < S; s += gridDim.y) {
+            const int64_t pi = (s / spg) * pstride + i;
+            g[s * D + i] = fmaf(softplus_f(rho[pi]), eps[s * D + i], mu[pi]);
+        }
+    }
 }
 
 // dmu[i] (+)= sum_s dg[s,i];  drho[i] (+)= (sum_s dg[s,i] eps[s,i]) * sigmoid(rho[i])
 // 32 columns x 8 sample slices per CTA; slice sums are combined in a fixed order (bit-reproducible).
 __global__ void __launch_bounds__(256)
 reparam_diag_bwd_kernel(const float* __restrict__ rho, const float* __restrict__ eps, const float* __restrict__ dg,
-                        float* __restrict__ dmu, float* __restrict__ drho, int64_t S, int64_t D, int accumulate)
+                        float* __restrict__ dmu, float* __restrict__ drho, int64_t S, int64_t D, int accumulate, int64_t pstride)
 {
     __shared__ float red[2][8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t i = int64_t(blockIdx.x) * 32 + tx;
+    // grouped form: blockIdx.y = parameter group; S samples per group, outputs (groups, D)
+    rho += int64_t(blockIdx.y) * pstride;
+    eps += int64_t(blockIdx.y) * S * D;
+    dg += int64_t(blockIdx.y) * S * D;
+    dmu += int64_t(blockIdx.y) * D;
+    drho += int64_t(blockIdx.y) * D;
     float a = 0.f, b = 0.f;
     if (i < D) {
 #pragma unroll 4
@@ -66,13 +80,15 @@ reparam_diag_bwd_kernel(const float* __restrict__ rho, const float* __restrict__
 // accumulated into dmu/drho when accumulate != 0).
 __global__ void __launch_bounds__(1024)
 kl_kernel(const float* __restrict__ mu, const float* __restrict__ rho, float lambda_, int64_t D, int mode,
-          float* __restrict__ out, float* __restrict__ dmu, float* __restrict__ drho, float grad_scale, int accumulate)
+          float* __restrict__ out, float* __restrict__ dmu, float* __restrict__ drho, float grad_scale, int accumulate,
+          int64_t Dg, int64_t pstride)   // grouped form: D = groups * Dg coordinates, group k's vectors at + k * pstride; outputs contiguous
 {
     __shared__ double red[3][32];
     double s_log = 0.0, s_ratio = 0.0, s_mu = 0.0;
     const float inv_l = 1.f / lambda_;
     for (int64_t i = threadIdx.x; i < D; i += blockDim.x) {
-        const float m = mu[i], r = rho[i];
+        const int64_t pi = Dg >= D ? i : (i / Dg) * pstride + i % Dg;
+        const float m = mu[pi], r = rho[pi];
         const float sg = softplus_f(r);
         const float v = mode ? sg * sg : sg;
         s_log += static_cast<double>(logf(v));
@@ -122,28 +138,32 @@ kl_kernel(const float* __restrict__ mu, const float* __restrict__ rho, float lam
 }
 
 int launch_reparam_diag(const float* mu, const float* rho, const float* eps, float* g, int64_t S, int64_t D,
-                        cudaStream_t stream)
+                        cudaStream_t stream, int64_t groups, int64_t pstride)
 {
     const int threads = 256;
     const unsigned gx = static_cast<unsigned>((D + threads - 1) / threads);
     unsigned gy = static_cast<unsigned>(S < 1 ? 1 : (S > 4096 ? 4096 : S));
-    reparam_diag_kernel<<<dim3(gx, gy), threads, 0, stream>>>(mu, rho, eps, g, S, D);
+    reparam_diag_kernel<<<dim3(gx, gy), threads, 0, stream>>>(mu, rho, eps, g, S, D, S / groups, pstride);
     return check_launch("reparam_diag_kernel");
 }
 
+// S: samples PER GROUP
 int launch_reparam_diag_bwd(const float* rho, const float* eps, const float* dg, float* dmu, float* drho, int64_t S,
-                            int64_t D, int accumulate, cudaStream_t stream)
+                            int64_t D, int accumulate, cudaStream_t stream, int64_t groups, int64_t pstride)
 {
-    reparam_diag_bwd_kernel<<<static_cast<unsigned>((D + 31) / 32), 256, 0, stream>>>(rho, eps, dg, dmu, drho, S, D, accumulate);
+    reparam_diag_bwd_kernel<<<dim3(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>(groups)), 256, 0, stream>>>(
+        rho, eps, dg, dmu, drho, S, D, accumulate, pstride);
     return check_launch("reparam_diag_bwd_kernel");
 }
 
+// D: coordinates PER GROUP
 int launch_kl(const float* mu, const float* rho, float lambda_, int64_t D, int mode, float* out, float* dmu, float* drho,
-              float grad_scale, int accumulate, cudaStream_t stream)
+              float grad_scale, int accumulate, cudaStream_t stream, int64_t groups, int64_t pstride)
 {
+    const int64_t total = D * groups;
     int threads = 32;
-    while (threads < D && threads < 1024) threads <<= 1;
-    kl_kernel<<<1, threads, 0, stream>>>(mu, rho, lambda_, D, mode, out, dmu, drho, grad_scale, accumulate);
+    while (threads < total && threads < 1024) threads <<= 1;
+    kl_kernel<<<1, threads, 0, stream>>>(mu, rho, lambda_, total, mode, out, dmu, drho, grad_scale, accumulate, D, pstride);
     return check_launch("kl_kernel");
 }
 

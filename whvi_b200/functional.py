@@ -24,7 +24,8 @@ _LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_fwht_f64": 1, "whvi_layer_fwd_f3
                       "whvi_layer_bwd_scaled_f32": 3, "whvi_layer_loss_f32": 3, "whvi_reparam_f32": 1,
                       "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1, "whvi_mc_moments_f32": 1,
                       "whvi_mc_moments_strided_f32": 1, "whvi_adam_f32": 1, "whvi_layer_moments_f32": 1,
-                      "whvi_reparam_dense_f32": 2, "whvi_reparam_dense_bwd_f32": 1, "whvi_kl_dense_f32": 2}
+                      "whvi_reparam_dense_f32": 2, "whvi_reparam_dense_bwd_f32": 1, "whvi_kl_dense_f32": 2,
+                      "whvi_fwht_bf16": 1, "whvi_layer_fwd_bf16": 1, "whvi_column_fwd_f32": 3, "whvi_column_bwd_f32": 7, "whvi_pad_rows_f32": 1, "whvi_stacked_fwd_f32": 3, "whvi_stacked_bwd_f32": 6, "whvi_kl_grouped_f32": 1}
 # When set to a dict {"name": [(start_event, stop_event), ...]}, the named calls are bracketed
 # by CUDA events on the launching stream (bench.py's per-kernel roofline timing).
 EVENT_SINK: dict[str, list] | None = None
@@ -130,6 +131,30 @@ def layer_forward_raw(x, g, s1, s2, bias=None, out=None, relu_out=False, target=
     _lib.check(rc, "whvi_layer_fwd_fused_f32")
     if target is not None:
         return out, partials.sum() if S * B > 0 else partials.sum() * 0
+    return out
+
+
+def layer_forward_bf16(x, g, s1, s2, bias=None, out=None, relu_out=False, from_t2=False):
+    """The fused forward with bf16 activations in HBM (``whvi_layer_fwd_bf16``): ``x`` (B, D) or (S, B, D) and
+    the result are ``torch.bfloat16``; g, s1, s2, bias stay fp32 and so does every FLOP; the output is rounded once, at the
+    store.  Inference only (no autograd): 4 B/element of activation traffic instead of 8."""
+    if x.dtype != torch.bfloat16 or x.device.type != "cuda":
+        raise RuntimeError("x must be a CUDA bfloat16 tensor")
+    x = x.contiguous()
+    g, s1, s2 = _f32c(g, "g"), _f32c(s1, "s1"), _f32c(s2, "s2")
+    S, B, D, xs = _layer_dims(x, g, s1, s2)
+    if bias is not None:
+        bias = _f32c(bias, "bias").reshape(-1)
+        if bias.numel() != D:
+            raise RuntimeError("bias must have D elements")
+    if out is None:
+        out = torch.empty((S, B, D), dtype=torch.bfloat16, device=x.device)
+    elif out.dtype != torch.bfloat16 or out.shape != (S, B, D) or not out.is_contiguous():
+        raise RuntimeError("out must be a contiguous bfloat16 (S, B, D) tensor")
+    with torch.cuda.device(x.device), _Timed("whvi_layer_fwd_bf16"):
+        rc = _lib.lib().whvi_layer_fwd_bf16(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias), out.data_ptr(),
+                                            S, B, D, (1 if relu_out else 0) | (2 if from_t2 else 0), _stream(x.device))
+    _lib.check(rc, "whvi_layer_fwd_bf16")
     return out
 
 
@@ -627,6 +652,211 @@ class KLDenseFunction(Function):
 
 def kl_gaussian_dense(mu, L, lambda_):
     return KLDenseFunction.apply(mu, L, lambda_)
+
+
+# ---------------------------------------------------------------------------------------------- Stacked layer, one call per direction
+def uniform_stride(tensors) -> int | None:
+    """Floats between consecutive tensors' first elements when they are evenly spaced in memory (stride >= numel, a multiple
+    of 4), else None.  The blocks' separate nn.Parameters are evenly spaced once packed (FlatParams, or the Stacked module's
+    own packing), and then the kernels read them where they lie."""
+    if len(tensors) == 1:
+        return tensors[0].numel()
+    p0 = tensors[0].data_ptr()
+    step = tensors[1].data_ptr() - p0
+    if step < 4 * tensors[0].numel() or step % 16 != 0:
+        return None
+    for k, t in enumerate(tensors):
+        if t.data_ptr() != p0 + k * step or not t.is_contiguous():
+            return None
+    return step // 4
+
+
+class WHVIStackedFunction(Function):
+    """WHVIStackedMatrix.forward (src/weights.py:182-208) for all G blocks in one C-ABI call per direction
+    (``whvi_stacked_fwd_f32`` / ``whvi_stacked_bwd_f32``): pad, reparameterisation, G x S virtual samples through the fused layer
+    kernel, bias, optional ReLU, concatenation, slice.  ``params`` = G x s1, G x s2, G x g_mu, G x g_rho (the blocks' own
+    parameters, so autograd routes the gradients); ``eps`` (G, S, D)."""
+
+    @staticmethod
+    def forward(ctx, x, eps, bias, n_out, relu_out, relu_in, *params):
+        G = len(params) // 4
+        eps = _f32c(eps, "eps")
+        _, S, D = eps.shape
+        x = _f32c(x, "x")
+        n_in = x.size(-1)
+        lib = _lib.lib()
+        dev = x.device
+        st = _stream(dev)
+        with torch.cuda.device(dev):
+            if n_in < D:  # src/weights.py:197-198
+                xp = torch.empty(x.shape[:-1] + (D,), dtype=torch.float32, device=dev)
+                with _Timed("whvi_pad_rows_f32"):
+                    _lib.check(lib.whvi_pad_rows_f32(x.data_ptr(), xp.data_ptr(), x.numel() // n_in, n_in, D, st), "whvi_pad_rows_f32")
+            else:
+                xp = x
+            if xp.dim() == 2:
+                B, xs = xp.size(0), 0
+            elif xp.dim() == 3 and xp.size(0) == S:
+                B, xs = xp.size(1), xp.size(1) * D
+            else:
+                raise RuntimeError(f"x must be (B, n_in) or (S, B, n_in) with S = {S}; got {tuple(x.shape)}")
+            groups = [params[i * G:(i + 1) * G] for i in range(4)]
+            strides = [uniform_stride(g_) for g_ in groups]
+            if any(v is None for v in strides) or len(set(strides)) != 1:
+                packed = torch.stack([torch.stack([t.detach().reshape(-1) for t in g_]) for g_ in groups])   # (4, G, D) copy
+                s1p, s2p, mup, rhop = packed[0], packed[1], packed[2], packed[3]
+                stride = D
+            else:
+                s1p, s2p, mup, rhop = (g_[0].detach() for g_ in groups)
+                stride = strides[0]
+            if bias is not None:
+                bias = _f32c(bias, "bias").reshape(-1)
+                if bias.numel() != G * D:
+                    raise RuntimeError("stacked bias must have G * D elements")
+            g = torch.empty((G, S, D), dtype=torch.float32, device=dev)
+            yb = torch.empty((G, S, B, D), dtype=torch.float32, device=dev)
+            y = torch.empty((S, B, n_out), dtype=torch.float32, device=dev)
+            with _Timed("whvi_stacked_fwd_f32"):
+                rc = lib.whvi_stacked_fwd_f32(xp.data_ptr(), xs, mup.data_ptr(), rhop.data_ptr(), s1p.data_ptr(), s2p.data_ptr(), stride,
+                                              eps.data_ptr(), _ptr(bias), g.data_ptr(), yb.data_ptr(), y.data_ptr(), S, B, D, G, n_out,
+                                              1 if relu_out else 0, st)
+            _lib.check(rc, "whvi_stacked_fwd_f32")
+        ctx.save_for_backward(xp, eps, g, s1p, s2p, rhop)
+        ctx.meta = (S, B, D, G, xs, n_in, n_out, stride, bool(relu_in), bias is not None, x.dim())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, eps, g, s1p, s2p, rhop = ctx.saved_tensors
+        S, B, D, G, xs, n_in, n_out, stride, relu_in, has_bias, xdim = ctx.meta
+        dy = _f32c(dy, "dy")
+        dev = dy.device
+        lib = _lib.lib()
+        want_dx = ctx.needs_input_grad[0]
+        need = ctypes.c_size_t(0)
+        _lib.check(lib.whvi_stacked_bwd_workspace_bytes(S, B, D, G, 1 if want_dx else 0, ctypes.byref(need)), "whvi_stacked_bwd_workspace_bytes")
+        with torch.cuda.device(dev):
+            ws = _workspace(dev, need.value)
+            out = torch.empty((5 if has_bias else 4, G, D), dtype=torch.float32, device=dev)   # dmu, drho, ds1, ds2, [dbias]
+            dx = torch.empty((S, B, n_in), dtype=torch.float32, device=dev) if want_dx else None
+            with _Timed("whvi_stacked_bwd_f32"):
+                rc = lib.whvi_stacked_bwd_f32(xp.data_ptr(), xs, dy.data_ptr(), g.data_ptr(), rhop.data_ptr(), s1p.data_ptr(), s2p.data_ptr(),
+                                              stride, eps.data_ptr(), _ptr(dx), n_in, out[0].data_ptr(), out[1].data_ptr(),
+                                              out[2].data_ptr(), out[3].data_ptr(), out[4].data_ptr() if has_bias else None,
+                                              ws.data_ptr(), ws.numel(), S, B, D, G, n_out, 1 if relu_in else 0, _stream(dev))
+            _lib.check(rc, "whvi_stacked_bwd_f32")
+        if want_dx and xdim == 2:
+            dx = dx.sum(dim=0)
+        dbias = out[4].reshape(1, G * D) if has_bias and ctx.needs_input_grad[2] else None
+        grads = [out[2, k] for k in range(G)] + [out[3, k] for k in range(G)] + [out[0, k] for k in range(G)] + [out[1, k] for k in range(G)]
+        return (dx, None, dbias, None, None, None, *grads)
+
+
+def whvi_stacked(x, eps, bias, n_out, blocks_s1, blocks_s2, blocks_mu, blocks_rho, relu_out=False, relu_in=False):
+    return WHVIStackedFunction.apply(x, eps, bias, n_out, relu_out, relu_in, *blocks_s1, *blocks_s2, *blocks_mu, *blocks_rho)
+
+
+class WHVIColumnFunction(Function):
+    """WHVIColumnMatrix.forward (src/weights.py:231-251, PAPER semantics) in one C-ABI call per direction
+    (``whvi_column_fwd_f32`` / ``whvi_column_bwd_f32``): reparameterisation, ONE FWHT of g per MC sample, the 1-wide product,
+    the bias.  ``x``: (B, n) / (S, B, n) when ``transposed`` (-> (S, B, 1)), (B, 1) / (S, B, 1) otherwise (-> (S, B, n))."""
+
+    @staticmethod
+    def forward(ctx, x, eps, mu, rho, s1, s2, bias, n, transposed, relu_out, relu_in):
+        x, eps = _f32c(x, "x"), _f32c(eps, "eps")
+        mu, rho, s1, s2 = _f32c(mu, "g_mu"), _f32c(rho, "g_rho"), _f32c(s1, "s1"), _f32c(s2, "s2")
+        S, D = eps.shape
+        width = n if transposed else 1
+        if x.size(-1) != width:
+            raise RuntimeError(f"last dimension of x must be {width}, got {x.size(-1)}")
+        if x.dim() == 2:
+            B, xs = x.size(0), 0
+        elif x.dim() == 3 and x.size(0) == S:
+            B, xs = x.size(1), x.size(1) * width
+        else:
+            raise RuntimeError(f"x must be (B, {width}) or (S, B, {width}) with S = {S}; got {tuple(x.shape)}")
+        if bias is not None:
+            bias = _f32c(bias, "bias").reshape(-1)
+        dev = x.device
+        g = torch.empty((S, D), dtype=torch.float32, device=dev)
+        hg = torch.empty((S, D), dtype=torch.float32, device=dev)    # H g, kept for the backward
+        y = torch.empty((S, B, 1 if transposed else n), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _Timed("whvi_column_fwd_f32"):
+            rc = _lib.lib().whvi_column_fwd_f32(x.data_ptr(), xs, mu.data_ptr(), rho.data_ptr(), s1.data_ptr(), s2.data_ptr(), eps.data_ptr(),
+                                                _ptr(bias), g.data_ptr(), hg.data_ptr(), y.data_ptr(), S, B, D, n, 1 if transposed else 0,
+                                                1 if relu_out else 0, _stream(dev))
+        _lib.check(rc, "whvi_column_fwd_f32")
+        ctx.save_for_backward(x, eps, hg, rho, s1, s2)
+        ctx.meta = (S, B, D, n, xs, bool(transposed), bool(relu_in), bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, eps, hg, rho, s1, s2 = ctx.saved_tensors
+        S, B, D, n, xs, transposed, relu_in, has_bias = ctx.meta
+        dy = _f32c(dy, "dy")
+        dev = dy.device
+        lib = _lib.lib()
+        want_dx = ctx.needs_input_grad[0]
+        need = ctypes.c_size_t(0)
+        _lib.check(lib.whvi_column_bwd_workspace_bytes(S, D, n, ctypes.byref(need)), "whvi_column_bwd_workspace_bytes")
+        with torch.cuda.device(dev):
+            ws = _workspace(dev, need.value)
+            out = torch.empty((4, D), dtype=torch.float32, device=dev)   # dmu, drho, ds1, ds2
+            dbias = torch.empty((1, 1 if transposed else n), dtype=torch.float32, device=dev) if has_bias else None
+            dx = torch.empty((S, B, n if transposed else 1), dtype=torch.float32, device=dev) if want_dx else None
+            with _Timed("whvi_column_bwd_f32"):
+                rc = lib.whvi_column_bwd_f32(x.data_ptr(), xs, dy.data_ptr(), hg.data_ptr(), rho.data_ptr(), s1.data_ptr(), s2.data_ptr(),
+                                             eps.data_ptr(), _ptr(dx), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                             out[3].data_ptr(), _ptr(dbias), ws.data_ptr(), ws.numel(), S, B, D, n, 1 if transposed else 0,
+                                             1 if relu_in else 0, _stream(dev))
+            _lib.check(rc, "whvi_column_bwd_f32")
+        if want_dx and xs == 0:
+            dx = dx.sum(dim=0)
+        return dx, None, out[0], out[1], out[2], out[3], dbias, None, None, None, None
+
+
+def whvi_column(x, eps, mu, rho, s1, s2, bias, n, transposed, relu_out=False, relu_in=False):
+    return WHVIColumnFunction.apply(x, eps, mu, rho, s1, s2, bias, n, transposed, relu_out, relu_in)
+
+
+class KLGroupedFunction(Function):
+    """Sum of the blocks' KL terms (src/weights.py:162-164) with all gradients in one launch."""
+
+    @staticmethod
+    def forward(ctx, lambda_, mode, *params):
+        G = len(params) // 2
+        mus, rhos = params[:G], params[G:]
+        D = mus[0].numel()
+        sm, sr = uniform_stride(mus), uniform_stride(rhos)
+        if sm is None or sm != sr:
+            mup, rhop, stride = torch.stack([t.detach() for t in mus]), torch.stack([t.detach() for t in rhos]), D
+        else:
+            mup, rhop, stride = mus[0].detach(), rhos[0].detach(), sm
+        dev = mup.device
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        need_grad = any(ctx.needs_input_grad[2:])
+        grads = torch.empty((2, G, D), dtype=torch.float32, device=dev) if need_grad else None
+        with torch.cuda.device(dev), _Timed("whvi_kl_grouped_f32"):
+            rc = _lib.lib().whvi_kl_grouped_f32(mup.data_ptr(), rhop.data_ptr(), float(lambda_), D, G, stride, int(mode), out.data_ptr(),
+                                                grads[0].data_ptr() if need_grad else None, grads[1].data_ptr() if need_grad else None,
+                                                1.0, _stream(dev))
+        _lib.check(rc, "whvi_kl_grouped_f32")
+        ctx.G = G
+        if need_grad:
+            ctx.save_for_backward(grads)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, dkl):
+        (grads,) = ctx.saved_tensors
+        gr = grads * dkl
+        G = ctx.G
+        return (None, None, *[gr[0, k] for k in range(G)], *[gr[1, k] for k in range(G)])
+
+
+def kl_gaussian_grouped(mus, rhos, lambda_, mode=0):
+    return KLGroupedFunction.apply(lambda_, mode, *mus, *rhos)
 
 
 class KLFunction(Function):

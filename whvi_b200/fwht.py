@@ -33,7 +33,8 @@ _FN = {}   # dtype -> (C entry point, name): looked up once, not per call
 def _entry(dtype):
     fn = _FN.get(dtype)
     if fn is None:
-        name = "whvi_fwht_f32" if dtype == torch.float32 else "whvi_fwht_f64"   # same dispatch as fwht_cuda_kernel.cu:170
+        # same dispatch as fwht_cuda_kernel.cu:170, plus bf16 activations (fp32 butterflies, one rounding at the store)
+        name = {torch.float32: "whvi_fwht_f32", torch.float64: "whvi_fwht_f64", torch.bfloat16: "whvi_fwht_bf16"}[dtype]
         fn = _FN[dtype] = (getattr(_lib.lib(), name), name)
     return fn
 
@@ -53,8 +54,8 @@ def fwht_(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     n = x.size(-1)
     if n < 1 or (n & (n - 1)) != 0:
         raise RuntimeError("n must be a power of 2")
-    if x.dtype not in (torch.float32, torch.float64):
-        raise RuntimeError(f"whvi_b200 FWHT supports float32 and float64 (got {x.dtype})")
+    if x.dtype not in (torch.float32, torch.float64, torch.bfloat16):
+        raise RuntimeError(f"whvi_b200 FWHT supports float32, float64 and bfloat16 (got {x.dtype})")
     if not x.is_contiguous():
         x = x.contiguous()
     if out is None:

@@ -77,6 +77,22 @@ class WHVINetwork(nn.Module, WHVI):
         return (isinstance(module, WHVILinear) and isinstance(module.weight_submodule, WHVISquarePow2Matrix)
                 and module.weight_submodule.fusable)
 
+    @staticmethod
+    def _fusable_stacked(module):
+        from .weights import WHVIStackedMatrix
+        return isinstance(module, WHVILinear) and isinstance(module.weight_submodule, WHVIStackedMatrix) and module.weight_submodule.grouped
+
+    @staticmethod
+    def _fusable_column(module):
+        from .weights import WHVIColumnMatrix
+        return isinstance(module, WHVILinear) and isinstance(module.weight_submodule, WHVIColumnMatrix) and module.weight_submodule.fused
+
+    @classmethod
+    def _relu_fusable(cls, module):
+        """Layers whose kernels can apply the mask of a ReLU folded into their producer to their dx (consumer side)."""
+        return (cls._fusable_square(module) or cls._fusable_stacked(module)
+                or (cls._fusable_column(module) and module.weight_submodule.transposed))
+
     def _run(self, x: torch.Tensor, n_samples: int, sqerr_target=None):
         """Run the sequence once with the MC samples as a leading axis.  Returns the
         (S, B, out) activations, or -- with ``sqerr_target`` and a fusable last layer --
@@ -95,10 +111,26 @@ class WHVINetwork(nn.Module, WHVI):
             while i < len(modules):
                 module = modules[i]
                 last = i == len(modules) - 1
+                if self.fuse and self._fusable_stacked(module):
+                    # all blocks of the Stacked layer in one grouped launch, the following ReLU folded in when the
+                    # consumer's kernels can apply the mask on the way back
+                    relu_out = (i + 2 < len(modules) and type(modules[i + 1]) is nn.ReLU and self._relu_fusable(modules[i + 2]))
+                    h = module.weight_submodule.forward(h, relu_out=relu_out, relu_in=relu_in)
+                    relu_in, scale_holder = relu_out, None
+                    i += 2 if relu_out else 1
+                    continue
+                if self.fuse and self._fusable_column(module):
+                    w = module.weight_submodule   # (.., n) -> (.., 1) consumes a folded ReLU; (.., 1) -> (.., n) can produce one
+                    relu_out = (not w.transposed and i + 2 < len(modules) and type(modules[i + 1]) is nn.ReLU
+                                and self._relu_fusable(modules[i + 2]))
+                    h = w.forward(h, relu_out=relu_out, relu_in=relu_in)
+                    relu_in, scale_holder = relu_out, None
+                    i += 2 if relu_out else 1
+                    continue
                 if self.fuse and self._fusable_square(module):
                     w = module.weight_submodule
                     relu_out = (i + 2 < len(modules) and type(modules[i + 1]) is nn.ReLU
-                                and self._fusable_square(modules[i + 2]))
+                                and self._relu_fusable(modules[i + 2]))
                     if last and sqerr_target is not None and w.loss_fusable and torch.is_grad_enabled():
                         # training: forward + residual + backward of the last layer in one pass; its dx is
                         # for a unit loss coefficient, which the producer of h applies (scale_holder)

@@ -253,6 +253,7 @@ class WHVIStackedMatrix(nn.Module):
             for _ in range(self.stack)
         ])
         self.bias = nn.Parameter(torch.zeros(1, self.D_out)) if bias else None
+        self.one_launch = True   # False: block after block, as the reference does (tests compare the two)
 
     @staticmethod
     def setup_dimensions(D_in, D_out):
@@ -272,9 +273,46 @@ class WHVIStackedMatrix(nn.Module):
         for w in self.weight_matrices:
             w.mc_samples = value
 
+    # ------------------------------------------------------------------ one-launch path
+    @property
+    def grouped(self):
+        """True when all blocks run as ONE grouped launch per direction (functional.WHVIStackedFunction): PAPER semantics,
+        diagonal posterior, block size inside the fused kernels' range.  Otherwise block after block, as the reference does."""
+        w = self.weight_matrices[0]
+        return self.one_launch and w.semantics == "paper" and w.covariance == "diag" and w.fusable
+
+    fusable = grouped   # WHVINetwork folds a following nn.ReLU into the grouped launch
+    loss_fusable = False
+
+    def _pack(self):
+        """Re-home the blocks' parameters into one (G, 4, D) buffer so that the kernels read them where they lie (evenly
+        spaced); a no-op when they already are (after the first call, or once FlatParams owns them).  Same values, same
+        Parameter objects, same state_dict -- only ``.data`` moves, like FlatParams does."""
+        ws = self.weight_matrices
+        names = ("s1", "s2", "g_mu", "g_rho")
+        strides = [WF.uniform_stride([getattr(w, n) for w in ws]) for n in names]
+        if None not in strides and len(set(strides)) == 1:
+            return
+        with torch.no_grad():
+            store = torch.empty((len(ws), 4, self.D_in), dtype=torch.float32, device=ws[0].s1.device)
+            for k, w in enumerate(ws):
+                for i, n in enumerate(names):
+                    p = getattr(w, n)
+                    store[k, i].copy_(p)
+                    p.data = store[k, i]
+
+    def _eps_blocks(self, S):
+        ws = self.weight_matrices
+        if any(w._eps_queue for w in ws):   # injected noise (reference draw order, tests): per block
+            return torch.stack([w._draw_eps(S) for w in ws])
+        return torch.randn(len(ws), S, self.D_in, device=ws[0].g_mu.device)
+
     @property
     def kl(self):
-        return sum(weight.kl for weight in self.weight_matrices)
+        ws = self.weight_matrices
+        if self.grouped and ws[0].g_mu.device.type == "cuda":
+            return WF.kl_gaussian_grouped([w.g_mu for w in ws], [w.g_rho for w in ws], self.lambda_, ws[0].kl_mode)
+        return sum(weight.kl for weight in ws)
 
     def sample(self):
         return torch.cat([weight.sample() for weight in self.weight_matrices])
@@ -282,14 +320,24 @@ class WHVIStackedMatrix(nn.Module):
     def sample_lrt(self, h):
         return torch.cat([weight.sample_lrt(h) for weight in self.weight_matrices], dim=-1)
 
-    def forward(self, x, use_lrt=True):
+    def forward(self, x, use_lrt=True, *, relu_out=False, relu_in=False):
         """x: (..., n_in) -> (..., n_out): zero-pad to D_in, apply every block, concatenate,
         add the bias, drop the padding outputs (src/weights.py:182-208)."""
+        if self.grouped:
+            if x.device.type != "cuda":
+                raise RuntimeError("whvi_b200 runs on CUDA only (no CPU fallback); move the module and its inputs to a GPU")
+            ws = self.weight_matrices
+            S, squeeze = ws[0]._resolve_samples(x)
+            self._pack()
+            y = WF.whvi_stacked(x, self._eps_blocks(S), self.bias, self.n_out, [w.s1 for w in ws], [w.s2 for w in ws],
+                                [w.g_mu for w in ws], [w.g_rho for w in ws], relu_out, relu_in)
+            return y[0] if squeeze else y
         x_padded = F.pad(x, (0, self.D_in - self.n_in)) if self.D_in != self.n_in else x
         output = self.sample_lrt(x_padded)
         if self.bias is not None:
             output = output + self.bias
-        return output[..., :self.n_out]
+        output = output[..., :self.n_out]
+        return F.relu(output) if relu_out else output
 
 
 class WHVIColumnMatrix(nn.Module):
@@ -302,6 +350,8 @@ class WHVIColumnMatrix(nn.Module):
                                                      kl_mode=kl_mode)
         self.transposed = transposed
         self.bias = nn.Parameter(torch.zeros(1, 1 if transposed else n_out)) if bias else None
+        self.one_launch = True   # False: the op chain of round 1 (FWHT of g + torch products); tests compare the two
+        self.loss_fusable = False
 
     @property
     def mc_samples(self):
@@ -331,8 +381,23 @@ class WHVIColumnMatrix(nn.Module):
         w = self._weights(1)[0].reshape(-1, 1)
         return w.T if self.transposed else w
 
-    def forward(self, x):
-        S, squeeze = self.weight_submodule._resolve_samples(x)
+    @property
+    def fused(self):
+        """True when the layer runs as one C-ABI call per direction (functional.WHVIColumnFunction): PAPER semantics."""
+        sub = self.weight_submodule
+        return self.one_launch and sub.semantics == "paper" and sub.covariance == "diag"
+
+    def forward(self, x, *, relu_out=False, relu_in=False):
+        sub = self.weight_submodule
+        S, squeeze = sub._resolve_samples(x)
+        if self.fused:
+            if x.device.type != "cuda":
+                raise RuntimeError("whvi_b200 runs on CUDA only (no CPU fallback); move the module and its inputs to a GPU")
+            y = WF.whvi_column(x, sub._draw_eps(S), sub.g_mu, sub.g_rho, sub.s1, sub.s2, self.bias, self.D, self.transposed,
+                               relu_out, relu_in)
+            return y[0] if squeeze else y
+        if relu_in:
+            raise RuntimeError("relu_in needs the fused Column path")
         w = self._weights(S)                                   # (S, D)
         if self.transposed:                                    # (.., D) -> (.., 1)
             if x.dim() == 2:
@@ -344,4 +409,6 @@ class WHVIColumnMatrix(nn.Module):
             y = xs * w.unsqueeze(1)                            # (S, B, D)
         if self.bias is not None:
             y = y + self.bias
+        if relu_out:
+            y = F.relu(y)
         return y[0] if squeeze else y
