@@ -181,7 +181,7 @@ def test_fp64_matches_oracle(k, rows):
     assert y.dtype == torch.float64
     assert rel_err(y.cpu().numpy(), O.fwht(a)) < 1e-13
     assert torch.equal(fwht_(x, out=x), y)          # in place
-    with pytest.raises(RuntimeError, match="float32 and float64"):
+    with pytest.raises(RuntimeError, match="float32, float64 and bfloat16"):
         fwht_(x.half())
 
 

@@ -64,9 +64,21 @@ def _stream(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_capturing = getattr(torch._C, "_cuda_isCurrentStreamCapturing", None) or torch.cuda.is_current_stream_capturing
+
+
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     """Per (device, stream) scratch buffer owned by PyTorch's caching allocator; the
-    library itself never allocates."""
+    library itself never allocates.
+
+    While a CUDA graph is being captured the buffer is a fresh tensor from the graph's own memory pool instead: a cached
+    buffer would tie the graph to memory it does not own -- a buffer created during an EARLIER capture lives in that
+    graph's pool (unmapped by the next ``empty_cache`` once that graph is gone, and ``torch.cuda.graph`` calls
+    ``empty_cache`` on entry), and growing the cached buffer in the middle of a capture frees the one the kernels captured
+    so far still point to.  Inside a capture the allocator reuses a freed scratch tensor for later allocations of the
+    same graph in stream order, which is exactly the lifetime a workspace has."""
+    if _capturing():
+        return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
     key = (device.index if device.index is not None else torch.cuda.current_device(), _stream(device))
     buf = _WORKSPACES.get(key)
     if buf is None or buf.numel() < nbytes:
