@@ -70,6 +70,9 @@ WHVI_API int whvi_fwht_f32(const float* in, float* out, int64_t rows, int64_t D,
  * src/fwht/cuda/fwht_cuda_kernel.cu:170, and its gradient check runs in double,
  * src/fwht/grad_check.py:26).  Parity tooling: correct for every D the fp32 entry accepts, not
  * tuned for bandwidth.  in == out allowed. */
+/* out[r, :] = H_D . (scale * in[r, :]) with a (D) vector broadcast over the rows: the sample-independent first transform
+ * t2 = H(s2 * x) of the layer (feeds WHVI_LAYER_FROM_T2 / whvi_layer_moments_f32) in one pass.  4 <= D <= 2^15. */
+WHVI_API int whvi_fwht_scaled_f32(const float* in, const float* scale, float* out, int64_t rows, int64_t D, whvi_stream_t stream);
 /* bf16 activations in HBM (not in the reference): the same transform with fp32 butterflies in registers and ONE
  * rounding (to nearest even) at the store, i.e. out = bf16( whvi_fwht_f32( float(in) ) ); 4 B/element of HBM traffic instead
  * of 8.  D <= 2^15 (single pass); pointers 8-byte aligned. */

@@ -215,3 +215,18 @@ def test_bf16_io_equals_fp32_kernel_rounded_once(k, rows):
     from whvi_b200 import fwht_
     fwht_(z, out=z)
     assert torch.equal(z, y)
+
+
+@pytest.mark.parametrize("k,rows", [(2, 9), (4, 70), (7, 33), (10, 19), (12, 5), (13, 3), (15, 2)])
+def test_scaled_transform(k, rows):
+    """whvi_fwht_scaled_f32: out = H(scale * x), the hoisted first transform t2 = H(s2 * x) of the layer in one pass."""
+    from whvi_b200 import functional as F
+    D = 1 << k
+    rng = np.random.default_rng(k)
+    x, sc = rng.standard_normal((rows, D)), rng.standard_normal(D)
+    xt, st = torch.from_numpy(x.astype(np.float32)).to(dev()), torch.from_numpy(sc.astype(np.float32)).to(dev())
+    y = F.fwht_scaled_(xt, st)
+    ref = O.fwht(xt.cpu().numpy().astype(np.float64) * st.cpu().numpy().astype(np.float64))
+    assert rel_err(y.cpu().numpy(), ref) < FWHT_TOL
+    from whvi_b200 import fwht_
+    assert torch.equal(y, fwht_(xt * st))   # the same fp32 product, the same butterflies

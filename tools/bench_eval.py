@@ -15,7 +15,7 @@ pass of S samples over the whole test batch).
 Inputs are a fixed function of the global row index and the noise comes from a fixed seed, so the printed checksum must
 agree for N = 1, 2, 4, 8 (up to fp32 summation order).
 
-    python tools/bench_eval.py [--inputs 85248]
+    python tools/bench_eval.py [--inputs 172864]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_eval.py
 
 Also imported by bench.py (`run_eval`), which puts the result under the `eval` key of its JSON line.
@@ -36,8 +36,9 @@ import whvi_b200 as W  # noqa: E402
 from whvi_b200 import functional as WF  # noqa: E402
 from whvi_b200.fwht import fwht_  # noqa: E402
 
-RESERVE_SMS = 4   # left to the pairwise reduce-scatter when there is one (N >= 2)
+RESERVE_SMS = 2   # left to the pairwise reduce-scatter when there is one (N >= 2); its communicator is capped at as many CTAs
 _PAIR_GROUPS = {}
+_CAP = [RESERVE_SMS]   # CTAs the pair communicator may use = SMs the moments kernel leaves free
 
 
 def _pair_group(world, g_s, rank):
@@ -46,7 +47,15 @@ def _pair_group(world, g_s, rank):
         return None
     key = (world, g_s)
     if key not in _PAIR_GROUPS:   # every rank creates every group, in the same order
-        _PAIR_GROUPS[key] = [dist.new_group(list(range(b * g_s, (b + 1) * g_s))) for b in range(world // g_s)]
+        opts = None
+        try:   # the exchange must fit the SMs the moments kernel leaves free: cap this communicator's CTAs
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = RESERVE_SMS
+            opts.config.min_ctas = 1
+        except Exception:   # older builds: the NCCL_MAX_CTAS environment variable (set by the callers) is the cap
+            opts = None
+            _CAP[0] = int(os.environ.get("NCCL_MAX_CTAS", "4"))
+        _PAIR_GROUPS[key] = [dist.new_group(list(range(b * g_s, (b + 1) * g_s)), pg_options=opts) for b in range(world // g_s)]
     return _PAIR_GROUPS[key][rank // g_s]
 
 
@@ -57,21 +66,23 @@ def synthetic_rows(row0, rows, D, dev):
     return torch.add(r, c).sin_()
 
 
-def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2):
+def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2, tiles=0):
     """Returns (on every rank) the result dict; timing = CUDA events, barrier on both sides, max over ranks."""
     D, S = 1 << log2d, samples
     g_s = 2 if world >= 2 else 1
     g_r = world // g_s
     a_idx, b_idx = rank % g_s, rank // g_s
     assert world == g_s * g_r and S % g_s == 0
-    reserve = RESERVE_SMS if g_s > 1 else 0
-    rows_mine = 4 * (148 - reserve)                       # four tiles per CTA of the persistent grid, every chunk
-    cb = rows_mine * g_r                                  # inputs per chunk over all row groups
-    # default: 85248 inputs = a whole number of chunks for N = 1 (592 rows), 2 (576), 4 (1152) and 8 (2304 rows per chunk):
-    # every N evaluates the same input set (strong scaling; same checksum)
-    n_chunks = max(1, (inputs or 85248) // cb)
-    lo, hi = a_idx * (S // g_s), (a_idx + 1) * (S // g_s)
     group = _pair_group(world, g_s, rank)
+    reserve = _CAP[0] if g_s > 1 else 0
+    # 4 * G_s tiles per CTA of the persistent grid per chunk: a rank of a sample-group pair runs half the samples per row, so
+    # it takes twice the rows per chunk to keep the launches as long as at N = 1
+    rows_mine = (tiles or 4 * g_s) * (148 - reserve)
+    cb = rows_mine * g_r                                  # inputs per chunk over all row groups
+    # default: 172864 inputs = a whole number of chunks for N = 1 (592 rows), 2 (1168), 4 (2336) and 8 (4672 rows per chunk):
+    # every N evaluates the same input set (strong scaling; same checksum)
+    n_chunks = max(1, (inputs or 172864) // cb)
+    lo, hi = a_idx * (S // g_s), (a_idx + 1) * (S // g_s)
     torch.manual_seed(0)                                   # replicated parameters
     layer = W.WHVISquarePow2Matrix(D, lambda_=1.0).to(dev)
     with torch.no_grad():
@@ -80,53 +91,50 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2)
         g = WF.reparam(layer.g_mu, layer.g_rho, eps)       # (S / G_s, D): this rank's weight samples, for ALL inputs
         s1, s2 = layer.s1.detach(), layer.s2.detach()
     n_fin = rows_mine // g_s                               # rows this rank finishes after the exchange
-    buckets = [torch.empty(2, rows_mine, D, device=dev) for _ in range(2)]   # (sum y, sum y^2) partials, double-buffered
-    mine = [torch.empty(2, n_fin, D, device=dev) for _ in range(2)]
+    total_chunks = warmup_chunks + n_chunks
+    # the product: (sum_s y, sum_s y^2) for every input this rank finishes -- what `WHVINetwork.predictive_sums` returns; the
+    # fused kernel (N = 1) or the pair's reduce-scatter (N >= 2) writes straight into it, nothing else touches the sums
+    result = torch.empty(total_chunks, 2, n_fin, D, device=dev)
+    buckets = [torch.empty(2, rows_mine, D, device=dev) for _ in range(2)] if g_s > 1 else None   # partial sums, double-buffered
     t2buf = [torch.empty(rows_mine, D, device=dev) for _ in range(2)]
     comm = torch.cuda.Stream(device=dev)
-    checksum = torch.zeros(2, device=dev, dtype=torch.float64)
+    # the inputs of this rank's row group, resident in HBM before the timed region starts (bench contract: `value` is
+    # measured with inputs already on the device); warm-up chunks first
+    x_all = torch.empty(total_chunks, rows_mine, D, device=dev)
+    for c in range(total_chunks):
+        x_all[c].copy_(synthetic_rows(c * cb + b_idx * rows_mine, rows_mine, D, dev))
 
     def prepare(c):
-        """t2 = H(s2 x) of this rank's rows of chunk c (the sample-group partner computes the same rows redundantly: a
-        fraction of a percent of the chunk's work, and it saves a collective)."""
-        x = synthetic_rows(c * cb + b_idx * rows_mine, rows_mine, D, dev)
-        fwht_(x.mul_(s2), out=t2buf[c % 2])
-
-    def finish(part, ev):
-        torch.cuda.current_stream().wait_event(ev)
-        mean = part[0] / S
-        var = part[1] / S - mean * mean
-        checksum[0] += mean.abs().sum(dtype=torch.float64)
-        checksum[1] += var.sum(dtype=torch.float64)
+        """t2 = H(s2 x) of this rank's rows of chunk c, one pass (the sample-group partner computes the same rows
+        redundantly: about a percent of the chunk's work, and it saves a collective)."""
+        WF.fwht_scaled_(x_all[c], s2, out=t2buf[c % 2])
 
     def run(first_chunk, count):
-        pending = None
+        rs_done = [None, None]   # per bucket: its reduce-scatter has finished (recorded on `comm`)
+        main = torch.cuda.current_stream()
         prepare(first_chunk)
         for c in range(first_chunk, first_chunk + count):
-            bucket = buckets[c % 2]
-            WF.layer_moments_raw(t2buf[c % 2], g, s1, s2, None, bucket[0], bucket[1], from_t2=True, reserve_sms=reserve)
-            ev = torch.cuda.Event()
-            part = bucket
-            if g_s > 1:
-                part = mine[c % 2]
-                comm.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(comm):              # overlaps the next chunk's kernel (which leaves SMs free for it)
-                    dist.reduce_scatter_tensor(part[0], bucket[0], group=group)
-                    dist.reduce_scatter_tensor(part[1], bucket[1], group=group)
-                    ev.record(comm)
+            if g_s == 1:
+                WF.layer_moments_raw(t2buf[c % 2], g, s1, s2, None, result[c, 0], result[c, 1], from_t2=True)
             else:
-                ev.record()
+                bucket = buckets[c % 2]
+                if rs_done[c % 2] is not None:             # chunk c - 2's exchange read this bucket
+                    main.wait_event(rs_done[c % 2])
+                WF.layer_moments_raw(t2buf[c % 2], g, s1, s2, None, bucket[0], bucket[1], from_t2=True, reserve_sms=reserve)
+                comm.wait_stream(main)
+                with torch.cuda.stream(comm):              # overlaps the next chunk's kernel (which leaves SMs free for it)
+                    dist.reduce_scatter_tensor(result[c, 0], bucket[0], group=group)
+                    dist.reduce_scatter_tensor(result[c, 1], bucket[1], group=group)
+                    rs_done[c % 2] = torch.cuda.Event()
+                    rs_done[c % 2].record(comm)
             if c + 1 < first_chunk + count:
                 prepare(c + 1)
-            if pending is not None:
-                finish(*pending)
-            pending = (part, ev)
-        if pending is not None:
-            finish(*pending)
+        for ev in rs_done:
+            if ev is not None:
+                main.wait_event(ev)
 
     with torch.no_grad():
         run(0, warmup_chunks)
-        checksum.zero_()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -138,6 +146,12 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2)
     if world > 1:
         dist.barrier()
     ms = torch.tensor([a.elapsed_time(b)], device=dev)
+    checksum = torch.zeros(2, device=dev, dtype=torch.float64)
+    # checksum of the product, after the timed region: mean |predictive mean| and mean predictive variance over the timed
+    # chunks, sum var = sum(sum y^2) / S - sum((sum y)^2) / S^2
+    timed_res = result[warmup_chunks:]
+    checksum[0] = torch.linalg.vector_norm(timed_res[:, 0], ord=1, dtype=torch.float64) / S
+    checksum[1] = timed_res[:, 1].sum(dtype=torch.float64) / S - torch.linalg.vector_norm(timed_res[:, 0], ord=2, dtype=torch.float64) ** 2 / (S * S)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(checksum)
@@ -150,6 +164,9 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2)
                                    f"(bounded sample of 1M) x {S} MC samples", "parallelism": f"{g_s} sample groups x {g_r} row groups",
                        "chunk_inputs": cb, "samples_per_rank": S // g_s, "rows_per_rank_per_chunk": rows_mine,
                        "kernel": "layer_moments_kernel (forward + sum y, sum y^2 in tensor memory, one launch per chunk per rank)",
+                       "inputs_resident": "the rank's inputs are in HBM before the timed region; per chunk: t2 = H(s2 x) in one pass "
+                                          "(whvi_fwht_scaled_f32), one fused launch whose sums (N = 1) or whose pair exchange (N >= 2) "
+                                          "land in the (inputs, 2, D) result; the checksum is taken after the timed region",
                        "collective": "none" if g_s == 1 else f"pairwise reduce-scatter of (sum y, sum y^2) inside each sample-group pair, "
                                                             f"overlapped on a side stream ({reserve} SMs left free for it)"},
             "equiv_algorithmic_gbs": 8.0 * D * pairs / ms.item() / 1e6,
@@ -163,13 +180,16 @@ def main():
     ap.add_argument("--inputs", type=int, default=0)
     ap.add_argument("--log2d", type=int, default=15)
     ap.add_argument("--samples", type=int, default=256)
+    ap.add_argument("--tiles", type=int, default=0, help="tiles (rows) per CTA of the persistent grid per chunk (0: 4 x sample groups)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the pair exchange must fit the SMs the moments kernel leaves free (RESERVE_SMS); bench.py sets the same
+        os.environ.setdefault("NCCL_MAX_CTAS", str(RESERVE_SMS))
         dist.init_process_group("nccl", device_id=dev)
-    res = run_eval(dev, rank, world, inputs=args.inputs, log2d=args.log2d, samples=args.samples)
+    res = run_eval(dev, rank, world, inputs=args.inputs, log2d=args.log2d, samples=args.samples, tiles=args.tiles)
     if rank == 0:
         print(json.dumps(res))
     if world > 1:

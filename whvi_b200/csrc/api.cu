@@ -30,6 +30,16 @@ int whvi_fwht_f32(const float* in, float* out, int64_t rows, int64_t D, whvi_str
     return launch_fwht(in, out, rows, D, static_cast<cudaStream_t>(stream));
 }
 
+int whvi_fwht_scaled_f32(const float* in, const float* scale, float* out, int64_t rows, int64_t D, whvi_stream_t stream)
+{
+    if (rows < 0 || D < 4) return fail(WHVI_E_SHAPE, "fwht_scaled: rows=%lld D=%lld (D >= 4)", (long long)rows, (long long)D);
+    if (!is_pow2(D)) return fail(WHVI_E_SHAPE, "fwht_scaled: n must be a power of 2 (got %lld)", (long long)D);
+    if (rows == 0) return WHVI_OK;
+    if (!in || !scale || !out) return fail(WHVI_E_NULL, "fwht_scaled: null pointer");
+    if (!aligned16(in) || !aligned16(out) || !aligned16(scale)) return fail(WHVI_E_ALIGN, "fwht_scaled: pointers must be 16-byte aligned");
+    return launch_fwht_scaled(in, scale, out, rows, D, static_cast<cudaStream_t>(stream));
+}
+
 int whvi_fwht_bf16(const void* in, void* out, int64_t rows, int64_t D, whvi_stream_t stream)
 {
     if (rows < 0 || D < 1) return fail(WHVI_E_SHAPE, "fwht_bf16: rows=%lld D=%lld", (long long)rows, (long long)D);

@@ -54,6 +54,7 @@ constexpr int kMaxLog2D = 15;       // single-pass kernels keep a whole row in o
 constexpr int kMaxLog2Dmulti = 30;  // multi-pass global variant beyond that
 
 int launch_fwht(const float* in, float* out, int64_t rows, int64_t D, cudaStream_t stream);
+int launch_fwht_scaled(const float* in, const float* scale, float* out, int64_t rows, int64_t D, cudaStream_t stream);
 int launch_fwht_bf16(const void* in, void* out, int64_t rows, int64_t D, cudaStream_t stream);
 int launch_fwht_f64(const double* in, double* out, int64_t rows, int64_t D, cudaStream_t stream);
 struct LayerFwdCall {

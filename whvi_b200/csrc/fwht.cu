@@ -12,9 +12,11 @@
 
 namespace whvi {
 
-template <int N, int C, int K, int GROUPS, class IO>
+// SCALED: out = H(scale * in) with a (D) fp32 vector broadcast over the rows -- the hoisted first transform t2 = H(s2 * x) of
+// the MC predictive evaluation without a separate scaling pass.
+template <int N, int C, int K, int GROUPS, class IO, bool SCALED = false>
 __global__ void __launch_bounds__((1 << (N - C)) * GROUPS)
-fwht_kernel(const IO* __restrict__ in, IO* __restrict__ out, int64_t total)
+fwht_kernel(const IO* __restrict__ in, IO* __restrict__ out, int64_t total, const float* __restrict__ scale = nullptr)
 {
     constexpr int T = 1 << (N - C);
     constexpr int E = 1 << C;
@@ -39,6 +41,11 @@ fwht_kernel(const IO* __restrict__ in, IO* __restrict__ out, int64_t total)
         const int64_t g = base + toff + roff;
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g < total) q = Io<IO>::ld4(in + g);
+        if constexpr (SCALED) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(scale + ((toff + roff) & ((1u << K) - 1u))));
+            // __fmul_rn: never contracted into the first butterfly's add, so the result is bit-identical to scale-then-transform
+            q.x = __fmul_rn(q.x, w.x), q.y = __fmul_rn(q.y, w.y), q.z = __fmul_rn(q.z, w.z), q.w = __fmul_rn(q.w, w.w);
+        }
         v[4 * m + 0] = q.x;
         v[4 * m + 1] = q.y;
         v[4 * m + 2] = q.z;
@@ -140,19 +147,43 @@ static int launch_strided(float* data, int64_t total, int log2_stride, int r, cu
     return check_launch("fwht_strided_kernel");
 }
 
-template <int N, int C, int K, int GROUPS, class IO>
-static int launch_cfg(const IO* in, IO* out, int64_t total, cudaStream_t stream)
+template <int N, int C, int K, int GROUPS, class IO, bool SCALED = false>
+static int launch_cfg(const IO* in, IO* out, int64_t total, cudaStream_t stream, const float* scale = nullptr)
 {
     static unsigned char smem_ok[64] = {};
     constexpr int threads = (1 << (N - C)) * GROUPS;
     constexpr size_t smem = (K <= 2) ? 0 : sizeof(float) * size_t(scratch_words(N, C)) * GROUPS;
-    auto kernel = fwht_kernel<N, C, K, GROUPS, IO>;
+    auto kernel = fwht_kernel<N, C, K, GROUPS, IO, SCALED>;
     if (int rc = ensure_smem(kernel, smem, smem_ok)) return rc;
     const int64_t tiles = (total + (int64_t(1) << N) - 1) >> N;
     const int64_t ctas = (tiles + GROUPS - 1) / GROUPS;
     if (ctas > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "fwht: %lld tiles exceed the grid limit", (long long)ctas);
-    kernel<<<static_cast<unsigned>(ctas), threads, smem, stream>>>(in, out, total);
+    kernel<<<static_cast<unsigned>(ctas), threads, smem, stream>>>(in, out, total, scale);
     return check_launch("fwht_kernel");
+}
+
+// out = H(scale * in), fp32, the layer kernels' range of D (4 .. 2^15)
+int launch_fwht_scaled(const float* in, const float* scale, float* out, int64_t rows, int64_t D, cudaStream_t stream)
+{
+    const int64_t total = rows * D;
+    switch (ilog2(D)) {
+    case 2: return launch_cfg<10, 5, 2, 8, float, true>(in, out, total, stream, scale);
+    case 3: return launch_cfg<10, 5, 3, 8, float, true>(in, out, total, stream, scale);
+    case 4: return launch_cfg<10, 5, 4, 8, float, true>(in, out, total, stream, scale);
+    case 5: return launch_cfg<10, 5, 5, 8, float, true>(in, out, total, stream, scale);
+    case 6: return launch_cfg<10, 5, 6, 8, float, true>(in, out, total, stream, scale);
+    case 7: return launch_cfg<10, 5, 7, 8, float, true>(in, out, total, stream, scale);
+    case 8: return launch_cfg<10, 5, 8, 8, float, true>(in, out, total, stream, scale);
+    case 9: return launch_cfg<10, 5, 9, 8, float, true>(in, out, total, stream, scale);
+    case 10: return launch_cfg<10, 5, 10, 8, float, true>(in, out, total, stream, scale);
+    case 11: return launch_cfg<11, 5, 11, 4, float, true>(in, out, total, stream, scale);
+    case 12: return launch_cfg<12, 5, 12, 2, float, true>(in, out, total, stream, scale);
+    case 13: return launch_cfg<13, 5, 13, 1, float, true>(in, out, total, stream, scale);
+    case 14: return launch_cfg<14, 6, 14, 1, float, true>(in, out, total, stream, scale);
+    case 15: return launch_cfg<15, 6, 15, 1, float, true>(in, out, total, stream, scale);
+    default: break;
+    }
+    return fail(WHVI_E_SHAPE, "fwht_scaled: D = %lld outside [4, 32768]", (long long)D);
 }
 
 // single-pass range (D <= 2^15); returns -1 when D is beyond it

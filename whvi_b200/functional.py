@@ -25,7 +25,7 @@ _LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_fwht_f64": 1, "whvi_layer_fwd_f3
                       "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1, "whvi_mc_moments_f32": 1,
                       "whvi_mc_moments_strided_f32": 1, "whvi_adam_f32": 1, "whvi_layer_moments_f32": 1,
                       "whvi_reparam_dense_f32": 2, "whvi_reparam_dense_bwd_f32": 1, "whvi_kl_dense_f32": 2,
-                      "whvi_fwht_bf16": 1, "whvi_layer_fwd_bf16": 1, "whvi_column_fwd_f32": 3, "whvi_column_bwd_f32": 7, "whvi_pad_rows_f32": 1, "whvi_stacked_fwd_f32": 3, "whvi_stacked_bwd_f32": 6, "whvi_kl_grouped_f32": 1}
+                      "whvi_fwht_bf16": 1, "whvi_fwht_scaled_f32": 1, "whvi_layer_fwd_bf16": 1, "whvi_column_fwd_f32": 3, "whvi_column_bwd_f32": 7, "whvi_pad_rows_f32": 1, "whvi_stacked_fwd_f32": 3, "whvi_stacked_bwd_f32": 6, "whvi_kl_grouped_f32": 1}
 # When set to a dict {"name": [(start_event, stop_event), ...]}, the named calls are bracketed
 # by CUDA events on the launching stream (bench.py's per-kernel roofline timing).
 EVENT_SINK: dict[str, list] | None = None
@@ -170,6 +170,22 @@ def layer_forward_bf16(x, g, s1, s2, bias=None, out=None, relu_out=False, from_t
     return out
 
 
+def fwht_scaled_(x, scale, out=None):
+    """out = H(scale * x) for a (D,) vector ``scale`` broadcast over the rows of ``x`` (rows, D), one pass
+    (``whvi_fwht_scaled_f32``): the hoisted first transform t2 = H(s2 * x) of the MC predictive evaluation."""
+    x, scale = _f32c(x, "x"), _f32c(scale, "scale").reshape(-1)
+    if x.dim() != 2 or scale.numel() != x.size(1):
+        raise RuntimeError("x must be (rows, D) and scale (D,)")
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.shape != x.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
+        raise RuntimeError("out must be a contiguous float32 tensor of x's shape on the same device")
+    with torch.cuda.device(x.device), _Timed("whvi_fwht_scaled_f32"):
+        rc = _lib.lib().whvi_fwht_scaled_f32(x.data_ptr(), scale.data_ptr(), out.data_ptr(), x.size(0), x.size(1), _stream(x.device))
+    _lib.check(rc, "whvi_fwht_scaled_f32")
+    return out
+
+
 def mc_moments_(y, sum_y, sum_y2=None, accumulate=True):
     """sum_y (+)= y.sum(0), sum_y2 (+)= (y*y).sum(0) over the leading MC-sample axis, in one pass
     over ``y`` (S, ...); samples ascending, bit-reproducible."""
@@ -256,7 +272,7 @@ def predictive_moments(x, mu, rho, s1, s2, bias=None, n_samples=64, chunk_sample
         raise RuntimeError("x must be (B, D)")
     B, D = x.shape
     lo, hi = sample_range if sample_range is not None else (0, n_samples if eps is None else eps.size(0))
-    t2 = fwht_(x * s2.reshape(1, D)) if t2 is None else x
+    t2 = (fwht_scaled_(x, s2) if D >= 4 else fwht_(x * s2.reshape(1, D))) if t2 is None else x
     if out is not None:
         sum_y, sum_y2 = out
     else:

@@ -55,7 +55,10 @@ class DevicePrefetcher:
         self.group = group
         self.world = dist.get_world_size(group) if (shard_over_ranks and dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
-        self.stream = torch.cuda.Stream(device=self.device)
+        # high priority: the slice all-gather is an SM-resident NCCL kernel, and the layer kernels it overlaps with fill every
+        # SM (the backward is one persistent CTA per SM) -- with equal priority it only starts when a whole compute kernel has
+        # drained, i.e. it does not overlap at all; with priority its few CTAs take the first slots that free up
+        self.stream = torch.cuda.Stream(device=self.device, priority=-1)
         self.bufs = [None, None]
         self.views = [None, None]   # what is handed out: the leading rows of bufs that the batch fills
         self.ready = [None, None]   # copy finished (recorded on the side stream)
