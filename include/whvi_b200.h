@@ -296,6 +296,13 @@ WHVI_API int whvi_mc_moments_f32(const float* y, float* sum_y, float* sum_y2, in
 WHVI_API int whvi_layer_moments_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1, const float* s2,
                                     const float* bias, float* sum_y, float* sum_y2, int64_t S, int64_t B, int64_t D,
                                     int flags, whvi_stream_t stream);
+/* The same with a starting value: sum_y = in_sum_y + sum_s y, sum_y2 = in_sum_y2 + sum_s y^2 (either may be NULL = 0).  The
+ * multi-GPU evaluation uses it for the exchange inside a sample-group pair without a collective kernel: a rank runs the
+ * rows its PARTNER owns first, with sum_y / sum_y2 pointing into the partner's (NVLink-mapped) staging buffer -- the partial
+ * sums travel as the kernel's own stores -- and then its own rows with in_sum_y / in_sum_y2 = what the partner stored. */
+WHVI_API int whvi_layer_moments_add_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1, const float* s2,
+                                        const float* bias, const float* in_sum_y, const float* in_sum_y2, float* sum_y,
+                                        float* sum_y2, int64_t S, int64_t B, int64_t D, int flags, whvi_stream_t stream);
 /*
  * The same reduction with separate inputs and outputs and a sample stride (so `y` may be a block of
  * rows of a larger (S, B, D) tensor):  out_sum_y[i] = in_sum_y[i] + sum_s y[s*y_sample_stride + i]

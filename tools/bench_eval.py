@@ -66,7 +66,7 @@ def synthetic_rows(row0, rows, D, dev):
     return torch.add(r, c).sin_()
 
 
-def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2, tiles=0):
+def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2, tiles=0, exchange="peer"):
     """Returns (on every rank) the result dict; timing = CUDA events, barrier on both sides, max over ranks."""
     D, S = 1 << log2d, samples
     g_s = 2 if world >= 2 else 1
@@ -74,14 +74,27 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2,
     a_idx, b_idx = rank % g_s, rank // g_s
     assert world == g_s * g_r and S % g_s == 0
     group = _pair_group(world, g_s, rank)
-    reserve = _CAP[0] if g_s > 1 else 0
+    # how the two ranks of a sample-group pair combine their partial sums:
+    #   "peer": no collective kernel -- a rank first runs the rows its PARTNER will finish, with the fused kernel's output
+    #           pointers aimed at the partner's staging buffer (symmetric memory, NVLink-mapped: the partial sums travel as
+    #           the kernel's own stores), then its own rows starting from what the partner stored (whvi_layer_moments_add_f32);
+    #           one signal-pad barrier per chunk orders the two; no SMs are set aside
+    #   "nccl": reduce-scatter on a side stream next to a kernel that leaves a few SMs free for it
+    peer = None
+    if g_s > 1 and exchange == "peer":
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            peer = symm_mem
+        except Exception:
+            peer = None
+    reserve = _CAP[0] if (g_s > 1 and peer is None) else 0
     # 4 * G_s tiles per CTA of the persistent grid per chunk: a rank of a sample-group pair runs half the samples per row, so
     # it takes twice the rows per chunk to keep the launches as long as at N = 1
     rows_mine = (tiles or 4 * g_s) * (148 - reserve)
     cb = rows_mine * g_r                                  # inputs per chunk over all row groups
     # default: 172864 inputs = a whole number of chunks for N = 1 (592 rows), 2 (1168), 4 (2336) and 8 (4672 rows per chunk):
     # every N evaluates the same input set (strong scaling; same checksum)
-    n_chunks = max(1, (inputs or 172864) // cb)
+    n_chunks = max(1, (inputs or (170496 if reserve == 0 else 172864)) // cb)
     lo, hi = a_idx * (S // g_s), (a_idx + 1) * (S // g_s)
     torch.manual_seed(0)                                   # replicated parameters
     layer = W.WHVISquarePow2Matrix(D, lambda_=1.0).to(dev)
@@ -95,7 +108,12 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2,
     # the product: (sum_s y, sum_s y^2) for every input this rank finishes -- what `WHVINetwork.predictive_sums` returns; the
     # fused kernel (N = 1) or the pair's reduce-scatter (N >= 2) writes straight into it, nothing else touches the sums
     result = torch.empty(total_chunks, 2, n_fin, D, device=dev)
-    buckets = [torch.empty(2, rows_mine, D, device=dev) for _ in range(2)] if g_s > 1 else None   # partial sums, double-buffered
+    buckets = [torch.empty(2, rows_mine, D, device=dev) for _ in range(2)] if (g_s > 1 and peer is None) else None   # nccl: partial sums
+    if peer is not None:
+        stage = peer.empty((3, 2, n_fin, D), dtype=torch.float32, device=dev)     # what the partner's kernels store into
+        handle = peer.rendezvous(stage, group)
+        peer_stage = handle.get_buffer(1 - a_idx, (3, 2, n_fin, D), torch.float32)
+        handle.barrier()
     t2buf = [torch.empty(rows_mine, D, device=dev) for _ in range(2)]
     comm = torch.cuda.Stream(device=dev)
     # the inputs of this rank's row group, resident in HBM before the timed region starts (bench contract: `value` is
@@ -109,7 +127,7 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2,
         redundantly: about a percent of the chunk's work, and it saves a collective)."""
         WF.fwht_scaled_(x_all[c], s2, out=t2buf[c % 2])
 
-    def run(first_chunk, count):
+    def run_nccl(first_chunk, count):
         rs_done = [None, None]   # per bucket: its reduce-scatter has finished (recorded on `comm`)
         main = torch.cuda.current_stream()
         prepare(first_chunk)
@@ -132,6 +150,34 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2,
         for ev in rs_done:
             if ev is not None:
                 main.wait_event(ev)
+
+    def run_peer(first_chunk, count):
+        """Per chunk k, on ONE stream:  t2(k+1);  theirs(k+1) -> partner's staging[(k+1) % 3];  barrier;  mine(k) = staging[k % 3]
+        + my sums -> result[k].  The barrier (after theirs(k+1) on both ranks) guarantees the partner's theirs(k) has landed
+        before mine(k) reads it; three staging slots keep the partner's theirs(k+3) -- issued only after it has passed the
+        barrier I reach after mine(k) -- off the slot mine(k) is reading."""
+        other = slice((1 - a_idx) * n_fin, (2 - a_idx) * n_fin)   # rows the partner finishes
+        own = slice(a_idx * n_fin, (a_idx + 1) * n_fin)
+
+        def theirs(c):
+            WF.layer_moments_raw(t2buf[c % 2][other], g, s1, s2, None, peer_stage[c % 3, 0], peer_stage[c % 3, 1], from_t2=True)
+
+        def mine(c):
+            WF.layer_moments_raw(t2buf[c % 2][own], g, s1, s2, None, result[c, 0], result[c, 1], from_t2=True,
+                                 init=(stage[c % 3, 0], stage[c % 3, 1]))
+
+        last = first_chunk + count - 1
+        prepare(first_chunk)
+        theirs(first_chunk)
+        for c in range(first_chunk, last + 1):
+            if c < last:
+                prepare(c + 1)      # t2buf[(c + 1) % 2]: its last reader, mine(c - 1), is already enqueued
+                theirs(c + 1)
+            handle.barrier()
+            mine(c)
+        handle.barrier()            # nobody leaves while its partner may still be writing into it
+
+    run = run_peer if peer is not None else run_nccl
 
     with torch.no_grad():
         run(0, warmup_chunks)
@@ -167,8 +213,12 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2,
                        "inputs_resident": "the rank's inputs are in HBM before the timed region; per chunk: t2 = H(s2 x) in one pass "
                                           "(whvi_fwht_scaled_f32), one fused launch whose sums (N = 1) or whose pair exchange (N >= 2) "
                                           "land in the (inputs, 2, D) result; the checksum is taken after the timed region",
-                       "collective": "none" if g_s == 1 else f"pairwise reduce-scatter of (sum y, sum y^2) inside each sample-group pair, "
-                                                            f"overlapped on a side stream ({reserve} SMs left free for it)"},
+                       "collective": "none" if g_s == 1 else (
+                           "none (no collective kernel): inside each sample-group pair the fused kernel stores the partner's rows "
+                           "straight into the partner's NVLink-mapped staging buffer and starts its own rows from what the partner "
+                           "stored; one signal-pad barrier per chunk" if peer is not None else
+                           f"pairwise reduce-scatter of (sum y, sum y^2) inside each sample-group pair, overlapped on a side stream "
+                           f"({reserve} SMs left free for it)")},
             "equiv_algorithmic_gbs": 8.0 * D * pairs / ms.item() / 1e6,
             "checksum": {"mean_abs_pred_mean": float(checksum[0]) / n_el, "mean_pred_var": float(checksum[1]) / n_el,
                          "inputs": n_chunks * cb,
@@ -180,6 +230,7 @@ def main():
     ap.add_argument("--inputs", type=int, default=0)
     ap.add_argument("--log2d", type=int, default=15)
     ap.add_argument("--samples", type=int, default=256)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--tiles", type=int, default=0, help="tiles (rows) per CTA of the persistent grid per chunk (0: 4 x sample groups)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -189,7 +240,7 @@ def main():
         # the pair exchange must fit the SMs the moments kernel leaves free (RESERVE_SMS); bench.py sets the same
         os.environ.setdefault("NCCL_MAX_CTAS", str(RESERVE_SMS))
         dist.init_process_group("nccl", device_id=dev)
-    res = run_eval(dev, rank, world, inputs=args.inputs, log2d=args.log2d, samples=args.samples, tiles=args.tiles)
+    res = run_eval(dev, rank, world, inputs=args.inputs, log2d=args.log2d, samples=args.samples, tiles=args.tiles, exchange=args.exchange)
     if rank == 0:
         print(json.dumps(res))
     if world > 1:

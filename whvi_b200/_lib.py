@@ -67,6 +67,8 @@ SIGNATURES = {
                                     c_int, c_int, c_void_p]),
     "whvi_kl_grouped_f32": (c_int, [c_void_p, c_void_p, c_float, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                     c_float, c_void_p]),
+    "whvi_layer_moments_add_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_int64, c_int64, c_int64, c_int, c_void_p]),
     "whvi_fwht_scaled_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "whvi_fwht_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "whvi_layer_fwd_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,

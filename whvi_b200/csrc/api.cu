@@ -485,6 +485,13 @@ int whvi_layer_moments_f32(const float* x, int64_t x_sample_stride, const float*
                            const float* bias, float* sum_y, float* sum_y2, int64_t S, int64_t B, int64_t D, int flags,
                            whvi_stream_t stream)
 {
+    return whvi_layer_moments_add_f32(x, x_sample_stride, g, s1, s2, bias, nullptr, nullptr, sum_y, sum_y2, S, B, D, flags, stream);
+}
+
+int whvi_layer_moments_add_f32(const float* x, int64_t x_sample_stride, const float* g, const float* s1, const float* s2,
+                               const float* bias, const float* in_sum_y, const float* in_sum_y2, float* sum_y, float* sum_y2,
+                               int64_t S, int64_t B, int64_t D, int flags, whvi_stream_t stream)
+{
     if (int rc = check_layer_shape("layer_moments", S, B, D, x_sample_stride, 32768)) return rc;
     if (D < 8192) return fail(WHVI_E_SHAPE, "layer_moments: D = %lld outside [8192, 32768] (use whvi_layer_fwd_fused_f32 + whvi_mc_moments_f32)", (long long)D);
     if (flags & ~(WHVI_LAYER_FROM_T2 | WHVI_LAYER_ACCUMULATE | 0xFF00)) return fail(WHVI_E_MODE, "layer_moments: unknown flags %d", flags);
@@ -493,8 +500,11 @@ int whvi_layer_moments_f32(const float* x, int64_t x_sample_stride, const float*
     if (!x || !s1 || !s2 || !sum_y || (S > 0 && !g)) return fail(WHVI_E_NULL, "layer_moments: null pointer");
     if (!aligned16(x) || !aligned16(g) || !aligned16(s1) || !aligned16(s2) || !aligned16(bias) || !aligned16(sum_y) || !aligned16(sum_y2))
         return fail(WHVI_E_ALIGN, "layer_moments: pointers must be 16-byte aligned");
+    if (!aligned16(in_sum_y) || !aligned16(in_sum_y2)) return fail(WHVI_E_ALIGN, "layer_moments: pointers must be 16-byte aligned");
+    if (in_sum_y2 && !sum_y2) return fail(WHVI_E_NULL, "layer_moments: in_sum_y2 given without sum_y2");
     return launch_layer_moments(x, x_sample_stride, g, s1, s2, bias, sum_y, sum_y2, S, B, D, (flags & WHVI_LAYER_FROM_T2) ? 1 : 0,
-                                (flags & WHVI_LAYER_ACCUMULATE) ? 1 : 0, (flags >> 8) & 0xFF, static_cast<cudaStream_t>(stream));
+                                (flags & WHVI_LAYER_ACCUMULATE) ? 1 : 0, (flags >> 8) & 0xFF, static_cast<cudaStream_t>(stream),
+                                in_sum_y, in_sum_y2);
 }
 
 int whvi_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

@@ -115,7 +115,8 @@ int launch_column_bwd(const float* x, int64_t xs, const float* dy, const float* 
                       const float* eps, float* dx, float* dmu, float* drho, float* ds1, float* ds2, float* dbias, float* ws, int64_t S,
                       int64_t B, int64_t D, int64_t n, int transposed, int relu_in, cudaStream_t st);
 int launch_layer_moments(const float* x, int64_t xs, const float* g, const float* s1, const float* s2, const float* bias, float* sum_y,
-                         float* sum_y2, int64_t S, int64_t B, int64_t D, int from_t2, int accumulate, int reserve_sms, cudaStream_t stream);
+                         float* sum_y2, int64_t S, int64_t B, int64_t D, int from_t2, int accumulate, int reserve_sms, cudaStream_t stream,
+                         const float* in_y = nullptr, const float* in_y2 = nullptr);
 int launch_mc_moments(const float* y, int64_t y_sample_stride, const float* in_y, const float* in_y2, float* out_y, float* out_y2,
                       int64_t S, int64_t n, cudaStream_t stream);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, const float* step,

@@ -34,6 +34,8 @@ struct MomArgs {
     int k;
     int accumulate;
     int reserve_sms;           // SMs to leave free (a concurrent NCCL kernel needs somewhere to run: these CTAs take whole SMs)
+    const float* in_y;         // optional: sums to start from (e.g. a partner rank's partial sums, written into this GPU's
+    const float* in_y2;        // memory over NVLink): out = in + this call's sums
 };
 
 // CTAs per SM are bounded by tensor-memory columns: 128 per thread, T / 128 warps per lane quadrant
@@ -146,6 +148,10 @@ __global__ void __launch_bounds__(1 << (N - C), moments_ctas_per_sm(N, C)) layer
                     }
                     float4* py = reinterpret_cast<float4*>(a.sum_y + e0 + off);
                     float4 r1 = make_float4(o1[0], o1[1], o1[2], o1[3]);
+                    if (a.in_y) {
+                        const float4 old = ldg_stream(a.in_y + e0 + off);
+                        r1 = make_float4(old.x + r1.x, old.y + r1.y, old.z + r1.z, old.w + r1.w);
+                    }
                     if (a.accumulate) {
                         const float4 old = *py;
                         r1 = make_float4(old.x + r1.x, old.y + r1.y, old.z + r1.z, old.w + r1.w);
@@ -154,6 +160,10 @@ __global__ void __launch_bounds__(1 << (N - C), moments_ctas_per_sm(N, C)) layer
                     if (a.sum_y2) {
                         float4* py2 = reinterpret_cast<float4*>(a.sum_y2 + e0 + off);
                         float4 r2 = make_float4(o2[0], o2[1], o2[2], o2[3]);
+                        if (a.in_y2) {
+                            const float4 old = ldg_stream(a.in_y2 + e0 + off);
+                            r2 = make_float4(old.x + r2.x, old.y + r2.y, old.z + r2.z, old.w + r2.w);
+                        }
                         if (a.accumulate) {
                             const float4 old = *py2;
                             r2 = make_float4(old.x + r2.x, old.y + r2.y, old.z + r2.z, old.w + r2.w);
@@ -187,11 +197,13 @@ static int launch_moments_cfg(const MomArgs& a, bool from_t2, cudaStream_t strea
 }
 
 int launch_layer_moments(const float* x, int64_t xs, const float* g, const float* s1, const float* s2, const float* bias, float* sum_y,
-                         float* sum_y2, int64_t S, int64_t B, int64_t D, int from_t2, int accumulate, int reserve_sms, cudaStream_t stream)
+                         float* sum_y2, int64_t S, int64_t B, int64_t D, int from_t2, int accumulate, int reserve_sms, cudaStream_t stream,
+                         const float* in_y, const float* in_y2)
 {
     const int k = ilog2(D);
     const int64_t tile = D;   // one row per tile
-    MomArgs a{x, xs, g, s1, s2, bias, sum_y, sum_y2, B * D, (B * D + tile - 1) / tile, static_cast<int>(S), k, accumulate, reserve_sms};
+    MomArgs a{x, xs, g, s1, s2, bias, sum_y, sum_y2, B * D, (B * D + tile - 1) / tile, static_cast<int>(S), k, accumulate, reserve_sms,
+              in_y, in_y2};
     if (k == 13) return launch_moments_cfg<13, 6, 13>(a, from_t2, stream);
     if (k == 14) return launch_moments_cfg<14, 6, 14>(a, from_t2, stream);
     if (k == 15) return launch_moments_cfg<15, 6, 15>(a, from_t2, stream);

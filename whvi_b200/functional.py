@@ -25,7 +25,7 @@ _LAUNCHES_PER_CALL = {"whvi_fwht_f32": 1, "whvi_fwht_f64": 1, "whvi_layer_fwd_f3
                       "whvi_reparam_bwd_f32": 1, "whvi_kl_f32": 1, "whvi_mc_moments_f32": 1,
                       "whvi_mc_moments_strided_f32": 1, "whvi_adam_f32": 1, "whvi_layer_moments_f32": 1,
                       "whvi_reparam_dense_f32": 2, "whvi_reparam_dense_bwd_f32": 1, "whvi_kl_dense_f32": 2,
-                      "whvi_fwht_bf16": 1, "whvi_fwht_scaled_f32": 1, "whvi_layer_fwd_bf16": 1, "whvi_column_fwd_f32": 3, "whvi_column_bwd_f32": 7, "whvi_pad_rows_f32": 1, "whvi_stacked_fwd_f32": 3, "whvi_stacked_bwd_f32": 6, "whvi_kl_grouped_f32": 1}
+                      "whvi_fwht_bf16": 1, "whvi_fwht_scaled_f32": 1, "whvi_layer_moments_add_f32": 1, "whvi_layer_fwd_bf16": 1, "whvi_column_fwd_f32": 3, "whvi_column_bwd_f32": 7, "whvi_pad_rows_f32": 1, "whvi_stacked_fwd_f32": 3, "whvi_stacked_bwd_f32": 6, "whvi_kl_grouped_f32": 1}
 # When set to a dict {"name": [(start_event, stop_event), ...]}, the named calls are bracketed
 # by CUDA events on the launching stream (bench.py's per-kernel roofline timing).
 EVENT_SINK: dict[str, list] | None = None
@@ -205,7 +205,7 @@ def mc_moments_(y, sum_y, sum_y2=None, accumulate=True):
 FUSED_MOMENTS_MIN_D, FUSED_MOMENTS_MAX_D = 8192, 32768
 
 
-def layer_moments_raw(x, g, s1, s2, bias, sum_y, sum_y2=None, from_t2=False, accumulate=False, reserve_sms=0):
+def layer_moments_raw(x, g, s1, s2, bias, sum_y, sum_y2=None, from_t2=False, accumulate=False, reserve_sms=0, init=None):
     """sum_y (+)= sum_s y[s], sum_y2 (+)= sum_s y[s]^2 for y[s] = s1 * H(g[s] * H(s2 * x)) + bias over ALL samples of ``g``
     in ONE kernel that keeps the running sums in tensor memory: no prediction is ever written to HBM
     (``whvi_layer_moments_f32``; 8192 <= D <= 32768).  ``x``: (B, D) shared or (S, B, D); ``from_t2``: x holds H(s2 * x);
@@ -217,11 +217,17 @@ def layer_moments_raw(x, g, s1, s2, bias, sum_y, sum_y2=None, from_t2=False, acc
     for t, name in ((sum_y, "sum_y"), (sum_y2, "sum_y2")):
         if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != B * D or t.device != x.device):
             raise RuntimeError(f"{name} must be a contiguous float32 tensor with {B * D} elements on {x.device}")
+    flags = (2 if from_t2 else 0) | (4 if accumulate else 0) | ((int(reserve_sms) & 0xFF) << 8)
+    if init is not None:   # (in_sum_y, in_sum_y2): out = in + this call's sums (``whvi_layer_moments_add_f32``)
+        iy, iy2 = init
+        with torch.cuda.device(x.device), _Timed("whvi_layer_moments_add_f32"):
+            rc = _lib.lib().whvi_layer_moments_add_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
+                                                       _ptr(iy), _ptr(iy2), sum_y.data_ptr(), _ptr(sum_y2), S, B, D, flags, _stream(x.device))
+        _lib.check(rc, "whvi_layer_moments_add_f32")
+        return sum_y, sum_y2
     with torch.cuda.device(x.device), _Timed("whvi_layer_moments_f32", "from_t2" if from_t2 else "full"):
         rc = _lib.lib().whvi_layer_moments_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
-                                               sum_y.data_ptr(), _ptr(sum_y2), S, B, D,
-                                               (2 if from_t2 else 0) | (4 if accumulate else 0) | ((int(reserve_sms) & 0xFF) << 8),
-                                               _stream(x.device))
+                                               sum_y.data_ptr(), _ptr(sum_y2), S, B, D, flags, _stream(x.device))
     _lib.check(rc, "whvi_layer_moments_f32")
     return sum_y, sum_y2
 
