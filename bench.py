@@ -352,9 +352,11 @@ def run_ours(args):
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
     loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_run(steps):
+    def e2e_run(steps, verify=False):
         losses, pending = [], None
         for i, (x, y) in enumerate(DevicePrefetcher(((x_host, y_host) for _ in range(steps)), dev, shard_over_ranks=True)):
+            if verify:   # warm-up only: what the ranks handed each other over NVLink is the minibatch, bit for bit
+                assert torch.equal(x, x_dev) and torch.equal(y, y_dev), "DevicePrefetcher delivered a different minibatch"
             total = step(x, y)
             loss_host[i % 2].copy_(total, non_blocking=True)
             loss_ready[i % 2].record()
@@ -367,7 +369,7 @@ def run_ours(args):
             losses.append(float(loss_host[pending]))
         return losses
 
-    e2e_run(2)
+    e2e_run(3, verify=True)
     e2e_losses = []
     ms_e2e = timed(lambda: e2e_losses.extend(e2e_run(args.steps)), 1) / args.steps
     e2e_value = rows_per_step / (ms_e2e * 1e-3)

@@ -38,6 +38,37 @@ def build_H(D, device):
 kl_gaussian = WF.kl_gaussian
 
 
+_PEER_SLOTS: dict = {}   # (device, group id, shapes) -> symmetric double buffers (allocating + rendezvous is collective and slow: once)
+
+
+def _peer_slots(device, group, shapes_dtypes):
+    """Two sets of symmetric (NVLink peer-mapped) device buffers for ``DevicePrefetcher(shard_over_ranks=True)``, or None when
+    symmetric memory is not available.  Collective over ``group`` on first use for a given set of shapes."""
+    import torch.distributed as dist
+    key = (torch.device(device).index, id(group), shapes_dtypes)
+    if key in _PEER_SLOTS:
+        return _PEER_SLOTS[key]
+    slots = None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = group if group is not None else dist.group.WORLD
+        world = dist.get_world_size(grp)
+        slots = []
+        for _ in range(2):
+            local, peers, handles = [], [], []
+            for shape, dtype in shapes_dtypes:
+                t = symm_mem.empty(shape, dtype=dtype, device=device)
+                h = symm_mem.rendezvous(t, grp)
+                local.append(t)
+                peers.append([h.get_buffer(q, shape, dtype) for q in range(world)])
+                handles.append(h)
+            slots.append((tuple(local), peers, handles))
+    except Exception:
+        slots = None
+    _PEER_SLOTS[key] = slots
+    return slots
+
+
 class DevicePrefetcher:
     """Iterate over host batches (tuples of pinned tensors) with the host->device copy of
     batch i+1 running on a side stream while batch i is being computed on.  Two fixed sets of
@@ -46,9 +77,12 @@ class DevicePrefetcher:
 
     def __init__(self, batches, device, group=None, shard_over_ranks=False):
         """``shard_over_ranks`` (MC-sample-sharded jobs, where every rank needs the WHOLE minibatch):
-        each rank copies only its 1/world slice of the rows over its own PCIe link and the slices
-        are all-gathered over NVLink on the side stream, so the job reads the minibatch from host
-        memory once per step instead of once per rank."""
+        each rank copies only its 1/world slice of the rows over its own PCIe link and hands it to the other ranks over
+        NVLink on the side stream, so the job reads the minibatch from host memory once per step instead of once per rank.
+        The hand-over uses no SMs when symmetric memory is available: every rank's buffers are peer-mapped and the slice is
+        written into each of them by the copy engines (``copy_`` device -> peer), bracketed by two signal-pad barriers (all
+        ranks done with the slot / all slices landed); the compute kernels it overlaps with keep every SM.  Fallback: an NCCL
+        all-gather (an SM-resident kernel that competes with them: measured 0.5 ms per step at 8 GPUs)."""
         import torch.distributed as dist
         self.batches = iter(batches)
         self.device = torch.device(device)
@@ -59,6 +93,8 @@ class DevicePrefetcher:
         # SM (the backward is one persistent CTA per SM) -- with equal priority it only starts when a whole compute kernel has
         # drained, i.e. it does not overlap at all; with priority its few CTAs take the first slots that free up
         self.stream = torch.cuda.Stream(device=self.device, priority=-1)
+        # the (cached, peer-mapped) buffers may still be in use by work enqueued before this object existed
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
         self.bufs = [None, None]
         self.views = [None, None]   # what is handed out: the leading rows of bufs that the batch fills
         self.ready = [None, None]   # copy finished (recorded on the side stream)
@@ -77,12 +113,31 @@ class DevicePrefetcher:
         # with drop_last=False) is copied into -- and handed out as -- the leading rows of the buffers
         fits = self.bufs[k] is not None and len(self.bufs[k]) == len(host) and all(
             d.shape[1:] == h.shape[1:] and d.dtype == h.dtype and d.size(0) >= h.size(0) for d, h in zip(self.bufs[k], host))
+        peer = None
+        if self.world > 1 and all(h.size(0) % self.world == 0 and h.size(0) > 0 for h in host):
+            slots = _peer_slots(self.device, self.group, tuple((tuple(h.shape), h.dtype) for h in host))
+            if slots is not None:
+                peer = slots[k]
+                self.bufs[k] = peer[0]
+                fits = True
         if not fits:
             self.bufs[k] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host)
         views = tuple(d[:h.size(0)] for d, h in zip(self.bufs[k], host))
         with torch.cuda.stream(self.stream):
             if self.done[k] is not None:
                 self.stream.wait_event(self.done[k])
+            if peer is not None:
+                _, peers, handles = peer
+                handles[0].barrier()                      # every rank's consumer has finished with this slot
+                for t, (d, h) in enumerate(zip(views, host)):
+                    n = h.size(0) // self.world
+                    rows = slice(self.rank * n, (self.rank + 1) * n)
+                    d[rows].copy_(h[rows], non_blocking=True)            # my slice: host -> my buffer (PCIe)
+                    for q in range(self.world):
+                        if q != self.rank:
+                            peers[t][q][rows].copy_(d[rows], non_blocking=True)   # -> rank q's buffer (NVLink, copy engine)
+                handles[0].barrier()                      # all slices have landed everywhere
+                host = ()
             for d, h in zip(views, host):
                 if self.world > 1 and h.size(0) % self.world == 0 and h.size(0) > 0:
                     import torch.distributed as dist
