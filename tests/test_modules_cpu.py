@@ -76,3 +76,19 @@ def test_dimensions_and_dispatch_match_reference_grid(golden):
                 kind = 1
             assert kind == int(kinds[a - 1, b - 1]), (a, b)
             assert sum(p.numel() for p in layer.parameters()) == int(counts[a - 1, b - 1]), (a, b)
+
+
+def test_uniform_stride_detection():
+    """Host logic of the grouped Stacked launch: per-block parameter vectors are read where they lie only when they are evenly
+    spaced, contiguous and 16-byte aligned relative to each other."""
+    import torch
+    from whvi_b200 import functional as F
+    store = torch.zeros(5, 4, 16)
+    assert F.uniform_stride([store[k, 0] for k in range(5)]) == 64
+    assert F.uniform_stride([store[k, 2] for k in range(5)]) == 64
+    assert F.uniform_stride([store[0, 1]]) == 16
+    assert F.uniform_stride([store[0, 0], store[2, 0], store[3, 0]]) is None            # uneven
+    assert F.uniform_stride([torch.zeros(16) for _ in range(3)]) in (None, 16, 32, 64, 128)  # separate allocations: whatever they are, not a crash
+    flat = torch.zeros(100)
+    assert F.uniform_stride([flat[0:16], flat[18:34]]) is None                           # 72 bytes apart: not a multiple of 16
+    assert F.uniform_stride([flat[0:16], flat[8:24]]) is None                            # overlapping

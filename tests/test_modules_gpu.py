@@ -257,6 +257,62 @@ def test_column_one_call_equals_op_chain(n, transposed, bias, shared):
             assert rel_err(g1[k].cpu().numpy(), ref) < TOL, k
 
 
+@pytest.mark.parametrize("n_in,n_out", [(13, 128), (20, 50), (100, 1), (1, 40)])
+def test_non_square_layers_standalone_two_dimensional(n_in, n_out):
+    """Outside a WHVINetwork (mc_samples unset) the one-call Stacked / Column paths behave like the reference's modules:
+    (batch, n_in) -> (batch, n_out), one noise draw, autograd through the input; also under no_grad."""
+    import copy
+    torch.manual_seed(n_in * 7 + n_out)
+    a = W.WHVILinear(n_in, n_out, lambda_=2.0, bias=True).to(dev())
+    b = copy.deepcopy(a)
+    b.weight_submodule.one_launch = False
+    x = torch.randn(11, n_in, device=dev())
+    outs = []
+    for layer in (a, b):
+        for blk in layer.square_blocks():
+            blk.inject_eps(torch.full((1, blk.D), 0.5, device=dev()))
+        xi = x.clone().requires_grad_()
+        y = layer(xi)
+        assert y.shape == (11, n_out)
+        y.sin().sum().backward()
+        outs.append((y.detach().cpu().numpy(), xi.grad.cpu().numpy()))
+        with torch.no_grad():
+            for blk in layer.square_blocks():
+                blk.inject_eps(torch.full((1, blk.D), 0.5, device=dev()))
+            assert rel_err(layer(x).cpu().numpy(), outs[-1][0]) < 1e-6
+    assert rel_err(outs[0][0], outs[1][0]) < 1e-5
+    assert rel_err(outs[0][1], outs[1][1]) < TOL
+
+
+def test_stacked_parameters_are_packed_once_and_survive_flat_params():
+    """The grouped launch reads the blocks' parameters where they lie: the module packs them evenly spaced on first use
+    (same values, same Parameter objects, same state_dict), and FlatParams' own re-homing keeps them evenly spaced."""
+    from whvi_b200 import functional as F
+    torch.manual_seed(1)
+    layer = W.WHVILinear(13, 128, lambda_=2.0).to(dev())
+    before = {k: v.clone() for k, v in layer.state_dict().items()}
+    params = list(layer.parameters())
+    blocks = layer.square_blocks()
+    with torch.no_grad():   # scatter them: the first forward has to pack
+        for i, b in enumerate(blocks):
+            b.s1.data = torch.cat([torch.zeros(4 * i, device=dev()), b.s1.data])[4 * i:]
+    assert F.uniform_stride([b.s1 for b in blocks]) is None
+    layer.mc_samples = 2
+    y0 = layer(torch.ones(4, 13, device=dev()))
+    assert F.uniform_stride([b.s1 for b in blocks]) is not None   # packed by the module, or already evenly spaced by the allocator
+    assert all(p is q for p, q in zip(params, layer.parameters()))
+    assert all(torch.equal(v, layer.state_dict()[k]) for k, v in before.items())
+    flat = W.FlatParams(layer.parameters())
+    assert F.uniform_stride([b.s1 for b in blocks]) is not None and F.uniform_stride([b.g_rho for b in blocks]) is not None
+    for b in blocks:
+        b.inject_eps(torch.zeros(2, b.D, device=dev()))
+    y1 = layer(torch.ones(4, 13, device=dev()))
+    y1.sum().backward()
+    assert flat.attached() and float(flat.grad.abs().sum()) > 0
+    layer.mc_samples = None
+    assert y0.shape == y1.shape == (2, 4, 128)
+
+
 def test_stacked_network_fused_equals_unfused():
     """BASELINE config 3's shape (13 -> 128 -> 128 -> 1 with ReLUs): the grouped Stacked launch with the ReLU folded into it
     and into the consumer's backward gives the same loss and gradients as every module run on its own."""
