@@ -71,7 +71,27 @@ def build(force: bool = False, verbose: bool = False, variant: str | None = None
     objs = [obj_dir / (s.stem + ".o") for s in sources()]
     if force or jobs or _stale(lib_path, objs):
         run([NVCC, *ARCH, "-shared", "-o", str(lib_path), *map(str, objs), "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    if not variant:
+        build_fastcall(force)
     return lib_path
+
+
+def build_fastcall(force: bool = False) -> Path | None:
+    """The CPython host shim of the FWHT call (csrc_host/fastcall.c: no CUDA, no torch headers; gcc, one second).  Optional:
+    without it whvi_b200.fwht_ reaches the same C-ABI entry points through ctypes, ~1 us per call slower."""
+    import sysconfig
+    src = PKG / "csrc_host" / "fastcall.c"
+    out = PKG / ("_fastcall" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+    inc = sysconfig.get_paths()["include"]
+    if not (Path(inc) / "Python.h").exists():
+        return None
+    if force or _stale(out, [src]):
+        r = subprocess.run([os.environ.get("CC", "gcc"), "-O2", "-fPIC", "-shared", "-I", inc, str(src), "-o", str(out)],
+                           capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            return None
+    return out
 
 
 if __name__ == "__main__":

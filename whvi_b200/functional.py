@@ -9,6 +9,7 @@ a network) or ``(S, B, D)``; ``g`` is ``(S, D)``, one reparameterised vector per
 from __future__ import annotations
 
 import ctypes
+import functools
 
 import torch
 from torch.autograd import Function
@@ -87,6 +88,20 @@ def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     return buf
 
 
+@functools.lru_cache(maxsize=None)
+def _query(name: str, *dims) -> tuple:
+    """Size queries of the C ABI (workspace bytes, partial-sum counts) are pure functions of the shape: asked once per shape,
+    not once per call (a ctypes call with byref out-parameters costs ~4 us of host time)."""
+    fn = getattr(_lib.lib(), name)
+    if name == "whvi_layer_loss_sizes":
+        a, b = ctypes.c_size_t(0), ctypes.c_int64(0)
+        _lib.check(fn(*dims, ctypes.byref(a), ctypes.byref(b)), name)
+        return a.value, b.value
+    out = ctypes.c_int64(0) if name == "whvi_layer_fwd_partials" else ctypes.c_size_t(0)
+    _lib.check(fn(*dims, ctypes.byref(out)), name)
+    return (out.value,)
+
+
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.device.type != "cuda":
         raise RuntimeError(f"{name} must be a CUDA tensor")
@@ -132,9 +147,7 @@ def layer_forward_raw(x, g, s1, s2, bias=None, out=None, relu_out=False, target=
         target = _f32c(target, "target")
         if target.shape != (B, D):
             raise RuntimeError(f"target must be {(B, D)}, got {tuple(target.shape)}")
-        n = ctypes.c_int64(0)
-        _lib.check(L.whvi_layer_fwd_partials(S, B, D, ctypes.byref(n)), "whvi_layer_fwd_partials")
-        partials = torch.empty(max(n.value, 1), dtype=torch.float32, device=x.device)
+        partials = torch.empty(max(_query("whvi_layer_fwd_partials", S, B, D)[0], 1), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device), _Timed("whvi_layer_fwd_fused_f32", ("shared_x" if xs == 0 else "distinct_x") + ("/from_t2" if from_t2 else "")):
         rc = L.whvi_layer_fwd_fused_f32(x.data_ptr(), xs, g.data_ptr(), s1.data_ptr(), s2.data_ptr(), _ptr(bias),
                                         out.data_ptr(), S, B, D, (1 if relu_out else 0) | (2 if from_t2 else 0),
@@ -370,9 +383,7 @@ def layer_backward_raw(x, dy, g, s1, s2, want_dx=True, want_dbias=False, relu_in
     ds2 = torch.empty(D, dtype=torch.float32, device=dev)
     dbias = torch.empty(D, dtype=torch.float32, device=dev) if want_dbias else None
     L = _lib.lib()
-    need = ctypes.c_size_t(0)
-    _lib.check(L.whvi_layer_bwd_workspace_bytes(S, B, D, ctypes.byref(need)), "whvi_layer_bwd_workspace_bytes")
-    ws = _workspace(dev, need.value)
+    ws = _workspace(dev, _query("whvi_layer_bwd_workspace_bytes", S, B, D)[0])
     if dy_scale is not None:  # upstream gradient = dy_scale * dy (see WHVILayerLossFunction)
         if target is not None:
             raise RuntimeError("dy_scale and target are mutually exclusive")
@@ -430,10 +441,9 @@ def layer_loss_raw(x, g, s1, s2, bias, target, want_dx=True, relu_in=False):
         bias = _f32c(bias, "bias").reshape(-1)
     dev = x.device
     L = _lib.lib()
-    need, nsq = ctypes.c_size_t(0), ctypes.c_int64(0)
-    _lib.check(L.whvi_layer_loss_sizes(S, B, D, ctypes.byref(need), ctypes.byref(nsq)), "whvi_layer_loss_sizes")
-    ws = _workspace(dev, need.value)
-    sqp = torch.zeros(max(nsq.value, 1), dtype=torch.float32, device=dev)   # an upper bound: unused entries stay zero
+    need, nsq = _query("whvi_layer_loss_sizes", S, B, D)
+    ws = _workspace(dev, need)
+    sqp = torch.zeros(max(nsq, 1), dtype=torch.float32, device=dev)   # an upper bound: unused entries stay zero
     dx = torch.empty((S, B, D), dtype=torch.float32, device=dev) if want_dx else None
     dg = torch.empty((S, D), dtype=torch.float32, device=dev)
     ds1 = torch.empty(D, dtype=torch.float32, device=dev)
@@ -623,9 +633,7 @@ class ReparamDenseFunction(Function):
             raise RuntimeError(f"L must be {(D, D)}, got {tuple(L.shape)}")
         g = torch.empty_like(eps)
         lib = _lib.lib()
-        need = ctypes.c_size_t(0)
-        _lib.check(lib.whvi_reparam_dense_workspace_bytes(S, D, ctypes.byref(need)), "whvi_reparam_dense_workspace_bytes")
-        ws = _workspace(eps.device, need.value)
+        ws = _workspace(eps.device, _query("whvi_reparam_dense_workspace_bytes", S, D)[0])
         with torch.cuda.device(eps.device), _Timed("whvi_reparam_dense_f32"):
             rc = lib.whvi_reparam_dense_f32(mu.data_ptr(), L.data_ptr(), eps.data_ptr(), g.data_ptr(), S, D, ws.data_ptr(),
                                             ws.numel(), _stream(eps.device))
@@ -767,10 +775,8 @@ class WHVIStackedFunction(Function):
         dev = dy.device
         lib = _lib.lib()
         want_dx = ctx.needs_input_grad[0]
-        need = ctypes.c_size_t(0)
-        _lib.check(lib.whvi_stacked_bwd_workspace_bytes(S, B, D, G, 1 if want_dx else 0, ctypes.byref(need)), "whvi_stacked_bwd_workspace_bytes")
         with torch.cuda.device(dev):
-            ws = _workspace(dev, need.value)
+            ws = _workspace(dev, _query("whvi_stacked_bwd_workspace_bytes", S, B, D, G, 1 if want_dx else 0)[0])
             out = torch.empty((5 if has_bias else 4, G, D), dtype=torch.float32, device=dev)   # dmu, drho, ds1, ds2, [dbias]
             dx = torch.empty((S, B, n_in), dtype=torch.float32, device=dev) if want_dx else None
             with _Timed("whvi_stacked_bwd_f32"):
@@ -832,10 +838,8 @@ class WHVIColumnFunction(Function):
         dev = dy.device
         lib = _lib.lib()
         want_dx = ctx.needs_input_grad[0]
-        need = ctypes.c_size_t(0)
-        _lib.check(lib.whvi_column_bwd_workspace_bytes(S, D, n, ctypes.byref(need)), "whvi_column_bwd_workspace_bytes")
         with torch.cuda.device(dev):
-            ws = _workspace(dev, need.value)
+            ws = _workspace(dev, _query("whvi_column_bwd_workspace_bytes", S, D, n)[0])
             out = torch.empty((4, D), dtype=torch.float32, device=dev)   # dmu, drho, ds1, ds2
             dbias = torch.empty((1, 1 if transposed else n), dtype=torch.float32, device=dev) if has_bias else None
             dx = torch.empty((S, B, n if transposed else 1), dtype=torch.float32, device=dev) if want_dx else None

@@ -27,13 +27,15 @@ def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-_FN = {}   # dtype -> (C entry point, name): looked up once, not per call
+_FN = {}   # dtype -> (callable(in_ptr, out_ptr, rows, D, stream) -> status, name): looked up once, not per call
 
 
 def _entry(dtype):
     fn = _FN.get(dtype)
     if fn is None:
-        # same dispatch as fwht_cuda_kernel.cu:170, plus bf16 activations (fp32 butterflies, one rounding at the store)
+        # same dispatch as fwht_cuda_kernel.cu:170, plus bf16 activations (fp32 butterflies, one rounding at the store).
+        # _lib.lib() hands out the entry point behind the CPython shim (csrc_host/fastcall.c) when that is built: at the sizes
+        # of the reference's published benchmark a call is launch-latency bound and ctypes' marshalling was 3.5 of its 9.5 us
         name = {torch.float32: "whvi_fwht_f32", torch.float64: "whvi_fwht_f64", torch.bfloat16: "whvi_fwht_bf16"}[dtype]
         fn = _FN[dtype] = (getattr(_lib.lib(), name), name)
     return fn
