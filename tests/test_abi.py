@@ -85,3 +85,41 @@ def test_argument_validation_without_a_gpu():
     assert L.whvi_mc_moments_f32(a, a, a, 2, 6, 0, None) == E_SHAPE                          # n % 4
     assert L.whvi_mc_moments_strided_f32(a, 8, None, None, a, None, 2, 16, None) == E_SHAPE  # stride < n
     assert L.whvi_mc_moments_f32(a, None, a, 2, 8, 0, None) == E_NULL
+
+
+def test_shim_and_ctypes_reach_the_same_entry_points():
+    """The CPython shim (csrc_host/fastcall.c) is a second way INTO the C ABI, not around it: for the all-integer entry points
+    it hands out, the status codes and error messages equal what the ctypes binding of the same function returns (argument
+    validation only -- no GPU is touched), new entry points of this round included."""
+    from whvi_b200 import _lib
+    L = _lib.lib()
+    raw = L._cdll
+    if L._fc is None:
+        pytest.skip("the shim is optional; ctypes is the binding without it")
+    a = 1 << 20   # a fake, 16-byte aligned "device pointer": validation failures come before any dereference
+    cases = [
+        ("whvi_fwht_f32", (a, a, 4, 12, None)),
+        ("whvi_fwht_f32", (a + 4, a, 4, 16, None)),
+        ("whvi_fwht_bf16", (a, a, 4, 24, None)),
+        ("whvi_fwht_scaled_f32", (a, None, a, 4, 16, None)),
+        ("whvi_layer_fwd_f32", (a, 7, a, a, a, None, a, 2, 3, 64, None)),
+        ("whvi_layer_fwd_bf16", (a, 0, a, a, a, None, a, 2, 3, 48, 0, None)),
+        ("whvi_layer_bwd_f32", (a, 0, a, a, a, a, a, a, a, a, None, a, 16, 2, 3, 64, None)),
+        ("whvi_stacked_fwd_f32", (a, 0, a, a, a, a, 8, a, None, a, a, a, 2, 3, 16, 4, 64, 0, None)),       # param_stride < D
+        ("whvi_stacked_fwd_f32", (a, 0, a, a, a, a, 16, a, None, a, a, a, 2, 3, 16, 4, 100, 0, None)),     # n_out does not match G * D
+        ("whvi_stacked_bwd_f32", (a, 0, a, a, a, a, a, 16, a, None, 13, None, a, a, a, None, a, 0, 2, 3, 16, 4, 64, 0, None)),
+        ("whvi_column_fwd_f32", (a, 0, a, a, a, a, a, None, a, a, a, 2, 3, 16, 5, 1, 0, None)),            # D != next_pow2(n)
+        ("whvi_column_bwd_f32", (a, 0, a, a, a, a, a, a, None, a, a, a, a, None, a, 0, 2, 3, 16, 16, 0, 1, None)),  # RELU_IN on the plain form
+        ("whvi_layer_moments_add_f32", (a, 0, a, a, a, None, a + 4, None, a, a, 2, 3, 8192, 0, None)),
+        ("whvi_pad_rows_f32", (a, a, 3, 20, 16, None)),
+        ("whvi_mc_moments_f32", (a, a, a, 2, 6, 0, None)),
+    ]
+    for name, args in cases:
+        fast = getattr(L, name)
+        assert not hasattr(fast, "argtypes"), name          # handed out behind the shim
+        rc_fast, msg_fast = fast(*args), L.whvi_last_error()
+        rc_raw, msg_raw = getattr(raw, name)(*args), L.whvi_last_error()
+        assert rc_fast == rc_raw and rc_fast < 0, (name, rc_fast, rc_raw)
+        assert msg_fast == msg_raw and msg_fast, name
+    # float or output-pointer parameters stay on ctypes
+    assert hasattr(L.whvi_kl_f32, "argtypes") and hasattr(L.whvi_layer_bwd_workspace_bytes, "argtypes")

@@ -313,6 +313,22 @@ def test_stacked_parameters_are_packed_once_and_survive_flat_params():
     assert y0.shape == y1.shape == (2, 4, 128)
 
 
+@pytest.mark.parametrize("n_in,n_out", [(16, 16), (13, 128), (100, 1), (1, 40)])
+def test_empty_batch(n_in, n_out):
+    """Edge case the reference's ops handle implicitly: a batch of zero rows gives an empty output and zero gradients."""
+    layer = W.WHVILinear(n_in, n_out, lambda_=2.0, bias=True).to(dev())
+    layer.mc_samples = 3
+    x = torch.zeros(0, n_in, device=dev(), requires_grad=True)
+    y = layer(x)
+    layer.mc_samples = None
+    assert y.shape == (3, 0, n_out)
+    (y.sum() + layer.kl).backward()
+    for name, p in layer.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        if not name.endswith(("g_mu", "g_rho")):   # only the KL term reaches mu / rho
+            assert float(p.grad.abs().sum()) == 0.0, name
+
+
 def test_stacked_network_fused_equals_unfused():
     """BASELINE config 3's shape (13 -> 128 -> 128 -> 1 with ReLUs): the grouped Stacked launch with the ReLU folded into it
     and into the consumer's backward gives the same loss and gradients as every module run on its own."""
