@@ -380,7 +380,8 @@ def run_ours(args):
     rows_per_launch = chunk * B
 
     def position(calls, tag, alg_bytes_per_row, dram_note):
-        ms = [a.elapsed_time(b) for name in calls for a, b, t in sink[name] if t == tag]
+        tags = tag if isinstance(tag, tuple) else (tag,)
+        ms = [a.elapsed_time(b) for name in calls for a, b, t in sink[name] if t in tags]
         if not ms:
             return None
         avg = sum(ms) / len(ms)
@@ -393,7 +394,8 @@ def run_ours(args):
     pos = {
         "bwd_layer2 (distinct x, dx written)": position(bwd_calls, "distinct_x", 12 * D, f"{12 * D} (x, dy in; dx out)"),
         "bwd_layer1 (shared x, no dx)": position(bwd_calls, "shared_x/nodx", 12 * D, shared + "; dy in, no dx"),
-        "fwd_layer1 (shared x)": position(("whvi_layer_fwd_fused_f32",), "shared_x", 8 * D, shared + "; y out"),
+        "fwd_layer1 (shared x)": position(("whvi_layer_fwd_fused_f32",), ("shared_x", "shared_x/from_t2"), 8 * D,
+                                          shared + " (its first transform hoisted: t2 = H(s2 x) once per launch); y out"),
         "fwd_layer2 (distinct x)": position(("whvi_layer_fwd_fused_f32",), "distinct_x", 8 * D, f"{8 * D} (x in, y out)"),
         "loss_layer3 (fwd + MNLL + bwd in one kernel)": position(("whvi_layer_loss_f32",), "distinct_x", 8 * D,
                                                                   f"{8 * D} (x in, dx out; the target is L2-resident)"),

@@ -481,3 +481,31 @@ def test_forward_bf16_io(S, B, D, shared):
         y2 = F.layer_forward_bf16(t2b, t(g), t(s1), t(s2), t(bias), from_t2=True)
         ref2 = F.layer_forward_raw(t2b.float(), t(g), t(s1), t(s2), t(bias), from_t2=True)
         assert torch.equal(y2, ref2.to(torch.bfloat16))
+
+
+def test_shared_input_transform_is_hoisted_in_the_autograd_path():
+    """First layer of a network (one (B, D) input block for all samples): above HOIST_MIN_ELEMENTS the autograd function
+    computes t2 = H(s2 x) once (whvi_fwht_scaled_f32) and runs the forward from it; same outputs and gradients as the
+    plain kernels."""
+    from whvi_b200 import functional as F
+    S, B, D = 4, 1024, 4096
+    assert S * B * D >= F.HOIST_MIN_ELEMENTS
+    gen = torch.Generator(device=dev()).manual_seed(3)
+    x = torch.randn(B, D, device=dev(), generator=gen, requires_grad=True)
+    g = torch.randn(S, D, device=dev(), generator=gen, requires_grad=True)
+    s1 = torch.randn(D, device=dev(), generator=gen, requires_grad=True)
+    s2 = torch.randn(D, device=dev(), generator=gen, requires_grad=True)
+    bias = torch.randn(D, device=dev(), generator=gen)
+    dy = torch.randn(S, B, D, device=dev(), generator=gen)
+    before = dict(F.LAUNCH_COUNTS)
+    y = F.whvi_layer(x, g, s1, s2, bias, relu_out=True)
+    assert F.LAUNCH_COUNTS.get("whvi_fwht_scaled_f32", 0) == before.get("whvi_fwht_scaled_f32", 0) + 1
+    y_ref = F.layer_forward_raw(x.detach(), g.detach(), s1.detach(), s2.detach(), bias, relu_out=True)
+    assert rel_err(y.detach().cpu().numpy(), y_ref.cpu().numpy()) < 1e-5
+    (y * dy).sum().backward()
+    # a folded ReLU's mask is the CONSUMER's job (relu_in), so the function's backward sees dy as it is
+    dx, dg, ds1, ds2, _ = F.layer_backward_raw(x.detach(), dy, g.detach(), s1.detach(), s2.detach(), want_dx=True)
+    assert rel_err(x.grad.cpu().numpy(), dx.sum(0).cpu().numpy()) < TOL
+    assert rel_err(g.grad.cpu().numpy(), dg.cpu().numpy()) < TOL
+    assert rel_err(s1.grad.cpu().numpy(), ds1.cpu().numpy()) < TOL
+    assert rel_err(s2.grad.cpu().numpy(), ds2.cpu().numpy()) < TOL
