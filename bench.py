@@ -330,8 +330,17 @@ def run_ours(args):
 
     # ---- warm-up, then the device-resident timed region -----------------------------------
     torch.manual_seed(100 + rank)  # timed steps: each rank draws its own eps shard
+    import time
     for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
+    # host time to ENQUEUE a step (empty launch queue at the start, no synchronisation inside: the GPU runs behind): the step
+    # is GPU-bound while this stays below ms_per_step; at N = 8 the per-rank GPU work is 1/8, the host work per sample chunk is not
+    torch.cuda.synchronize()
+    t_host = time.perf_counter()
+    step(x_dev, y_dev)
+    step(x_dev, y_dev)
+    host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / 2
+    torch.cuda.synchronize()
     WF.LAUNCH_COUNTS.clear()
     timed_calls = ("whvi_layer_bwd_fused_f32", "whvi_layer_bwd_scaled_f32", "whvi_layer_fwd_fused_f32", "whvi_layer_loss_f32")
     WF.EVENT_SINK = {k: [] for k in timed_calls}
@@ -476,7 +485,7 @@ def run_ours(args):
                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                        "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
                        "last_loss": e2e_losses[-1]},
-               "check": check, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+               "check": check, "host_enqueue_ms_per_step": host_enqueue_ms, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                "fwht": {"elements_per_gpu": n, "unit": "GB/s", "n_gpus": world, "scaling": "weak (rows sharded, no collective)",
                         "sweep": fw, "bf16_io_sweep": fw16, "cpu_baseline": cpu_f, "ref_cuda_baseline": gpu_f},
                "eval": ev, "clocks": clk.summary()}

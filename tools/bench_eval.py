@@ -1,21 +1,28 @@
 """BASELINE config 5 on 1..8 GPUs: MC predictive mean/variance of WHVILinear(32768, 32768) over synthetic inputs,
 256 MC samples, sharded over the ranks in two dimensions ("sharding MC samples and minibatch rows"):
     rank = (sample group a, row group b),  sample groups G_s = min(2, N),  row groups G_r = N / G_s
-Per input chunk a rank runs ONE launch of the fused moments kernel (whvi_layer_moments_f32: the forward over its S / G_s
-samples for its rows with sum y / sum y^2 kept in tensor memory -- no prediction ever reaches HBM); the partial sums are
-then reduce-scattered INSIDE the sample-group pair that shares those rows (NCCL, side stream, overlapping the next
-chunk), so each rank finishes mean/variance for rows / G_s of its inputs.  Why not samples over all N ranks: the
-exchange is 8*D bytes per input per rank whatever N is (256 KB at D = 2^15), so with 256/8 = 32 samples per rank it
-would be a quarter of the compute time and an 8-way collective; with two sample groups it is 1/8 of that and pairwise.
-The moments kernel takes whole SMs (all registers), so it leaves a few SMs free for the collective's CTAs
-(WHVI_LAYER_RESERVE_SMS), otherwise the exchange could only start when the next chunk's kernel has finished.
-The noise is ONE (S, D) draw for all inputs, as in the reference's eval_model (src/networks.py:101-115: one forward
-pass of S samples over the whole test batch).
+Per input chunk a rank computes t2 = H(s2 x) for its row group in one pass (whvi_fwht_scaled_f32) and runs the fused moments
+kernel (whvi_layer_moments_f32: the forward over its S / G_s samples with sum y / sum y^2 kept in tensor memory -- no
+prediction ever reaches HBM).  The two ranks of a sample-group pair share their rows and each FINISHES half of them:
 
-Inputs are a fixed function of the global row index and the noise comes from a fixed seed, so the printed checksum must
-agree for N = 1, 2, 4, 8 (up to fp32 summation order).
+  --exchange peer (default): no collective kernel.  A rank first runs the rows its PARTNER finishes, with the kernel's output
+      pointers aimed at the partner's staging buffer (symmetric memory, NVLink-mapped): the partial sums travel as the
+      kernel's own stores.  After one signal-pad barrier it runs its own rows starting from what the partner stored
+      (whvi_layer_moments_add_f32) and the sums land in the result.  No SM is set aside, the sums make no second trip
+      through HBM.  Three staging slots keep the partner's next store off the slot being read.
+  --exchange nccl: reduce-scatter of the partial sums on a side stream, next to a kernel that leaves a few SMs free for it
+      (WHVI_LAYER_RESERVE_SMS; the pair communicator is capped at as many CTAs).  With so few channels the reduce-scatter
+      itself becomes the limit at 8 GPUs (6.66x against 7.72x for the peer exchange).
 
-    python tools/bench_eval.py [--inputs 172864]
+Why not samples over all N ranks: the exchange is 8*D bytes per input per rank whatever N is (256 KB at D = 2^15), so with
+256/8 = 32 samples per rank it would be a quarter of the compute time; with two sample groups it is 1/8 of that and pairwise.
+The noise is ONE (S, D) draw for all inputs, as in the reference's eval_model (src/networks.py:101-115: one forward pass of S
+samples over the whole test batch).  The inputs are resident in HBM before the timed region (a fixed function of the global
+row index) and the product is (sum_s y, sum_s y^2) for every input -- what WHVINetwork.predictive_sums returns; the checksum
+(mean |predictive mean|, mean predictive variance) is taken after the timed region and must agree for N = 1, 2, 4, 8 up to
+fp32 summation order.
+
+    python tools/bench_eval.py [--inputs 170496] [--exchange peer|nccl]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_eval.py
 
 Also imported by bench.py (`run_eval`), which puts the result under the `eval` key of its JSON line.
@@ -92,8 +99,8 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2,
     # it takes twice the rows per chunk to keep the launches as long as at N = 1
     rows_mine = (tiles or 4 * g_s) * (148 - reserve)
     cb = rows_mine * g_r                                  # inputs per chunk over all row groups
-    # default: 172864 inputs = a whole number of chunks for N = 1 (592 rows), 2 (1168), 4 (2336) and 8 (4672 rows per chunk):
-    # every N evaluates the same input set (strong scaling; same checksum)
+    # default: 170496 inputs = a whole number of chunks for N = 1 (592 rows), 2 (1184), 4 (2368) and 8 (4736 rows per chunk) --
+    # 172864 for the nccl exchange, whose kernels leave SMs free: every N evaluates the same input set (strong scaling)
     n_chunks = max(1, (inputs or (170496 if reserve == 0 else 172864)) // cb)
     lo, hi = a_idx * (S // g_s), (a_idx + 1) * (S // g_s)
     torch.manual_seed(0)                                   # replicated parameters
