@@ -87,12 +87,19 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2,
     #           the kernel's own stores), then its own rows starting from what the partner stored (whvi_layer_moments_add_f32);
     #           one signal-pad barrier per chunk orders the two; no SMs are set aside
     #   "nccl": reduce-scatter on a side stream next to a kernel that leaves a few SMs free for it
-    peer = None
+    peer = stage = handle = peer_stage = None
     if g_s > 1 and exchange == "peer":
-        try:
+        try:   # symmetric staging buffer: 3 slots x (sum y, sum y^2) x the rows this rank finishes per chunk
             import torch.distributed._symmetric_memory as symm_mem
+            shape = (3, 2, (tiles or 4 * g_s) * 148 // g_s, D)
+            stage = symm_mem.empty(shape, dtype=torch.float32, device=dev)
+            handle = symm_mem.rendezvous(stage, group)
+            peer_stage = handle.get_buffer(1 - a_idx, shape, torch.float32)
+            handle.barrier()
             peer = symm_mem
-        except Exception:
+        except Exception as exc:   # no symmetric memory on this box (the same on every rank): the NCCL exchange
+            if rank == 0:
+                print(f"[bench_eval] peer exchange unavailable ({type(exc).__name__}: {exc}); using --exchange nccl", file=sys.stderr)
             peer = None
     reserve = _CAP[0] if (g_s > 1 and peer is None) else 0
     # 4 * G_s tiles per CTA of the persistent grid per chunk: a rank of a sample-group pair runs half the samples per row, so
@@ -116,11 +123,7 @@ def run_eval(dev, rank, world, inputs=0, log2d=15, samples=256, warmup_chunks=2,
     # fused kernel (N = 1) or the pair's reduce-scatter (N >= 2) writes straight into it, nothing else touches the sums
     result = torch.empty(total_chunks, 2, n_fin, D, device=dev)
     buckets = [torch.empty(2, rows_mine, D, device=dev) for _ in range(2)] if (g_s > 1 and peer is None) else None   # nccl: partial sums
-    if peer is not None:
-        stage = peer.empty((3, 2, n_fin, D), dtype=torch.float32, device=dev)     # what the partner's kernels store into
-        handle = peer.rendezvous(stage, group)
-        peer_stage = handle.get_buffer(1 - a_idx, (3, 2, n_fin, D), torch.float32)
-        handle.barrier()
+    assert peer is None or tuple(stage.shape) == (3, 2, n_fin, D)
     t2buf = [torch.empty(rows_mine, D, device=dev) for _ in range(2)]
     comm = torch.cuda.Stream(device=dev)
     # the inputs of this rank's row group, resident in HBM before the timed region starts (bench contract: `value` is
