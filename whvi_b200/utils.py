@@ -38,6 +38,16 @@ def build_H(D, device):
 kl_gaussian = WF.kl_gaussian
 
 
+class Cosine(torch.nn.Module):
+    """cos(x) as a module: the interface of the reference's one custom activation (``src/activations.py:5-13``).  None of the
+    reference's experiments uses it (``src/evaluation.py:37`` builds ReLU networks), so unlike ``nn.ReLU`` -- which
+    ``WHVINetwork`` folds into the layer kernels -- it stays an ordinary elementwise op; inside a ``WHVINetwork`` it sees the
+    MC samples folded into the batch like any foreign module."""
+
+    def forward(self, x):
+        return x.cos()
+
+
 _PEER_SLOTS: dict = {}   # (device, group id, shapes) -> symmetric double buffers (allocating + rendezvous is collective and slow: once)
 
 
