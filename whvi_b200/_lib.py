@@ -1,4 +1,6 @@
-"""ctypes binding of libwhvi_b200.so (C ABI declared in include/whvi_b200.h).
+"""Binding of libwhvi_b200.so (C ABI declared in include/whvi_b200.h): ctypes loads the library and declares every
+signature; the launch calls whose parameters are all pointers / integers are then handed out behind a small CPython shim
+(csrc_host/fastcall.c) that calls the same function without ctypes' per-call marshalling.
 
 There is no fallback of any kind: if the library is missing or a call fails, a
 RuntimeError is raised (mirroring the TORCH_CHECK -> RuntimeError behaviour of the
