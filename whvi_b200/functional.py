@@ -470,7 +470,7 @@ class WHVILayerFunction(Function):
 
     @staticmethod
     def forward(ctx, x, g, s1, s2, bias, relu_out=False, relu_in=False, dy_scale_from=None):
-        if x.dim() == 2 and g.size(0) >= 4 and g.size(0) * x.numel() >= HOIST_MIN_ELEMENTS:
+        if x.dim() == 2 and g.size(0) >= 4 and g.size(-1) >= 128 and g.size(0) * x.numel() >= HOIST_MIN_ELEMENTS:
             # one (B, D) input block for all samples (the first layer of a network): the first transform does not depend
             # on the sample, so it is done once -- t2 = H(s2 * x), one pass over B * D elements -- and every
             # (sample, row) pair costs one transform; the output stream is the same, the kernel 12% shorter (D = 4096)
@@ -498,7 +498,8 @@ class WHVILayerFunction(Function):
 
 
 MIN_LAYER_D = 4  # narrowest row the layer kernels take (one float4)
-HOIST_MIN_ELEMENTS = 1 << 24   # S * B * D from which hoisting the shared-input transform pays for its extra launch
+HOIST_MIN_ELEMENTS = 1 << 24   # S * B * D from which hoisting the shared-input transform pays for its extra launch (measured
+                               # for D = 1024, 4096, 8192; not applied below D = 128)
 
 
 def whvi_layer(x, g, s1, s2, bias=None, relu_out=False, relu_in=False, dy_scale_from=None):
