@@ -29,12 +29,23 @@ fwht_kernel(const IO* __restrict__ in, IO* __restrict__ out, int64_t total, cons
     extern __shared__ float4 smem4[];
     const int group = threadIdx.x / T;
     const uint32_t tid = threadIdx.x % T;
-    const int64_t base = (int64_t(blockIdx.x) * GROUPS + group) * TILE;
-    if (base >= total) return;  // whole group leaves together; barriers are per group
+    // N == 15: a 128 KB transposition buffer leaves one CTA per SM, so nothing overlaps a tile's load latency with another
+    // tile's work; there the grid is persistent (one CTA per SM looping over tiles) and the next tile is pulled into L2
+    // while the current one is transformed.  Smaller tiles have several CTAs per SM: one tile per group, no loop.
+    constexpr bool PERSIST = (N >= 15) && GROUPS == 1;
     float* buf = reinterpret_cast<float*>(smem4) + size_t(group) * (kOneRound ? 0 : scratch_words(N, C));
-
-    float v[E];
     const uint32_t toff = tile_thread_offset<N, C, V_FIRST>(tid);
+    const int64_t step = PERSIST ? int64_t(gridDim.x) * GROUPS * TILE : total;
+#pragma unroll 1
+    for (int64_t base = (int64_t(blockIdx.x) * GROUPS + group) * TILE; base < total; base += step) {
+    if constexpr (PERSIST) {
+        if (tid == 0 && base + step < total) {
+            const int64_t left1 = total - (base + step);
+            l2_prefetch_bulk(in + base + step, static_cast<uint32_t>((left1 < TILE ? left1 : TILE) * sizeof(IO)));
+        }
+        if (base != (int64_t(blockIdx.x) * GROUPS + group) * TILE) group_sync<T, GROUPS>(group);   // the previous tile's reads of buf are done
+    }
+    float v[E];
     static_for<0, E / 4>([&](auto m_) {
         constexpr int m = decltype(m_)::value;
         constexpr uint32_t roff = tile_reg_offset<N, C, V_FIRST>(m);
@@ -79,6 +90,7 @@ fwht_kernel(const IO* __restrict__ in, IO* __restrict__ out, int64_t total, cons
             if (g < total) Io<IO>::st4(out + g, make_float4(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]));
         });
     }
+    }   // tile loop
 }
 
 // D = 1 (identity) and D = 2: too narrow for a float4; one thread per row.
@@ -156,7 +168,8 @@ static int launch_cfg(const IO* in, IO* out, int64_t total, cudaStream_t stream,
     auto kernel = fwht_kernel<N, C, K, GROUPS, IO, SCALED>;
     if (int rc = ensure_smem(kernel, smem, smem_ok)) return rc;
     const int64_t tiles = (total + (int64_t(1) << N) - 1) >> N;
-    const int64_t ctas = (tiles + GROUPS - 1) / GROUPS;
+    int64_t ctas = (tiles + GROUPS - 1) / GROUPS;
+    if (N >= 15 && GROUPS == 1 && ctas > 148) ctas = 148;   // persistent: one CTA per SM (see the kernel)
     if (ctas > 0x7fffffffLL) return fail(WHVI_E_SHAPE, "fwht: %lld tiles exceed the grid limit", (long long)ctas);
     kernel<<<static_cast<unsigned>(ctas), threads, smem, stream>>>(in, out, total, scale);
     return check_launch("fwht_kernel");
