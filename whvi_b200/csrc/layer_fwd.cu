@@ -276,7 +276,7 @@ int launch_layer_fwd(const LayerFwdCall& c, int64_t D, cudaStream_t stream)
     if (k == 13) return launch_fwd_cfg<13, 6, 13, 1, 3, 1, 4>(c, k, stream);
     // D = 16384, 32768 (forward only: MC predictive evaluation, BASELINE config 5): three views,
     // 64 floats per thread, one in-place transposition buffer (64 / 128 KB)
-    if (k == 14) return launch_fwd_cfg<14, 6, 14, 1, 3, 1, 1>(c, k, stream);
+    if (k == 14) return launch_fwd_cfg<14, 6, 14, 1, 3, 1, 2>(c, k, stream);   // two 64 KB CTAs per SM: 128 registers per thread (one CTA at 218 registers ran at 35% of the roofline)
     if (k == 15) return launch_fwd_cfg<15, 6, 15, 1, 3, 1, 1>(c, k, stream);
     return fail(WHVI_E_SHAPE, "layer_fwd: D = %lld unsupported (4 <= D <= 32768)", (long long)D);
 }
