@@ -329,6 +329,39 @@ def test_empty_batch(n_in, n_out):
             assert float(p.grad.abs().sum()) == 0.0, name
 
 
+def test_column_layers_in_a_fused_network():
+    """[Column 1 -> 64 (produces a folded ReLU), Square 64, Column 64 -> 1 (consumes one)]: the fused network against every
+    module run on its own."""
+    import copy
+    torch.manual_seed(9)
+    S, B = 3, 21
+    fused = W.WHVIRegression([W.WHVILinear(1, 64, lambda_=3.0, bias=True), torch.nn.ReLU(), W.WHVILinear(64, 64, lambda_=3.0),
+                              torch.nn.ReLU(), W.WHVILinear(64, 1, lambda_=3.0, bias=True)], train_samples=S).to(dev()).train()
+    with torch.no_grad():
+        for name, p in fused.named_parameters():
+            if name.endswith(("s1", "s2", "g_mu")):
+                p.normal_()
+    plain = copy.deepcopy(fused)
+    plain.fuse = False
+    for m in plain._whvi_layers():
+        if isinstance(m.weight_submodule, W.WHVIColumnMatrix):
+            m.weight_submodule.one_launch = False
+    x, y = torch.randn(B, 1, device=dev()), torch.randn(B, 1, device=dev())
+    eps = [torch.randn(S, b.D, device=dev()) for layer in fused._whvi_layers() for b in layer.square_blocks()]
+    out = []
+    for model in (fused, plain):
+        for b, e in zip([b for layer in model._whvi_layers() for b in layer.square_blocks()], eps):
+            b.inject_eps(e)
+        loss = model.loss(x, y, n=500)
+        loss.backward()
+        out.append((loss.item(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    assert abs(out[0][0] - out[1][0]) < 1e-5 * abs(out[1][0])
+    assert out[0][1].keys() == out[1][1].keys()
+    scale = max(float(v.abs().max()) for v in out[1][1].values())
+    for n, v in out[1][1].items():
+        assert float((out[0][1][n] - v).abs().max()) < TOL * scale, n
+
+
 def test_stacked_network_fused_equals_unfused():
     """BASELINE config 3's shape (13 -> 128 -> 128 -> 1 with ReLUs): the grouped Stacked launch with the ReLU folded into it
     and into the consumer's backward gives the same loss and gradients as every module run on its own."""
